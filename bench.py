@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the per-cell chrM pileup hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA, C-ABI)
+    python bench.py --impl reference [...]                       CPU arm (oracle port, all host threads)
+
+A step is one pass of stages 1-6 over one batch of synthetic records. At N=1 the workload is
+BASELINE.json configs[1] (2 000 cells x 20 M records, 2x50 bp, default `run` filters); at N>1 every
+rank owns a barcode shard of that same size (weak scaling, no data-path collective). `value` is records/s
+with inputs resident in HBM (CUDA events, max over ranks); `e2e` is the same metric through
+`mgatk_pileup_host` with pinned HOST buffers (H2D + kernels + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "dedup chrM reads/sec counted"
+UNIT = "reads/s"
+CONFIG_INDEX = 1
+BASE_SEED = 20261018
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=2000)
+    ap.add_argument("--records", type=int, default=20_000_000)
+    ap.add_argument("--profile", default="atac50")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="check per-cell QC rows against the oracle at full size")
+    return ap.parse_args()
+
+
+def config_dict(a, n_gpus):
+    return {"workload": f"synthetic 10x-ATAC chrM, BASELINE configs[{CONFIG_INDEX}]: {a.cells} cells x {a.records} "
+                        f"records per GPU, profile {a.profile}, default run filters (q20 mapq30 d5 bias1.0, "
+                        f"alignment_and_fragment_length dedup)",
+            "cells_per_gpu": a.cells, "records_per_gpu": a.records, "profile": a.profile,
+            "sharding": f"by barcode, {n_gpus} shard(s), no data-path collective",
+            "l2": "inputs per step (>2 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+def algorithmic_bytes(batch, n_cells, P=16569):
+    """each input byte read once, each output byte written once.
+    per record 15 + 4*n_cigar + ceil(L/2) + L; per (cell, position) 11 planes x 2 B; 32 B QC row per cell."""
+    per_rec = 15 * batch.n_records + int((4 * batch.n_cigar.astype(np.int64) + (batch.l_seq.astype(np.int64) + 1) // 2
+                                           + batch.l_seq).sum())
+    return per_rec + n_cells * P * 22 + n_cells * 32
+
+
+def default_params(n_cells, extent):
+    from mgatk2_b200._lib import ParamsC
+    return ParamsC(20, 30, 5, 0, 1.0, 1, 16569, n_cells, extent)
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_sample(a):
+    """Bounded sample with the per-cell shape of the workload (same reads/cell)."""
+    from mgatk2_b200.synth import synth_batch
+    cells = max(1, min(a.cells, 200))
+    recs = max(1000, int(a.records * cells / a.cells))
+    return synth_batch(cells, recs, a.profile, seed=BASE_SEED + CONFIG_INDEX + 99), cells, recs
+
+
+def time_oracle(batch, cells, threads, steps, warmup):
+    from oracle.oracle import make_params, run_oracle
+    p = make_params(cells, max_read_extent=batch.max_read_extent())
+    for _ in range(warmup):
+        run_oracle(batch, p, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run_oracle(batch, p, n_threads=threads)
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch, cells, recs = cpu_sample(a)
+    dt = time_oracle(batch, cells, threads, a.steps, a.warmup)
+    v = recs / dt
+    sample = (f"{cells} cells x {recs} records per step (same reads/cell as the workload), C port of the reference's "
+              f"Python path (oracle/mgatk2_oracle.c), {threads} threads over cells, serial read/dedup loop as in the reference")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic", "config": config_dict(a, a.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.p:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower() == "active":
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        os.unlink(self.f.name)
+        return out
+
+
+# --------------------------------------------------------------------------- our arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the pileup path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from mgatk2_b200.build import build_extension
+    if rank == 0:
+        build_extension()
+    if world > 1:
+        dist.barrier()
+    from mgatk2_b200.engine import PileupEngine
+    from mgatk2_b200.synth import synth_batch
+
+    t_gen = time.perf_counter()
+    batch = synth_batch(a.cells, a.records, a.profile, seed=BASE_SEED + CONFIG_INDEX + 1000 * rank)
+    t_gen = time.perf_counter() - t_gen
+    extent = batch.max_read_extent()
+    params = default_params(a.cells, extent)
+    eng = PileupEngine(local)
+
+    # pinned host staging (e2e) and device-resident copy (value)
+    from mgatk2_b200.batch import FIELDS, ReadBatch
+    pinned = {}
+    for name, _ in FIELDS:
+        src = torch.from_numpy(getattr(batch, name))
+        pinned[name] = torch.empty_like(src, pin_memory=True).copy_(src)
+    pbatch = ReadBatch(**{name: pinned[name].numpy() for name, _ in FIELDS})
+    dbatch = eng.upload(pbatch, pinned_src=pinned)
+    dout = eng.alloc_device_outputs(a.cells, 16569, batch.n_records)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then K timed steps with inputs resident in HBM ----
+    for _ in range(max(a.warmup, 3)):
+        eng.run_device(dbatch, params, dout)
+    barrier()
+    clocks = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        eng.run_device(dbatch, params, dout)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.launch_count() * a.steps
+    # per-stage device times (events inside the library, same stream), averaged over K more steps
+    stage_acc = {}
+    for _ in range(a.steps):
+        eng.run_device(dbatch, params, dout)
+        torch.cuda.synchronize()
+        for k, v in eng.stage_times().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / a.steps
+    clock_info = clocks.stop()
+    res = eng.download(dout, params)           # also checks the device error bits
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / a.steps
+    total_records = a.records * world
+    value = total_records / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers through mgatk_pileup_host ----
+    hout = eng.alloc_host_outputs(a.cells, 16569)
+    eng.run_host(pbatch, params, out=hout)      # warm-up: device buffers get allocated here
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        r_e2e = eng.run_host(pbatch, params, out=hout)
+    torch.cuda.synchronize()
+    dt = torch.tensor([(time.perf_counter() - t0) / a.e2e_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = total_records / float(dt.item())
+    h2d = pbatch.nbytes()
+    d2h = int(hout["planes"].nbytes + hout["cell_qc"].nbytes + hout["stats"].nbytes + hout["base_totals"].nbytes)
+    assert r_e2e.stats["filtered_reads"] == res.stats["filtered_reads"]
+
+    if a.verify:
+        from oracle.oracle import make_params, run_oracle
+        ora = run_oracle(batch, make_params(a.cells, max_read_extent=extent), n_threads=os.cpu_count() or 1, dense=False)
+        for f in ("n_reads", "n_paired", "sum_depth", "covered", "max_depth", "median_lo", "median_hi"):
+            np.testing.assert_array_equal(res.cell_qc[f], ora.cell_qc[f])
+        np.testing.assert_array_equal(res.base_totals, ora.base_totals)
+        assert all(res.stats[k] == ora.stats[k] for k in ("filtered_reads", "dup_with_length", "dup_position_only"))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    bytes_alg = algorithmic_bytes(batch, a.cells)
+    dom = max(stage_acc, key=stage_acc.get) if stage_acc else "pileup"
+    dom_ms = stage_acc.get(dom, ms_step)
+    achieved = bytes_alg / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": f"k_{dom}" if dom == "pileup" else dom, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_alg, "kernel_ms": dom_ms,
+                "whole_step": {"achieved": bytes_alg / (ms_step * 1e-3) / 1e9, "frac": bytes_alg / (ms_step * 1e-3) / 1e9 / peak},
+                "stage_ms": stage_acc}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        sb, sc, sr = cpu_sample(a)
+        threads = os.cpu_count() or 1
+        dtc = time_oracle(sb, sc, threads, 3, 1)
+        cpu = {"value": sr / dtc, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{sc} cells x {sr} records (same reads/cell), oracle/mgatk2_oracle.c, mean of 3 runs; the "
+                         f"reference's own Python path measured 2.2 k reads/s on 1 core (BASELINE.md §2)"}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic", "config": config_dict(a, world), "clocks": clock_info,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "counted": {"total_reads": res.stats["total_reads"], "filtered_reads": res.stats["filtered_reads"],
+                    "dup_with_length": res.stats["dup_with_length"], "sum_depth": int(res.cell_qc["sum_depth"].sum())},
+        "synth_seconds": t_gen,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

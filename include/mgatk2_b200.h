@@ -169,8 +169,8 @@ const char *mgatk_last_error(const mgatk_handle *h);
 int64_t     mgatk_workspace_bytes(int64_t n_records, int32_t n_cells);
 
 /* Stages 1-6 on device-resident buffers; enqueues on `stream`, never blocks.
- * After the stream has drained, mgatk_check_device_status() turns
- * stats->error_bits (host copy) into a status code. */
+ * After the stream has drained, mgatk_check_stats turns a host copy of
+ * stats (its error_bits) into a status code. */
 int mgatk_pileup_device(mgatk_handle *h, const mgatk_params *params,
                         const mgatk_batch *batch_dev, const mgatk_outputs *out_dev,
                         void *workspace_dev, int64_t workspace_bytes, void *stream);

@@ -1,0 +1,37 @@
+"""Build the CUDA library in-tree: nvcc, sm_100a only, -lineinfo (so ncu source pages map back)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmgatk2_b200.so")
+SOURCES = ("api.cu",)
+DEPS = ("api.cu", "kernels.cuh", os.path.join("..", "..", "include", "mgatk2_b200.h"))
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
+
+
+def nvcc_path() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libmgatk2_b200.so")
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build_extension(force: bool = False, verbose: bool = False) -> str:
+    if force or is_stale():
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB, *SOURCES]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.run(cmd, cwd=CSRC, check=True)
+    return LIB

@@ -1,0 +1,420 @@
+// mgatk2_b200 — C-ABI host side (include/mgatk2_b200.h). Launch sequencing, workspace carving,
+// host-buffer entry point. No torch types; everything here is plain CUDA runtime.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace mgatk;
+
+namespace {
+
+constexpr int kMaxChunks = 148 * 3 * kWarpsPerCta;   // one wave of partition warps at 3 CTAs/SM
+constexpr int kMaxDigitBits = 11;                    // 2048 bins * 4 B * 8 warps = 64 KB of shared memory per CTA
+constexpr int kMaxStages = 16;
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct Layout {          // carve-up of the caller's workspace
+    int64_t n; int32_t n_cells;
+    int nchunks; int64_t chunk; int ngroups;
+    int passes, bits[2], shift[2];
+    int unit_reads; int64_t max_units;
+    size_t g[2][6];      // grouped arrays (two generations)
+    size_t gflags, mat, part, cell_start, unit_start, units, scalars, total;
+};
+
+int unit_reads_setting() {
+    const char *e = getenv("MGATK_UNIT_READS");
+    int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 768;
+}
+
+bool make_layout(int64_t n, int32_t n_cells, Layout &L) {
+    if (n < 0 || n_cells < 0 || n >= (int64_t)0x7fffff00) return false;
+    L.n = n; L.n_cells = n_cells;
+    int64_t nch = (n + 1023) / 1024;
+    L.nchunks = (int)(nch < 1 ? 1 : nch > kMaxChunks ? kMaxChunks : nch);
+    L.chunk = ((n + L.nchunks - 1) / L.nchunks + 31) / 32 * 32;
+    if (L.chunk < 32) L.chunk = 32;
+    L.ngroups = (L.nchunks + kScanGroup - 1) / kScanGroup;
+    int bits = 1;
+    while ((1ll << bits) < n_cells) bits++;
+    if (bits > 2 * kMaxDigitBits) return false;
+    L.passes = bits <= kMaxDigitBits ? 1 : 2;
+    if (L.passes == 1) { L.bits[0] = bits; L.shift[0] = 0; L.bits[1] = 0; L.shift[1] = 0; }
+    else { L.bits[0] = (bits + 1) / 2; L.shift[0] = 0; L.bits[1] = bits - L.bits[0]; L.shift[1] = L.bits[0]; }
+    L.unit_reads = unit_reads_setting();
+    L.max_units = (int64_t)n_cells + n / L.unit_reads + 1;
+    const int max_bins = 1 << (L.bits[0] > L.bits[1] ? L.bits[0] : L.bits[1]);
+    size_t o = 0;
+    const size_t cap = (size_t)(n > 0 ? n : 1);
+    const size_t elt[6] = {4, 4, 4, 4, 4, 2};
+    for (int gen = 0; gen < 2; gen++)
+        for (int k = 0; k < 6; k++) { L.g[gen][k] = o; if (gen < L.passes) o += align_up(cap * elt[k]); }
+    L.gflags = o; o += align_up(cap);
+    L.mat = o; o += align_up((size_t)L.nchunks * max_bins * 4);
+    L.part = o; o += align_up((size_t)L.ngroups * max_bins * 4);
+    L.cell_start = o; o += align_up(((size_t)n_cells + 1) * 4);
+    L.unit_start = o; o += align_up(((size_t)n_cells + 1) * 4);
+    L.units = o; o += align_up((size_t)L.max_units * sizeof(Unit));
+    L.scalars = o; o += 256;
+    L.total = o;
+    return true;
+}
+
+Grouped grouped_at(char *ws, const Layout &L, int gen) {
+    Grouped g;
+    g.cell = (int32_t *)(ws + L.g[gen][0]); g.pos = (int32_t *)(ws + L.g[gen][1]);
+    g.tlen = (u32 *)(ws + L.g[gen][2]); g.off = (u32 *)(ws + L.g[gen][3]);
+    g.len = (u32 *)(ws + L.g[gen][4]); g.mq = (uint16_t *)(ws + L.g[gen][5]);
+    return g;
+}
+
+struct DevBuf { void *p = nullptr; size_t cap = 0; };
+
+}  // namespace
+
+struct mgatk_handle {
+    int device = 0;
+    int sm_count = 148;
+    std::string err;
+    int64_t launches = 0;
+    // stage timing
+    cudaEvent_t ev[kMaxStages + 1] = {};
+    const char *stage_names[kMaxStages] = {};
+    int n_stages = 0;
+    bool events_ready = false;
+    // device buffers of the host entry point
+    DevBuf in[9], planes, qc, stats, totals, ovf, ws;
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+int fail(mgatk_handle *h, int code, const std::string &msg) { if (h) h->err = msg; return code; }
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, MGATK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+__global__ void k_init(mgatk_stats *stats, int64_t n_records, int32_t *work_counter) {
+    stats->total_reads = (uint64_t)n_records;            // readers.py:93 counts every fetched record
+    stats->stage1_reads = 0; stats->filtered_reads = 0; stats->dup_with_length = 0;
+    stats->dup_position_only = 0; stats->n_empty_seq = 0; stats->n_overflow = 0; stats->error_bits = 0;
+    *work_counter = 0;
+}
+__global__ void k_publish_m(mgatk_stats *stats, const int64_t *m) { stats->stage1_reads = (uint64_t)*m; }
+
+void mark(mgatk_handle *h, cudaStream_t s, const char *name) {
+    if (h->n_stages < kMaxStages) {
+        h->stage_names[h->n_stages] = name;
+        cudaEventRecord(h->ev[h->n_stages + 1], s);
+        h->n_stages++;
+    }
+}
+
+template <class Src>
+int partition_pass(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout &L, int pass, char *ws,
+                   const int32_t *sorted_pos, u64 *error_bits, int64_t *m_out, const Grouped &dst) {
+    const int bins = 1 << L.bits[pass];
+    u32 *mat = (u32 *)(ws + L.mat), *part = (u32 *)(ws + L.part);
+    const int grid = (L.nchunks + kWarpsPerCta - 1) / kWarpsPerCta;
+    const size_t smem = (size_t)kWarpsPerCta * bins * 4;
+    CU(cudaFuncSetAttribute(k_hist<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_scatter<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_hist<Src><<<grid, kThreads, smem, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, sorted_pos, error_bits);
+    dim3 sg((bins + 255) / 256, L.ngroups);
+    k_scan_group_sums<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part);
+    k_scan_bases<<<1, 1024, 0, s>>>(part, L.ngroups, bins, m_out);
+    k_scan_apply<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part);
+    k_scatter<Src><<<grid, kThreads, smem, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, dst);
+    h->launches += 5;
+    CU(cudaGetLastError());
+    return MGATK_OK;
+}
+
+template <int R>
+int launch_pileup(mgatk_handle *h, cudaStream_t s, const PileupArgs &a) {
+    int warps = kWarpsPerCta;
+    while (warps > 1 && (size_t)warps * 10 * R * 4 > 200 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * 10 * R * 4;
+    CU(cudaFuncSetAttribute(k_pileup<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup<R>, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    k_pileup<R><<<h->sm_count * per_sm, warps * 32, smem, s>>>(a);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return MGATK_OK;
+}
+
+int validate(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, const mgatk_outputs *o) {
+    if (!h || !p || !b || !o) return fail(h, MGATK_ERR_BAD_ARG, "null argument");
+    if (b->n_records < 0 || p->n_cells < 0 || p->mito_length <= 0 || b->blob_bytes < 0 || o->overflow_capacity < 0)
+        return fail(h, MGATK_ERR_BAD_ARG, "negative size");
+    if (p->dedup_mode < 0 || p->dedup_mode > 2) return fail(h, MGATK_ERR_BAD_ARG, "dedup_mode must be 0, 1 or 2");
+    if (p->mito_length >= (1 << 24)) return fail(h, MGATK_ERR_RANGE, "mito_length must be below 2^24");
+    if (b->n_records >= (int64_t)0x7fffff00) return fail(h, MGATK_ERR_RANGE, "at most 2^31-257 records per batch");
+    if (b->n_records > 0 && (!b->pos || !b->tlen || !b->flag || !b->mapq || !b->bc_idx || !b->l_seq || !b->n_cigar || !b->blob_off))
+        return fail(h, MGATK_ERR_BAD_ARG, "null batch array");
+    if (b->blob_bytes > 0 && !b->blob) return fail(h, MGATK_ERR_BAD_ARG, "null blob");
+    if (!o->stats || (p->n_cells > 0 && (!o->planes || !o->cell_qc)) || !o->base_totals)
+        return fail(h, MGATK_ERR_BAD_ARG, "null output array");
+    if (o->overflow_capacity > 0 && !o->overflow) return fail(h, MGATK_ERR_BAD_ARG, "null overflow list");
+    if (p->max_read_extent < 1) return fail(h, MGATK_ERR_BAD_ARG, "max_read_extent must be >= 1");
+    if (p->max_read_extent + 64 > 4096)
+        return fail(h, MGATK_ERR_EXTENT, "max_read_extent above 4032 (long / spliced reads) is not supported");
+    return MGATK_OK;
+}
+
+int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, const mgatk_outputs *o, void *ws_v,
+               int64_t ws_bytes, cudaStream_t s) {
+    int rc = validate(h, p, b, o);
+    if (rc) return rc;
+    Layout L;
+    if (!make_layout(b->n_records, p->n_cells, L)) return fail(h, MGATK_ERR_RANGE, "n_records / n_cells outside limits");
+    if ((int64_t)L.total > ws_bytes || !ws_v) return fail(h, MGATK_ERR_WORKSPACE, "workspace too small");
+    char *ws = (char *)ws_v;
+    CU(cudaSetDevice(h->device));
+    if (!h->events_ready) {
+        for (int i = 0; i <= kMaxStages; i++) CU(cudaEventCreate(&h->ev[i]));
+        h->events_ready = true;
+    }
+    h->launches = 0; h->n_stages = 0;
+    cudaEventRecord(h->ev[0], s);
+
+    const int P = p->mito_length, ppad = (int)MGATK_POS_PAD(P), C = p->n_cells;
+    int64_t *m_ptr = (int64_t *)(ws + L.scalars);
+    int32_t *n_units = (int32_t *)(ws + L.scalars + 8);
+    int32_t *work_counter = (int32_t *)(ws + L.scalars + 16);
+    u64 *error_bits = (u64 *)&o->stats->error_bits;
+
+    k_init<<<1, 1, 0, s>>>(o->stats, b->n_records, work_counter);
+    h->launches++;
+    CU(cudaMemsetAsync(o->base_totals, 0, sizeof(int64_t) * (size_t)P * 4, s));
+    if (C > 0) CU(cudaMemsetAsync(o->cell_qc, 0, sizeof(mgatk_cell_qc) * (size_t)C, s));
+    if (C == 0) { mark(h, s, "init"); return MGATK_OK; }
+
+    // ---- stage 1 + partition by cell ----
+    SrcUser su; su.b = *b; su.n_cells = C;
+    Grouped g0 = grouped_at(ws, L, 0);
+    rc = partition_pass(h, s, su, L, 0, ws, b->pos, error_bits, m_ptr, g0);
+    if (rc) return rc;
+    Grouped g = g0;
+    if (L.passes == 2) {
+        SrcGrouped sg; sg.a = g0; sg.m = m_ptr;
+        Grouped g1 = grouped_at(ws, L, 1);
+        rc = partition_pass(h, s, sg, L, 1, ws, nullptr, error_bits, nullptr, g1);
+        if (rc) return rc;
+        g = g1;
+    }
+    k_publish_m<<<1, 1, 0, s>>>(o->stats, m_ptr);
+    int32_t *cell_start = (int32_t *)(ws + L.cell_start);
+    k_cell_start<<<(C + 1 + 255) / 256, 256, 0, s>>>(g.cell, m_ptr, C, cell_start);
+    h->launches += 2;
+    mark(h, s, "filter+partition");
+
+    // ---- stage 2: dedup ----
+    uint8_t *gflags = (uint8_t *)(ws + L.gflags);
+    if (b->n_records > 0) {
+        k_dedup<<<(unsigned)((b->n_records + 255) / 256), 256, 0, s>>>(g, m_ptr, gflags, p->dedup_mode, p->min_mapq, o->cell_qc, o->stats);
+        h->launches++;
+    }
+    mark(h, s, "dedup");
+
+    // ---- units ----
+    int32_t *unit_start = (int32_t *)(ws + L.unit_start);
+    Unit *units = (Unit *)(ws + L.units);
+    k_plan_scan<<<1, 1024, 0, s>>>(cell_start, o->cell_qc, C, p->min_reads_per_cell, L.unit_reads, ppad, unit_start, n_units);
+    k_plan_units<<<(unsigned)((L.max_units + 255) / 256), 256, 0, s>>>(cell_start, o->cell_qc, g.pos, unit_start, C,
+                                                                      p->min_reads_per_cell, L.unit_reads, ppad,
+                                                                      p->max_read_extent, units);
+    h->launches += 2;
+    mark(h, s, "plan");
+
+    // ---- stages 3-6 ----
+    PileupArgs a;
+    a.gpos = g.pos; a.goff = g.off; a.glen = g.len; a.gflags = gflags; a.blob = b->blob;
+    a.units = units; a.n_units = n_units; a.work_counter = work_counter;
+    a.planes = o->planes; a.qc = o->cell_qc; a.stats = o->stats; a.ovf = o->overflow; a.ovf_cap = o->overflow_capacity;
+    a.P = P; a.ppad = ppad; a.min_baseq = p->min_baseq; a.dist = p->min_distance_from_end;
+    a.max_bias = p->max_strand_bias;
+    a.apply_bias = !(p->max_strand_bias >= 1.0);          // max(f,r)/total never exceeds 1.0
+    const int need = p->max_read_extent + 64;
+    if (need <= 128) rc = launch_pileup<128>(h, s, a);
+    else if (need <= 256) rc = launch_pileup<256>(h, s, a);
+    else if (need <= 512) rc = launch_pileup<512>(h, s, a);
+    else if (need <= 1024) rc = launch_pileup<1024>(h, s, a);
+    else if (need <= 2048) rc = launch_pileup<2048>(h, s, a);
+    else rc = launch_pileup<4096>(h, s, a);
+    if (rc) return rc;
+    mark(h, s, "pileup");
+
+    // ---- reference-allele totals, median depth ----
+    dim3 tg((ppad / 2 + 127) / 128, (C + kTotalsCellGroup - 1) / kTotalsCellGroup);
+    k_base_totals<<<tg, 128, 0, s>>>(o->planes, C, P, ppad, (u64 *)o->base_totals);
+    h->launches++;
+    if (o->overflow_capacity > 0) {
+        k_base_totals_overflow<<<8, 256, 0, s>>>(o->overflow, o->stats, o->overflow_capacity, P, (u64 *)o->base_totals);
+        h->launches++;
+    }
+    k_median<<<C, 256, 0, s>>>(o->planes, P, ppad, o->cell_qc);
+    h->launches++;
+    CU(cudaGetLastError());
+    mark(h, s, "totals+median");
+    return MGATK_OK;
+}
+
+int ensure(mgatk_handle *h, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return MGATK_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes < 256 ? 256 : bytes;
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return MGATK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgatk_abi_version(void) { return MGATK_ABI_VERSION; }
+
+const char *mgatk_status_string(int status) {
+    switch (status) {
+        case MGATK_OK: return "ok";
+        case MGATK_ERR_BAD_ARG: return "bad argument";
+        case MGATK_ERR_CUDA: return "CUDA error";
+        case MGATK_ERR_WORKSPACE: return "workspace too small";
+        case MGATK_ERR_UNSORTED: return "records are not sorted by reference_start";
+        case MGATK_ERR_EXTENT: return "a read exceeds max_read_extent";
+        case MGATK_ERR_OVERFLOW_CAP: return "overflow list capacity exceeded";
+        case MGATK_ERR_NO_DEVICE: return "no usable CUDA device";
+        case MGATK_ERR_RANGE: return "size outside supported range";
+        default: return "unknown status";
+    }
+}
+
+int mgatk_create(mgatk_handle **out, int device) {
+    if (!out) return MGATK_ERR_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return MGATK_ERR_NO_DEVICE;
+    mgatk_handle *h = new mgatk_handle();
+    h->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return MGATK_ERR_NO_DEVICE; }
+    h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    return MGATK_OK;
+}
+
+int mgatk_destroy(mgatk_handle *h) {
+    if (!h) return MGATK_OK;
+    cudaSetDevice(h->device);
+    DevBuf *all[] = {&h->planes, &h->qc, &h->stats, &h->totals, &h->ovf, &h->ws};
+    for (DevBuf *b : all) if (b->p) cudaFree(b->p);
+    for (DevBuf &b : h->in) if (b.p) cudaFree(b.p);
+    if (h->events_ready) for (int i = 0; i <= kMaxStages; i++) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MGATK_OK;
+}
+
+const char *mgatk_last_error(const mgatk_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int64_t mgatk_workspace_bytes(int64_t n_records, int32_t n_cells) {
+    Layout L;
+    if (!make_layout(n_records, n_cells, L)) return -1;
+    return (int64_t)L.total;
+}
+
+int mgatk_pileup_device(mgatk_handle *h, const mgatk_params *params, const mgatk_batch *batch_dev,
+                        const mgatk_outputs *out_dev, void *workspace_dev, int64_t workspace_bytes, void *stream) {
+    if (!h) return MGATK_ERR_BAD_ARG;
+    h->err.clear();
+    return run_device(h, params, batch_dev, out_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+int mgatk_check_stats(const mgatk_stats *st) {
+    if (!st) return MGATK_ERR_BAD_ARG;
+    if (st->error_bits & ERR_UNSORTED) return MGATK_ERR_UNSORTED;
+    if (st->error_bits & ERR_EXTENT) return MGATK_ERR_EXTENT;
+    if (st->error_bits & ERR_OVERFLOW_CAP) return MGATK_ERR_OVERFLOW_CAP;
+    return MGATK_OK;
+}
+
+int mgatk_pileup_host(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, const mgatk_outputs *o) {
+    if (!h) return MGATK_ERR_BAD_ARG;
+    h->err.clear();
+    int rc = validate(h, p, b, o);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    if (!h->stream) CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    cudaStream_t s = h->stream;
+    const size_t n = (size_t)b->n_records, C = (size_t)p->n_cells, P = (size_t)p->mito_length;
+    const size_t ppad = (size_t)MGATK_POS_PAD(P);
+    const void *src[9] = {b->pos, b->tlen, b->flag, b->mapq, b->bc_idx, b->l_seq, b->n_cigar, b->blob_off, b->blob};
+    const size_t bytes[9] = {4 * n, 4 * n, 2 * n, n, 4 * n, 2 * n, 2 * n, 4 * n, (size_t)b->blob_bytes};
+    for (int k = 0; k < 9; k++) {
+        if ((rc = ensure(h, h->in[k], bytes[k]))) return rc;
+        if (bytes[k]) CU(cudaMemcpyAsync(h->in[k].p, src[k], bytes[k], cudaMemcpyHostToDevice, s));
+    }
+    const size_t planes_bytes = C * MGATK_N_PLANES * ppad * 2;
+    const int64_t ws_bytes = mgatk_workspace_bytes(b->n_records, p->n_cells);
+    if (ws_bytes < 0) return fail(h, MGATK_ERR_RANGE, "n_records / n_cells outside limits");
+    if ((rc = ensure(h, h->planes, planes_bytes)) || (rc = ensure(h, h->qc, C * sizeof(mgatk_cell_qc))) ||
+        (rc = ensure(h, h->stats, sizeof(mgatk_stats))) || (rc = ensure(h, h->totals, P * 4 * 8)) ||
+        (rc = ensure(h, h->ovf, (size_t)o->overflow_capacity * sizeof(mgatk_overflow))) ||
+        (rc = ensure(h, h->ws, (size_t)ws_bytes)))
+        return rc;
+    mgatk_batch bd = *b;
+    bd.pos = (const int32_t *)h->in[0].p; bd.tlen = (const int32_t *)h->in[1].p; bd.flag = (const uint16_t *)h->in[2].p;
+    bd.mapq = (const uint8_t *)h->in[3].p; bd.bc_idx = (const int32_t *)h->in[4].p; bd.l_seq = (const uint16_t *)h->in[5].p;
+    bd.n_cigar = (const uint16_t *)h->in[6].p; bd.blob_off = (const uint32_t *)h->in[7].p; bd.blob = (const uint8_t *)h->in[8].p;
+    mgatk_outputs od = *o;
+    od.planes = (uint16_t *)h->planes.p; od.cell_qc = (mgatk_cell_qc *)h->qc.p; od.stats = (mgatk_stats *)h->stats.p;
+    od.base_totals = (int64_t *)h->totals.p; od.overflow = o->overflow_capacity ? (mgatk_overflow *)h->ovf.p : nullptr;
+    rc = run_device(h, p, &bd, &od, h->ws.p, ws_bytes, s);
+    if (rc) return rc;
+    if (planes_bytes) CU(cudaMemcpyAsync(o->planes, od.planes, planes_bytes, cudaMemcpyDeviceToHost, s));
+    if (C) CU(cudaMemcpyAsync(o->cell_qc, od.cell_qc, C * sizeof(mgatk_cell_qc), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(o->stats, od.stats, sizeof(mgatk_stats), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(o->base_totals, od.base_totals, P * 4 * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (o->overflow_capacity && o->stats->n_overflow) {
+        size_t k = (size_t)(o->stats->n_overflow < (uint64_t)o->overflow_capacity ? o->stats->n_overflow : (uint64_t)o->overflow_capacity);
+        CU(cudaMemcpy(o->overflow, od.overflow, k * sizeof(mgatk_overflow), cudaMemcpyDeviceToHost));
+    }
+    rc = mgatk_check_stats(o->stats);
+    if (rc) return fail(h, rc, mgatk_status_string(rc));
+    return MGATK_OK;
+}
+
+int64_t mgatk_last_launch_count(const mgatk_handle *h) { return h ? h->launches : 0; }
+
+int mgatk_last_stage_times(const mgatk_handle *h, const char **names, float *ms, int *n) {
+    if (!h || !n) return MGATK_ERR_BAD_ARG;
+    *n = 0;
+    if (!h->events_ready) return MGATK_OK;
+    for (int i = 0; i < h->n_stages; i++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); break; }
+        if (names) names[i] = h->stage_names[i];
+        if (ms) ms[i] = t;
+        *n = i + 1;
+    }
+    return MGATK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,35 @@
+"""Error types of the pileup path, named after the reference's (src/core/exceptions.py:4-86) so callers
+that catch `ProcessingError` / `BAMReadError` keep working. `PileupKernelError` is new: a non-zero
+C-ABI status mapped onto `ProcessingError` (SURVEY §8b error convention)."""
+from __future__ import annotations
+
+
+class MgatkError(Exception):
+    pass
+
+
+class InvalidInputError(MgatkError):
+    pass
+
+
+class ProcessingError(MgatkError):
+    pass
+
+
+class BAMReadError(ProcessingError):
+    def __init__(self, bam_path: str, message: str):
+        super().__init__(f"BAM read error for {bam_path}: {message}")
+        self.bam_path = bam_path
+
+
+class NoBarcodeTagsError(BAMReadError):
+    def __init__(self, bam_path: str, barcode_tag: str, total_reads_checked: int):
+        super().__init__(bam_path, f"No reads with barcode tag '{barcode_tag}' found "
+                                   f"(checked {total_reads_checked:,} reads).")
+        self.barcode_tag, self.total_reads_checked = barcode_tag, total_reads_checked
+
+
+class PileupKernelError(ProcessingError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"mgatk2_b200 kernel path failed (status {status}): {message}")
+        self.status = status

@@ -50,6 +50,42 @@ def _sample_categorical(rng, weights: np.ndarray, n: int) -> np.ndarray:
     return np.minimum(np.searchsorted(cdf, rng.random(n), side="right"), len(weights) - 1)
 
 
+_PAYLOAD_CHUNK = 1 << 17          # rows per independently seeded chunk: results do not depend on thread count
+
+
+def _payload_chunk(args):
+    child, rows, L = args
+    rng = np.random.default_rng(child)
+    Lp = L + (L & 1)
+    nib_lut = np.left_shift(1, np.arange(200) & 3).astype(np.uint8)
+    nib_lut[199] = 15                                     # 0.5 % N
+    nib = nib_lut[rng.integers(0, 200, size=(rows, Lp), dtype=np.uint8)]
+    if L & 1:
+        nib[:, -1] = 0
+    packed = (nib[:, 0::2] << 4) | nib[:, 1::2]
+    u = np.arange(100)
+    q_lut = np.where(u < 70, 40, np.where(u < 90, 25 + u % 15, 2 + u % 18)).astype(np.uint8)
+    qual = q_lut[rng.integers(0, 100, size=(rows, L), dtype=np.uint8)]
+    return packed, qual
+
+
+def _payload(seed: int, n: int, L: int):
+    """Packed 4-bit bases [n, ceil(L/2)] and qualities [n, L], drawn in row chunks on a thread pool."""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    n_chunks = max(1, (n + _PAYLOAD_CHUNK - 1) // _PAYLOAD_CHUNK)
+    children = np.random.SeedSequence([seed, 0xB200]).spawn(n_chunks)
+    jobs = [(children[k], min(_PAYLOAD_CHUNK, n - k * _PAYLOAD_CHUNK), L) for k in range(n_chunks)]
+    Lp = L + (L & 1)
+    packed = np.empty((n, Lp // 2), np.uint8)
+    qual = np.empty((n, L), np.uint8)
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        for k, (p, q) in enumerate(ex.map(_payload_chunk, jobs)):
+            packed[k * _PAYLOAD_CHUNK: k * _PAYLOAD_CHUNK + len(p)] = p
+            qual[k * _PAYLOAD_CHUNK: k * _PAYLOAD_CHUNK + len(q)] = q
+    return packed, qual
+
+
 def synth_batch(n_cells: int, n_records: int, profile: str = "atac50", seed: int = 20261018,
                 dup_rate: float = 0.30, mito_length: int = MITO_LENGTH) -> ReadBatch:
     prof = PROFILES[profile]
@@ -129,16 +165,7 @@ def synth_batch(n_cells: int, n_records: int, profile: str = "atac50", seed: int
 
     # ---- bases (0.5 % N) and qualities {40: 70 %, 25-39: 20 %, 2-19: 10 %} ----
     Lp = L + (L & 1)
-    nib = np.left_shift(np.uint8(1), rng.integers(0, 4, size=(n, Lp), dtype=np.uint8))
-    nib[rng.random((n, Lp), dtype=np.float32) < 0.005] = 15
-    if L & 1:
-        nib[:, -1] = 0
-    packed = (nib[:, 0::2] << 4) | nib[:, 1::2]
-    del nib
-    uq = rng.integers(0, 100, size=(n, L), dtype=np.uint8)
-    qual = np.where(uq < 70, np.uint8(40),
-                    np.where(uq < 90, np.uint8(25) + (uq % 15), np.uint8(2) + (uq % 18))).astype(np.uint8)
-    del uq
+    packed, qual = _payload(seed, n, L)
 
     # ---- blobs: cigar | seq | qual, 16-byte aligned, laid out in record order ----
     nbytes = 4 * ncig + Lp // 2 + L

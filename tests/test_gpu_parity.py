@@ -1,0 +1,158 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle and the reference-generated goldens."""
+import numpy as np
+import pytest
+
+from mgatk2_b200.batch import ReadBatch
+from mgatk2_b200.synth import synth_batch
+from tests.helpers import (GOLDEN, assert_matches_golden, assert_result_equals_oracle, golden_ids, load_golden)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from mgatk2_b200.engine import PileupEngine
+    eng = PileupEngine(0)
+    yield eng
+    eng.close()
+
+
+def make_params(batch, n_cells, **kw):
+    from oracle.oracle import make_params as mk
+    return mk(n_cells, max_read_extent=batch.max_read_extent(), **kw)
+
+
+def to_lib_params(p):
+    from mgatk2_b200._lib import ParamsC
+    return ParamsC(*[getattr(p, f) for f, _ in p._fields_])
+
+
+def run_both(engine, batch, n_cells, device_path=False, threads=8, **kw):
+    from oracle.oracle import run_oracle
+    p = make_params(batch, n_cells, **kw)
+    ora = run_oracle(batch, p, n_threads=threads)
+    lp = to_lib_params(p)
+    if device_path:
+        db = engine.upload(batch)
+        do = engine.alloc_device_outputs(n_cells, lp.mito_length, batch.n_records, overflow_capacity=1 << 16)
+        engine.run_device(db, lp, do)
+        res = engine.download(do, lp)
+    else:
+        res = engine.run_host(batch, lp, overflow_capacity=1 << 16)
+    return res, ora
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=golden_ids())
+@pytest.mark.parametrize("device_path", [False, True], ids=["host_abi", "device_abi"])
+def test_golden_vectors(engine, path, device_path):
+    d, batch, barcodes, params = load_golden(path)
+    res, ora = run_both(engine, batch, len(barcodes), device_path=device_path, **params)
+    assert_matches_golden(d, params, res.counts(), res.tn5(), res.coverage(), res.cell_qc, res.stats)
+    np.testing.assert_array_equal(res.base_totals, d["exp_counts"].sum(axis=(0, 3)).astype(np.int64))
+    assert_result_equals_oracle(res, ora)
+
+
+CASES = {
+    "run_defaults": dict(profile="atac50", n_cells=200, n=300_000, kw=dict()),
+    "tenx": dict(profile="atac50", n_cells=200, n=300_000,
+                 kw=dict(min_baseq=0, min_mapq=0, dedup_mode=1, min_reads_per_cell=0)),
+    "dedup_none_gate": dict(profile="atac50", n_cells=150, n=100_000, kw=dict(dedup_mode=2, min_reads_per_cell=400)),
+    "stress150": dict(profile="stress150", n_cells=100, n=120_000,
+                      kw=dict(max_strand_bias=0.8, min_distance_from_end=10)),
+    "atac70_d0": dict(profile="atac70", n_cells=64, n=80_000, kw=dict(min_distance_from_end=0, max_strand_bias=0.6)),
+    "two_pass_partition": dict(profile="atac50", n_cells=5000, n=250_000, kw=dict()),
+    "one_cell": dict(profile="atac50", n_cells=1, n=60_000, kw=dict(dedup_mode=1)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_synthetic_vs_oracle(engine, name):
+    c = CASES[name]
+    batch = synth_batch(c["n_cells"], c["n"], c["profile"], seed=20261018 + len(name))
+    res, ora = run_both(engine, batch, c["n_cells"], device_path=(len(name) % 2 == 0), **c["kw"])
+    assert ora.stats["filtered_reads"] > 0
+    assert_result_equals_oracle(res, ora)
+    assert res.launches > 0
+
+
+def test_large_checksums(engine):
+    """BASELINE configs[1] shape at 1/5 scale: per-cell QC rows, global counters and base totals against the
+    oracle (no dense arrays), plus the self-consistency invariants the reference's goldens obey."""
+    n_cells = 2000
+    batch = synth_batch(n_cells, 4_000_000, "atac50", seed=20261019)
+    from oracle.oracle import run_oracle
+    p = make_params(batch, n_cells)
+    ora = run_oracle(batch, p, n_threads=16, dense=False)
+    res = engine.run_host(batch, to_lib_params(p))
+    assert_result_equals_oracle(res, ora, dense=False)
+    pl = res.planes[:, :, :16569].astype(np.int64)
+    np.testing.assert_array_equal(pl[:, 10], pl[:, :8].sum(axis=1))            # coverage == sum of base planes
+    assert not ((pl[:, 10] == 0) & ((pl[:, 8] > 0) | (pl[:, 9] > 0))).any()     # Tn5 only where covered
+    np.testing.assert_array_equal(pl[:, 10].sum(axis=1), res.cell_qc["sum_depth"].astype(np.int64))
+    assert res.stats["filtered_reads"] == res.stats["stage1_reads"] - res.stats["dup_with_length"]
+
+
+def test_saturation_and_overflow_list(engine):
+    """>65535 reads over one position: planes saturate like the HDF5 writer (writers.py:205-218), the
+    overflow list keeps the exact text-format values."""
+    n = 70_000
+    recs_pos = np.full(n, 5000, np.int32)
+    b = ReadBatch.from_records([dict(pos=5000, flag=0, mapq=60, seq="ACGTACGTAC" * 2, cigar=[(0, 20)], tlen=0, bc_idx=0)])
+    batch = ReadBatch(pos=recs_pos, tlen=np.arange(n, dtype=np.int32), flag=np.zeros(n, np.uint16),
+                      mapq=np.full(n, 60, np.uint8), bc_idx=np.zeros(n, np.int32), l_seq=np.full(n, 20, np.uint16),
+                      n_cigar=np.ones(n, np.uint16), blob_off=np.zeros(n, np.uint32), blob=b.blob)
+    res, ora = run_both(engine, batch, 2, min_distance_from_end=0)
+    assert res.stats["n_overflow"] > 0 and res.planes.max() == 65535
+    assert_result_equals_oracle(res, ora)
+    assert res.coverage()[0, 5000] == n and res.tn5()[0, 5000, 0] == n
+
+
+def test_edge_cases(engine):
+    from mgatk2_b200.exceptions import PileupKernelError
+    empty = ReadBatch.from_records([])
+    res, ora = run_both(engine, empty, 3)
+    assert_result_equals_oracle(res, ora)
+    assert not res.planes.any() and res.stats["total_reads"] == 0
+    # everything filtered at stage 1
+    recs = [dict(pos=10 + i, flag=4, mapq=60, seq="ACGT" * 5, cigar=[(0, 20)], bc_idx=0) for i in range(5)]
+    recs += [dict(pos=20 + i, flag=0, mapq=60, seq="ACGT" * 5, cigar=[(0, 20)], bc_idx=-1) for i in range(5)]
+    res, ora = run_both(engine, ReadBatch.from_records(recs), 3)
+    assert_result_equals_oracle(res, ora)
+    assert res.stats["total_reads"] == 10 and res.stats["stage1_reads"] == 0
+    # unsorted input is refused, not silently mis-deduplicated
+    recs = [dict(pos=50, flag=0, mapq=60, seq="ACGT" * 5, cigar=[(0, 20)], bc_idx=0),
+            dict(pos=40, flag=0, mapq=60, seq="ACGT" * 5, cigar=[(0, 20)], bc_idx=0)]
+    with pytest.raises(PileupKernelError) as e:
+        run_both(engine, ReadBatch.from_records(recs), 1)
+    assert e.value.status == 4
+    # a read longer than the declared extent is refused
+    b = ReadBatch.from_records([dict(pos=50, flag=0, mapq=60, seq="ACGT" * 50, cigar=[(0, 200)], bc_idx=0)])
+    from oracle.oracle import make_params as mk
+    with pytest.raises(PileupKernelError) as e:
+        engine.run_host(b, to_lib_params(mk(1, max_read_extent=20)))
+    assert e.value.status == 5
+    # empty SEQ survivors are reported (the reference raises on them, readers.py:157)
+    b = ReadBatch.from_records([dict(pos=50, flag=0, mapq=60, seq="", cigar=[], bc_idx=0),
+                                dict(pos=60, flag=16, mapq=60, seq="ACGT" * 5, cigar=[(0, 20)], bc_idx=0)])
+    res, ora = run_both(engine, b, 1)
+    assert res.stats["n_empty_seq"] == 1
+    assert_result_equals_oracle(res, ora)
+
+
+def test_long_extent_ring_sizes(engine):
+    """Deletions / skips up to ~1500 bp exercise the larger position rings."""
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(3000):
+        gap = int(rng.choice([0, 0, 0, 100, 400, 1500]))
+        cig = [(0, 25), (3, gap), (0, 25)] if gap else [(0, 50)]
+        recs.append(dict(pos=int(rng.integers(0, 16569)), flag=int(rng.choice([0, 16])), mapq=60,
+                         seq="".join(rng.choice(list("ACGT"), size=50)), cigar=cig, tlen=int(rng.integers(0, 300)),
+                         bc_idx=int(rng.integers(0, 4))))
+    recs.sort(key=lambda r: r["pos"])
+    for cap in (60, 500, 2000):
+        sub = [r for r in recs if sum(l for o, l in r["cigar"]) <= cap]
+        res, ora = run_both(engine, ReadBatch.from_records(sub), 4)
+        assert_result_equals_oracle(res, ora)
