@@ -15,9 +15,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -109,46 +107,55 @@ def run_reference(a):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and clock-event reasons through NVML every few ms on a thread while the timed
+    region runs (nvidia-smi -lms is too coarse for a region of tens of milliseconds)."""
 
-    def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+               "hw_power_brake_slowdown": 0x80}
+
+    def __init__(self, gpu_index, period_s=0.004):
+        import threading
+        self.samples, self.bits, self.max_mhz, self.power = [], 0, None, []
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            import torch
+            uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.p = None
+            self.nv = None
+            return
+
+        def loop():
+            nv = self.nv
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                self._stop.wait(period_s)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if not self.p:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower() == "active":
-                    reasons.add(name)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
-        os.unlink(self.f.name)
-        return out
+        if self._thread:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(k for k, b in self.REASONS.items() if self.bits & b),
+                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
 
 
 # --------------------------------------------------------------------------- our arm

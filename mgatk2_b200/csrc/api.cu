@@ -25,8 +25,8 @@ struct Layout {          // carve-up of the caller's workspace
     int nchunks; int64_t chunk; int ngroups;
     int passes, bits[2], shift[2];
     int unit_reads; int64_t max_units;
-    size_t g[2][6];      // grouped arrays (two generations)
-    size_t gflags, mat, part, cell_start, unit_start, units, scalars, total;
+    size_t key[2], loc[2];   // grouped records (two generations for a two-digit partition)
+    size_t recs, mat, part, cell_start, unit_start, units, scalars, total;
 };
 
 int unit_reads_setting() {
@@ -54,10 +54,11 @@ bool make_layout(int64_t n, int32_t n_cells, Layout &L) {
     const int max_bins = 1 << (L.bits[0] > L.bits[1] ? L.bits[0] : L.bits[1]);
     size_t o = 0;
     const size_t cap = (size_t)(n > 0 ? n : 1);
-    const size_t elt[6] = {4, 4, 4, 4, 4, 2};
-    for (int gen = 0; gen < 2; gen++)
-        for (int k = 0; k < 6; k++) { L.g[gen][k] = o; if (gen < L.passes) o += align_up(cap * elt[k]); }
-    L.gflags = o; o += align_up(cap);
+    for (int gen = 0; gen < 2; gen++) {
+        L.key[gen] = o; if (gen < L.passes) o += align_up(cap * sizeof(KeyRec));
+        L.loc[gen] = o; if (gen < L.passes) o += align_up(cap * sizeof(LocRec));
+    }
+    L.recs = o; o += align_up(cap * sizeof(ReadRec));
     L.mat = o; o += align_up((size_t)L.nchunks * max_bins * 4);
     L.part = o; o += align_up((size_t)L.ngroups * max_bins * 4);
     L.cell_start = o; o += align_up(((size_t)n_cells + 1) * 4);
@@ -70,9 +71,8 @@ bool make_layout(int64_t n, int32_t n_cells, Layout &L) {
 
 Grouped grouped_at(char *ws, const Layout &L, int gen) {
     Grouped g;
-    g.cell = (int32_t *)(ws + L.g[gen][0]); g.pos = (int32_t *)(ws + L.g[gen][1]);
-    g.tlen = (u32 *)(ws + L.g[gen][2]); g.off = (u32 *)(ws + L.g[gen][3]);
-    g.len = (u32 *)(ws + L.g[gen][4]); g.mq = (uint16_t *)(ws + L.g[gen][5]);
+    g.key = (KeyRec *)(ws + L.key[gen]);
+    g.loc = (LocRec *)(ws + L.loc[gen]);
     return g;
 }
 
@@ -142,16 +142,11 @@ int partition_pass(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout
     return MGATK_OK;
 }
 
-template <int R>
 int launch_pileup(mgatk_handle *h, cudaStream_t s, const PileupArgs &a) {
-    int warps = kWarpsPerCta;
-    while (warps > 1 && (size_t)warps * 10 * R * 4 > 200 * 1024) warps >>= 1;
-    const size_t smem = (size_t)warps * 10 * R * 4;
-    CU(cudaFuncSetAttribute(k_pileup<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup<R>, warps * 32, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
-    k_pileup<R><<<h->sm_count * per_sm, warps * 32, smem, s>>>(a);
+    k_pileup<<<h->sm_count * per_sm, kThreads, 0, s>>>(a);    // persistent warps pulling units
     h->launches += 1;
     CU(cudaGetLastError());
     return MGATK_OK;
@@ -167,12 +162,13 @@ int validate(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, const
     if (b->n_records > 0 && (!b->pos || !b->tlen || !b->flag || !b->mapq || !b->bc_idx || !b->l_seq || !b->n_cigar || !b->blob_off))
         return fail(h, MGATK_ERR_BAD_ARG, "null batch array");
     if (b->blob_bytes > 0 && !b->blob) return fail(h, MGATK_ERR_BAD_ARG, "null blob");
+    if (((uintptr_t)b->blob & 15) != 0) return fail(h, MGATK_ERR_BAD_ARG, "blob must be 16-byte aligned");
     if (!o->stats || (p->n_cells > 0 && (!o->planes || !o->cell_qc)) || !o->base_totals)
         return fail(h, MGATK_ERR_BAD_ARG, "null output array");
     if (o->overflow_capacity > 0 && !o->overflow) return fail(h, MGATK_ERR_BAD_ARG, "null overflow list");
     if (p->max_read_extent < 1) return fail(h, MGATK_ERR_BAD_ARG, "max_read_extent must be >= 1");
-    if (p->max_read_extent + 64 > 4096)
-        return fail(h, MGATK_ERR_EXTENT, "max_read_extent above 4032 (long / spliced reads) is not supported");
+    if (p->max_read_extent > (1 << 20))
+        return fail(h, MGATK_ERR_EXTENT, "max_read_extent above 2^20");
     return MGATK_OK;
 }
 
@@ -219,14 +215,14 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     }
     k_publish_m<<<1, 1, 0, s>>>(o->stats, m_ptr);
     int32_t *cell_start = (int32_t *)(ws + L.cell_start);
-    k_cell_start<<<(C + 1 + 255) / 256, 256, 0, s>>>(g.cell, m_ptr, C, cell_start);
+    k_cell_start<<<(C + 1 + 255) / 256, 256, 0, s>>>(g.key, m_ptr, C, cell_start);
     h->launches += 2;
     mark(h, s, "filter+partition");
 
     // ---- stage 2: dedup ----
-    uint8_t *gflags = (uint8_t *)(ws + L.gflags);
+    ReadRec *recs = (ReadRec *)(ws + L.recs);
     if (b->n_records > 0) {
-        k_dedup<<<(unsigned)((b->n_records + 255) / 256), 256, 0, s>>>(g, m_ptr, gflags, p->dedup_mode, p->min_mapq, o->cell_qc, o->stats);
+        k_dedup<<<(unsigned)((b->n_records + 255) / 256), 256, 0, s>>>(g, m_ptr, recs, p->dedup_mode, p->min_mapq, o->cell_qc, o->stats);
         h->launches++;
     }
     mark(h, s, "dedup");
@@ -235,7 +231,7 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     int32_t *unit_start = (int32_t *)(ws + L.unit_start);
     Unit *units = (Unit *)(ws + L.units);
     k_plan_scan<<<1, 1024, 0, s>>>(cell_start, o->cell_qc, C, p->min_reads_per_cell, L.unit_reads, ppad, unit_start, n_units);
-    k_plan_units<<<(unsigned)((L.max_units + 255) / 256), 256, 0, s>>>(cell_start, o->cell_qc, g.pos, unit_start, C,
+    k_plan_units<<<(unsigned)((L.max_units + 255) / 256), 256, 0, s>>>(cell_start, o->cell_qc, recs, unit_start, C,
                                                                       p->min_reads_per_cell, L.unit_reads, ppad,
                                                                       p->max_read_extent, units);
     h->launches += 2;
@@ -243,19 +239,14 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
 
     // ---- stages 3-6 ----
     PileupArgs a;
-    a.gpos = g.pos; a.goff = g.off; a.glen = g.len; a.gflags = gflags; a.blob = b->blob;
+    a.recs = recs; a.blob = b->blob;
     a.units = units; a.n_units = n_units; a.work_counter = work_counter;
     a.planes = o->planes; a.qc = o->cell_qc; a.stats = o->stats; a.ovf = o->overflow; a.ovf_cap = o->overflow_capacity;
     a.P = P; a.ppad = ppad; a.min_baseq = p->min_baseq; a.dist = p->min_distance_from_end;
     a.max_bias = p->max_strand_bias;
     a.apply_bias = !(p->max_strand_bias >= 1.0);          // max(f,r)/total never exceeds 1.0
-    const int need = p->max_read_extent + 64;
-    if (need <= 128) rc = launch_pileup<128>(h, s, a);
-    else if (need <= 256) rc = launch_pileup<256>(h, s, a);
-    else if (need <= 512) rc = launch_pileup<512>(h, s, a);
-    else if (need <= 1024) rc = launch_pileup<1024>(h, s, a);
-    else if (need <= 2048) rc = launch_pileup<2048>(h, s, a);
-    else rc = launch_pileup<4096>(h, s, a);
+    a.extent = p->max_read_extent;
+    rc = launch_pileup(h, s, a);
     if (rc) return rc;
     mark(h, s, "pileup");
 

@@ -7,9 +7,9 @@
 //                                     n_reads / n_paired (processors.py:33-34), global counters (readers.py:193-199)
 //   3  k_plan*                        cut every cell into position tiles ("units") of bounded read count
 //   4  k_pileup                       stages 3-6: CIGAR walk, base-quality / distance-from-end masks, per-base
-//                                     per-strand counting and Tn5 sites (pileup.py:32-95) in a per-warp
-//                                     shared-memory position ring; strand-bias filter, coverage, Tn5 gating
-//                                     (pileup.py:128-154) and depth statistics at flush; planes written once
+//                                     per-strand counting and Tn5 sites (pileup.py:32-95) gathered per position
+//                                     in registers; strand-bias filter, coverage, Tn5 gating (pileup.py:128-154)
+//                                     and depth statistics in the same pass; planes written once
 //   5  k_base_totals, k_median        reference-allele vote input and median depth (writers.py:187-197,220-222)
 #pragma once
 #include <cuda_runtime.h>
@@ -29,19 +29,18 @@ constexpr u32 kFull = 0xffffffffu;
 
 constexpr u32 ERR_UNSORTED = 1, ERR_EXTENT = 2, ERR_OVERFLOW_CAP = 4;
 
-// gflags bits written by k_dedup, read by k_pileup
+// ReadRec.flags bits written by k_dedup, read by k_pileup
 constexpr int GF_PROCESS = 1, GF_STRAND = 2, GF_KEEP = 4;
-// gmq layout: mapq | strand<<8 | paired<<9
+// KeyRec.mq layout: mapq | strand<<8 | paired<<9
 constexpr int GMQ_STRAND = 0x100, GMQ_PAIRED = 0x200;
 
-struct Grouped {          // records that passed stage 1, grouped by cell, BAM order inside a cell
-    int32_t *cell;
-    int32_t *pos;
-    u32 *tlen;            // |template_length|
-    u32 *off;             // blob offset, 16-byte units
-    u32 *len;             // l_seq | n_cigar<<16
-    uint16_t *mq;
-};
+// Records that passed stage 1, grouped by cell, BAM order inside a cell. 16-byte records so the
+// scattered side of the partition is one full-width store per record.
+struct __align__(16) KeyRec { int32_t cell; int32_t pos; u32 tlen; u32 mq; };   // dedup key (+mapq, strand, paired)
+struct __align__(8) LocRec { u32 off; u32 len; };                               // blob offset (16 B units), l_seq | n_cigar<<16
+struct __align__(16) ReadRec { int32_t pos; u32 off; u32 len; u32 flags; };     // what k_pileup consumes (from k_dedup)
+struct Grouped { KeyRec *key; LocRec *loc; };
+struct Item { KeyRec k; LocRec l; };
 
 struct Unit { int32_t cell, t0, t1, rbeg, rend; };
 
@@ -51,7 +50,8 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 // Stable counting partition by a digit of the cell index.
 // Each warp owns a contiguous chunk of records and a private histogram in shared memory, so ranks
 // follow record order without atomics: match_any groups the lanes of one 32-record step by digit,
-// the lowest lane of each group bumps the private counter.
+// the lowest lane of each group bumps the private counter. Loads run one group of steps ahead of
+// the ranking so several 128-byte requests per array are in flight per warp.
 // ---------------------------------------------------------------------------------------------
 struct SrcUser {          // pass 0: reads the caller's SoA batch and applies the stage-1 filter
     mgatk_batch b;
@@ -59,19 +59,21 @@ struct SrcUser {          // pass 0: reads the caller's SoA batch and applies th
     __device__ __forceinline__ int64_t count() const { return b.n_records; }
     __device__ __forceinline__ int cell(int64_t i) const {
         // readers.py:96-97 unmapped/secondary/supplementary; :104-111 tag absent or not whitelisted
-        if (b.flag[i] & 0x904) return -1;
-        int c = b.bc_idx[i];
-        return (c < 0 || c >= n_cells) ? -1 : c;
+        const int c = b.bc_idx[i];
+        return ((b.flag[i] & 0x904) || c < 0 || c >= n_cells) ? -1 : c;
     }
-    __device__ __forceinline__ void emit(int64_t i, int c, const Grouped &g, int64_t d) const {
-        int32_t t = b.tlen[i];
-        uint16_t f = b.flag[i];
-        g.cell[d] = c;
-        g.pos[d] = b.pos[i];
-        g.tlen[d] = t < 0 ? (u32)(-(int64_t)t) : (u32)t;     // abs(read.template_length), readers.py:124
-        g.off[d] = b.blob_off[i];
-        g.len[d] = (u32)b.l_seq[i] | ((u32)b.n_cigar[i] << 16);
-        g.mq[d] = (uint16_t)(b.mapq[i] | ((f & 0x10) ? GMQ_STRAND : 0) | ((f & 0x1) ? GMQ_PAIRED : 0));
+    __device__ __forceinline__ Item load(int64_t i) const {
+        Item it;
+        const int32_t t = b.tlen[i];
+        const uint16_t f = b.flag[i];
+        const int c = b.bc_idx[i];
+        it.k.cell = ((f & 0x904) || c < 0 || c >= n_cells) ? -1 : c;
+        it.k.pos = b.pos[i];
+        it.k.tlen = t < 0 ? (u32)(-(int64_t)t) : (u32)t;     // abs(read.template_length), readers.py:124
+        it.k.mq = (u32)b.mapq[i] | ((f & 0x10) ? GMQ_STRAND : 0) | ((f & 0x1) ? GMQ_PAIRED : 0);
+        it.l.off = b.blob_off[i];
+        it.l.len = (u32)b.l_seq[i] | ((u32)b.n_cigar[i] << 16);
+        return it;
     }
 };
 
@@ -79,12 +81,12 @@ struct SrcGrouped {       // pass 1 of a two-digit partition: already filtered, 
     Grouped a;
     const int64_t *m;
     __device__ __forceinline__ int64_t count() const { return *m; }
-    __device__ __forceinline__ int cell(int64_t i) const { return a.cell[i]; }
-    __device__ __forceinline__ void emit(int64_t i, int c, const Grouped &g, int64_t d) const {
-        g.cell[d] = c; g.pos[d] = a.pos[i]; g.tlen[d] = a.tlen[i];
-        g.off[d] = a.off[i]; g.len[d] = a.len[i]; g.mq[d] = a.mq[i];
-    }
+    __device__ __forceinline__ int cell(int64_t i) const { return a.key[i].cell; }
+    __device__ __forceinline__ Item load(int64_t i) const { Item it; it.k = a.key[i]; it.l = a.loc[i]; return it; }
 };
+
+constexpr int kHistAhead = 8;     // 32-record steps loaded before ranking (k_hist)
+constexpr int kScatAhead = 4;     // same for k_scatter (full records)
 
 template <class Src>
 __global__ void __launch_bounds__(kThreads)
@@ -101,17 +103,24 @@ k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict
     int64_t beg = (int64_t)w * chunk, end = beg + chunk;
     if (end > n) end = n;
     bool unsorted = false;
-    for (int64_t i0 = beg; i0 < end; i0 += 32) {
-        const int64_t i = i0 + lane;
-        int d = -1;
-        if (i < end) {
-            int c = src.cell(i);
-            if (c >= 0) d = (c >> shift) & (bins - 1);
-            if (sorted_check_pos && i > 0 && sorted_check_pos[i] < sorted_check_pos[i - 1]) unsorted = true;
+    for (int64_t i0 = beg; i0 < end; i0 += 32 * kHistAhead) {
+        int d[kHistAhead];
+#pragma unroll
+        for (int k = 0; k < kHistAhead; k++) {
+            const int64_t i = i0 + 32 * k + lane;
+            d[k] = -1;
+            if (i < end) {
+                const int c = src.cell(i);
+                if (c >= 0) d[k] = (c >> shift) & (bins - 1);
+                if (sorted_check_pos && i > 0 && sorted_check_pos[i] < sorted_check_pos[i - 1]) unsorted = true;
+            }
         }
-        const u32 peers = __match_any_sync(kFull, d);
-        if (d >= 0 && lane == __ffs(peers) - 1) h[d] += __popc(peers);
-        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < kHistAhead; k++) {
+            const u32 peers = __match_any_sync(kFull, d[k]);
+            if (d[k] >= 0 && lane == __ffs(peers) - 1) h[d[k]] += __popc(peers);
+            __syncwarp();
+        }
     }
     if (unsorted) atomicOr(error_bits, (u64)ERR_UNSORTED);
     u32 *row = mat + (size_t)w * bins;
@@ -184,27 +193,40 @@ k_scatter(Src src, int64_t chunk, int nchunks, int shift, int bins, const u32 *_
     int64_t beg = (int64_t)w * chunk, end = beg + chunk;
     if (end > n) end = n;
     const u32 lt = (1u << lane) - 1;
-    for (int64_t i0 = beg; i0 < end; i0 += 32) {
-        const int64_t i = i0 + lane;
-        int d = -1, c = -1;
-        if (i < end) { c = src.cell(i); if (c >= 0) d = (c >> shift) & (bins - 1); }
-        const u32 peers = __match_any_sync(kFull, d);
-        u32 base = 0;
-        if (d >= 0) base = off[d];
-        __syncwarp();
-        if (d >= 0 && lane == __ffs(peers) - 1) off[d] = base + __popc(peers);
-        __syncwarp();
-        if (d >= 0) src.emit(i, c, dst, (int64_t)base + __popc(peers & lt));
+    for (int64_t i0 = beg; i0 < end; i0 += 32 * kScatAhead) {
+        Item it[kScatAhead];
+#pragma unroll
+        for (int k = 0; k < kScatAhead; k++) {
+            const int64_t i = i0 + 32 * k + lane;
+            it[k].k.cell = -1;
+            if (i < end) it[k] = src.load(i);
+        }
+#pragma unroll
+        for (int k = 0; k < kScatAhead; k++) {
+            const int c = it[k].k.cell;
+            const int d = c >= 0 ? (c >> shift) & (bins - 1) : -1;
+            const u32 peers = __match_any_sync(kFull, d);
+            u32 base = 0;
+            if (d >= 0) base = off[d];
+            __syncwarp();
+            if (d >= 0 && lane == __ffs(peers) - 1) off[d] = base + __popc(peers);
+            __syncwarp();
+            if (d >= 0) {
+                const size_t dd = (size_t)base + __popc(peers & lt);
+                dst.key[dd] = it[k].k;                   // one 16-byte and one 8-byte store per record
+                dst.loc[dd] = it[k].l;
+            }
+        }
     }
 }
 
 // first grouped index of every cell: lower_bound on the cell column (records are grouped by cell)
-__global__ void k_cell_start(const int32_t *__restrict__ gcell, const int64_t *__restrict__ m_ptr, int n_cells,
+__global__ void k_cell_start(const KeyRec *__restrict__ key, const int64_t *__restrict__ m_ptr, int n_cells,
                              int32_t *__restrict__ cell_start) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > n_cells) return;
     int lo = 0, hi = (int)*m_ptr;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (gcell[mid] < c) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (key[mid].cell < c) lo = mid + 1; else hi = mid; }
     cell_start[c] = lo;
 }
 
@@ -213,9 +235,10 @@ __global__ void k_cell_start(const int32_t *__restrict__ gcell, const int64_t *_
 // of record i sit directly before it in the same (cell, start) run; the first record of a key in
 // BAM order survives (readers.py:129-150). Both key sets are evaluated for every stage-1 survivor
 // (readers.py:128-144) so both duplicate counters are exact whichever strategy is selected.
+// The kernel also emits the 16-byte record k_pileup consumes.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_dedup(Grouped g, const int64_t *__restrict__ m_ptr, uint8_t *__restrict__ gflags, int dedup_mode, int min_mapq,
+k_dedup(Grouped g, const int64_t *__restrict__ m_ptr, ReadRec *__restrict__ recs, int dedup_mode, int min_mapq,
         mgatk_cell_qc *__restrict__ qc, mgatk_stats *__restrict__ stats) {
     __shared__ u32 s_cnt[4];
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
@@ -226,30 +249,33 @@ k_dedup(Grouped g, const int64_t *__restrict__ m_ptr, uint8_t *__restrict__ gfla
     int cell = -1;
     bool keep = false, paired = false;
     if (i < m) {
-        cell = g.cell[i];
-        const int pos = g.pos[i];
-        const u32 tl = g.tlen[i];
-        const u32 mq = g.mq[i];
-        const u32 strand = mq & GMQ_STRAND;
-        paired = mq & GMQ_PAIRED;
+        const KeyRec me = g.key[i];
+        const LocRec lc = g.loc[i];
+        cell = me.cell;
+        const u32 strand = me.mq & GMQ_STRAND;
+        paired = me.mq & GMQ_PAIRED;
         bool len_dup = false, pos_dup = false;
         if (dedup_mode != MGATK_DEDUP_NONE) {
             for (int64_t j = i - 1; j >= 0; j--) {
-                if (g.pos[j] != pos || g.cell[j] != cell) break;
-                if ((g.mq[j] & GMQ_STRAND) == strand) {
+                const KeyRec o = g.key[j];
+                if (o.pos != me.pos || o.cell != me.cell) break;
+                if ((o.mq & GMQ_STRAND) == strand) {
                     pos_dup = true;
-                    if (g.tlen[j] == tl) { len_dup = true; break; }
+                    if (o.tlen == me.tlen) { len_dup = true; break; }
                 }
             }
         }
         keep = dedup_mode == MGATK_DEDUP_FRAGMENT_LENGTH ? !len_dup : dedup_mode == MGATK_DEDUP_POSITION_ONLY ? !pos_dup : true;
         // pileup.py:33-34 mapq gate (after dedup, Q2). An empty SEQ makes the reference raise
         // (readers.py:157); such survivors are reported in stats.n_empty_seq and not piled up.
-        const bool process = keep && (int)(mq & 0xff) >= min_mapq && (g.len[i] & 0xffff) != 0;
-        gflags[i] = (uint8_t)((process ? GF_PROCESS : 0) | (strand ? GF_STRAND : 0) | (keep ? GF_KEEP : 0));
+        const bool process = keep && (int)(me.mq & 0xff) >= min_mapq && (lc.len & 0xffff) != 0;
+        ReadRec rr;
+        rr.pos = me.pos; rr.off = lc.off; rr.len = lc.len;
+        rr.flags = (process ? GF_PROCESS : 0) | (strand ? GF_STRAND : 0) | (keep ? GF_KEEP : 0);
+        recs[i] = rr;
         if (len_dup) atomicAdd(&s_cnt[1], 1u);
         if (pos_dup) atomicAdd(&s_cnt[2], 1u);
-        if (keep) { atomicAdd(&s_cnt[0], 1u); if ((g.len[i] & 0xffff) == 0) atomicAdd(&s_cnt[3], 1u); }
+        if (keep) { atomicAdd(&s_cnt[0], 1u); if ((lc.len & 0xffff) == 0) atomicAdd(&s_cnt[3], 1u); }
     }
     // per-cell survivors: lanes of a warp mostly share one cell
     const u32 peers = __match_any_sync(kFull, cell);
@@ -321,7 +347,7 @@ k_plan_scan(const int32_t *__restrict__ cell_start, const mgatk_cell_qc *__restr
 }
 
 __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk_cell_qc *__restrict__ qc,
-                             const int32_t *__restrict__ gpos, const int32_t *__restrict__ unit_start, int n_cells,
+                             const ReadRec *__restrict__ recs, const int32_t *__restrict__ unit_start, int n_cells,
                              int min_reads, int unit_reads, int ppad, int halo, Unit *__restrict__ units) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= unit_start[n_cells]) return;
@@ -339,198 +365,243 @@ __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk
     if (dead) { un.rbeg = un.rend = 0; }
     else {
         const int first = un.t0 - halo + 1;                // reads starting before cannot reach t0
-        int a = cs, b = ce;
-        while (a < b) { int mid = (a + b) >> 1; if (gpos[mid] < first) a = mid + 1; else b = mid; }
+        int a = cs, b = un.t0 == 0 ? cs : ce;              // tile 0 also takes (and extent-checks) reads left of 0
+        while (a < b) { int mid = (a + b) >> 1; if (recs[mid].pos < first) a = mid + 1; else b = mid; }
         un.rbeg = a;
         b = ce;
-        while (a < b) { int mid = (a + b) >> 1; if (gpos[mid] < un.t1) a = mid + 1; else b = mid; }
+        while (a < b) { int mid = (a + b) >> 1; if (recs[mid].pos < un.t1) a = mid + 1; else b = mid; }
         un.rend = a;
     }
     units[u] = un;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stages 3-6. One warp per unit. The warp streams the unit's reads in start order; lanes take
-// consecutive reference positions of an aligned block, so every shared-memory update of one
-// instruction hits 32 different banks of the ring[plane][slot] layout and needs no atomics (the
-// warp is the only writer). Positions left of the current read start are final: they are filtered,
-// reduced and written out in 64-position chunks (one 128-byte store per plane), and the ring slots
-// are recycled.
+// Stages 3-6 as a gather. One warp per unit (cell, position tile); the warp walks the tile in chunks
+// of 32 positions, lane = position. For a chunk, the candidate reads are those starting in
+// (chunk - extent, chunk + 32): lanes first take one candidate read each and walk its CIGAR in
+// parallel (pileup.py:52-95) to the aligned block(s) overlapping the chunk; every such block is then
+// broadcast by shuffle and each lane picks the base / quality of its own position, accumulating the
+// eight base x strand counters in registers (byte-packed, spilled every 255 visits). Nothing is
+// shared between warps, so there are no atomics and no shared-memory counters; when the chunk's
+// reads are exhausted the counts are final and the strand-bias filter, coverage, Tn5 gating
+// (pileup.py:128-154) and the depth statistics are applied in registers and the 11 planes are
+// written once.
 // ---------------------------------------------------------------------------------------------
 struct PileupArgs {
-    const int32_t *gpos; const u32 *goff; const u32 *glen; const uint8_t *gflags;
+    const ReadRec *recs;
     const uint8_t *blob;
     const Unit *units; const int32_t *n_units; int32_t *work_counter;
     uint16_t *planes; mgatk_cell_qc *qc; mgatk_stats *stats;
     mgatk_overflow *ovf; int64_t ovf_cap;
-    int P, ppad, min_baseq, dist, apply_bias;
+    int P, ppad, min_baseq, dist, apply_bias, extent;
     double max_bias;
 };
 
-template <int R>
-__device__ __forceinline__ void flush_chunk(const PileupArgs &a, u32 *ring, int cell, int base, bool dirty,
-                                            u64 &sum, u32 &covered, u32 &maxd) {
-    const int lane = lane_id();
-    const int p0 = base + 2 * lane;
-    u32 *out = reinterpret_cast<u32 *>(a.planes + ((size_t)cell * MGATK_N_PLANES) * a.ppad + p0);
-    const size_t pstride = (size_t)a.ppad / 2;             // plane stride in u32
-    if (!dirty) {
+constexpr int kOpCap = 1 << 20;     // cigar lengths above this cannot be valid for a short-read batch
+
+__device__ __forceinline__ void spill_packed(u32 (&cnt)[8], u32 &accf, u32 &accr) {
 #pragma unroll
-        for (int pl = 0; pl < MGATK_N_PLANES; pl++) out[pl * pstride] = 0u;
-        return;
+    for (int b = 0; b < 4; b++) {
+        cnt[2 * b] += (accf >> (8 * b)) & 255u;
+        cnt[2 * b + 1] += (accr >> (8 * b)) & 255u;
     }
-    const int slot = p0 & (R - 1);
-    u32 v[10][2];
-#pragma unroll
-    for (int pl = 0; pl < 10; pl++) {
-        uint2 t = *reinterpret_cast<uint2 *>(&ring[pl * R + slot]);
-        v[pl][0] = t.x; v[pl][1] = t.y;
-        *reinterpret_cast<uint2 *>(&ring[pl * R + slot]) = make_uint2(0u, 0u);
-    }
-    u32 cov[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        u32 c = 0;
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            u32 f = v[2 * b][k], r = v[2 * b + 1][k];
-            const u32 t = f + r;
-            if (a.apply_bias && t > 0) {                   // pileup.py:143-148, IEEE double, strict >
-                const double bias = (double)max(f, r) / (double)t;
-                if (bias > a.max_bias) { f = 0; r = 0; v[2 * b][k] = 0; v[2 * b + 1][k] = 0; }
-            }
-            c += f + r;                                    // pileup.py:150
-        }
-        cov[k] = c;
-        if (c == 0) { v[8][k] = 0; v[9][k] = 0; }          // pileup.py:152-153: position dropped with its Tn5 counts
-        else { sum += c; covered++; maxd = max(maxd, c); }
-    }
-    u32 all[MGATK_N_PLANES][2];
-#pragma unroll
-    for (int pl = 0; pl < 10; pl++) { all[pl][0] = v[pl][0]; all[pl][1] = v[pl][1]; }
-    all[10][0] = cov[0]; all[10][1] = cov[1];
-#pragma unroll
-    for (int pl = 0; pl < MGATK_N_PLANES; pl++) {
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            if (all[pl][k] > 65535u) {                     // writers.py:205-218 saturation; exact value kept aside
-                const u64 idx = atomicAdd((u64 *)&a.stats->n_overflow, 1ull);
-                if ((int64_t)idx < a.ovf_cap) {
-                    a.ovf[idx].cell = cell;
-                    a.ovf[idx].plane_pos = ((u32)pl << 24) | (u32)(p0 + k);
-                    a.ovf[idx].value = all[pl][k];
-                } else atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_OVERFLOW_CAP);
-                all[pl][k] = 65535u;
-            }
-        }
-        out[pl * pstride] = all[pl][0] | (all[pl][1] << 16);
-    }
+    accf = 0; accr = 0;
 }
 
-template <int R>
+// One lane's share of one aligned block: the base and quality at its own position -> (fwd, rev) increment.
+__device__ __forceinline__ uint2 visit(u64 sb, int pa, u32 sp, int qd, int lane, int min_baseq, u32 lut_addr) {
+    const bool valid = (unsigned)(lane - pa) < (sp & 0xffffu);
+    const int q = valid ? lane + qd : 0;                      // pileup.py:75; lanes outside the block read base 0
+    const uint8_t *seq = reinterpret_cast<const uint8_t *>(sb & ~(u64)3);
+    u32 by = __ldg(seq + (q >> 1));
+    const int ql = (int)__ldg(reinterpret_cast<const int8_t *>(seq) + (sp >> 16) + q);
+    if (!valid || ql < min_baseq) by = 0;                     // int8 compare, pileup.py:80
+    const u32 addr = lut_addr + ((((u32)sb & 1u) << 12) | (((u32)q & 1u) << 11) | (by << 3));
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_pileup(PileupArgs a) {
-    extern __shared__ u32 smem[];
+    // (fwd, rev) byte-packed increments indexed by [strand][q parity][SEQ byte]: the BAM base code
+    // 1,2,4,8 = A,C,G,T of the addressed nibble selects byte 0..3, anything else adds nothing
+    // (pileup.py:83-86); the pair form lets the visit add to both accumulators without a branch.
+    __shared__ uint2 lut[2 * 2 * 256];
+    for (int e = threadIdx.x; e < 1024; e += blockDim.x) {
+        const int by = e & 255, odd = (e >> 8) & 1, st = e >> 9;
+        const int n = odd ? (by & 15) : (by >> 4);
+        const u32 inc = n == 1 ? 1u : n == 2 ? 1u << 8 : n == 4 ? 1u << 16 : n == 8 ? 1u << 24 : 0u;
+        lut[e] = st ? make_uint2(0u, inc) : make_uint2(inc, 0u);
+    }
+    __syncthreads();
+    const u32 lut_addr = (u32)__cvta_generic_to_shared(lut);
     const int lane = lane_id();
-    u32 *ring = smem + (threadIdx.x >> 5) * (10 * R);
-    for (int k = lane; k < 10 * R; k += 32) ring[k] = 0;
-    __syncwarp();
     const int n_units = *a.n_units;
+    const int q_lo = a.dist > 0 ? a.dist : 0;                // pileup.py:67-72
     for (;;) {
         int u = 0;
         if (lane == 0) u = atomicAdd(a.work_counter, 1);
         u = __shfl_sync(kFull, u, 0);
         if (u >= n_units) break;
         const Unit un = a.units[u];
-        const int T0 = un.t0, T1 = un.t1, T1c = min(un.t1, a.P);
-        int base = T0, dirty_hi = T0;
+        int ra = un.rbeg;
         u64 sum = 0; u32 covered = 0, maxd = 0;
         bool extent_err = false;
+        uint16_t *out_cell = a.planes + (size_t)un.cell * MGATK_N_PLANES * a.ppad;
 
-        for (int b0 = un.rbeg; b0 < un.rend; b0 += 32) {
-            const int i = b0 + lane;
-            int my_pos = 0; u32 my_off = 0, my_len = 0, my_fl = 0;
-            if (i < un.rend) {
-                my_fl = a.gflags[i];
-                if (my_fl & GF_PROCESS) {
-                    my_pos = a.gpos[i]; my_off = a.goff[i]; my_len = a.glen[i];
-                    const uint8_t *bl = a.blob + 16 * (size_t)my_off;
-                    const int L = my_len & 0xffff, nbytes = 4 * (int)(my_len >> 16) + (L + 1) / 2 + L;
-                    for (int o = 0; o < nbytes + 127 && o < 1024; o += 128)
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(bl + o));
+        for (int c0 = un.t0; c0 < un.t1; c0 += 32) {
+            const int c1 = c0 + 32;
+            u32 cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            u32 accf = 0, accr = 0, tn5f = 0, tn5r = 0;
+            int nacc = 0;
+            const int skip_le = c0 - a.extent;               // reads starting at or before this cannot reach the chunk
+            bool prefix = true;
+            for (int r = ra; r < un.rend; r += 32) {
+                const int i = r + lane;
+                ReadRec rr; rr.pos = 0x7fffffff; rr.off = 0; rr.len = 0; rr.flags = 0;
+                if (i < un.rend) rr = a.recs[i];             // one 16-byte load per candidate
+                const int pos = rr.pos;
+                const bool before = pos <= skip_le;
+                const u32 m_after = __ballot_sync(kFull, pos >= c1);
+                if (prefix) {                                // reads are sorted by start: "before" is a prefix
+                    const int nb = __popc(__ballot_sync(kFull, before));
+                    ra += nb;
+                    prefix = nb == 32;
                 }
-            }
-            u32 active = __ballot_sync(kFull, my_fl & GF_PROCESS);
-            while (active) {
-                const int j = __ffs(active) - 1;
-                active &= active - 1;
-                const int pos = __shfl_sync(kFull, my_pos, j);
-                const u32 off = __shfl_sync(kFull, my_off, j);
-                const u32 ln = __shfl_sync(kFull, my_len, j);
-                const int strand = (__shfl_sync(kFull, my_fl, j) & GF_STRAND) ? 1 : 0;
+                const bool live = pos < c1 && (rr.flags & GF_PROCESS);   // implies i < rend
+                const bool cand = live && !before;
+                const bool chk = live && (pos >= c0 || c0 == un.t0);     // once per read and unit: verify the declared extent
+                const u32 off = rr.off, ln = rr.len;
+                const int strand = (rr.flags & GF_STRAND) ? 1 : 0;
                 const int L = ln & 0xffff, ncig = ln >> 16;
-
-                // positions left of this read's start are final
-                const int lim = min(pos, T1);
-                while (base + 64 <= lim) {
-                    flush_chunk<R>(a, ring, un.cell, base, base < dirty_hi, sum, covered, maxd);
-                    base += 64;
+                const u32 *cig = reinterpret_cast<const u32 *>(a.blob + 16 * (size_t)off);
+                const int t5 = strand ? pos + L - 1 : pos;   // pileup.py:43-50
+                if (chk) {
+                    const int nbytes = 4 * ncig + ((L + 1) >> 1) + L;  // pull the whole blob towards L1 once
+                    for (int o = 32; o < nbytes && o < 512; o += 32)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(cig) + o));
+                    if (L > a.extent) extent_err = true;
+                    int span = 0;
+                    for (int ci = 0; ci < ncig; ci++) {
+                        const u32 w = __ldg(cig + ci);
+                        const int op = w & 15;
+                        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += min((int)(w >> 4), kOpCap);
+                        if (span > a.extent) { extent_err = true; break; }
+                    }
                 }
-                __syncwarp();
-                const long long ring_end = (long long)base + R;   // first position the ring cannot hold
-
-                // Tn5 site (pileup.py:43-50): reverse = start + len(SEQ) - 1, forward = start
-                const long long t5 = strand ? (long long)pos + L - 1 : (long long)pos;
-                if (t5 >= T0 && t5 < T1c) {
-                    if (t5 < ring_end) {
-                        if (lane == 0) ring[(8 + strand) * R + ((int)t5 & (R - 1))] += 1;
-                        dirty_hi = max(dirty_hi, (int)t5 + 1);
-                    } else extent_err = true;
+                // Tn5 sites falling into this chunk
+                u32 mt = __ballot_sync(kFull, cand && t5 >= c0 && t5 < c1 && t5 < a.P);
+                while (mt) {
+                    const int j = __ffs(mt) - 1;
+                    mt &= mt - 1;
+                    const int x = __shfl_sync(kFull, t5, j) - c0;
+                    const int s = __shfl_sync(kFull, strand, j);
+                    if (lane == x) { if (s) tn5r++; else tn5f++; }
                 }
-
-                const uint8_t *bl = a.blob + 16 * (size_t)off;
-                const u32 *cig = reinterpret_cast<const u32 *>(bl);
-                const uint8_t *seq = bl + 4 * ncig;
-                const int8_t *qual = reinterpret_cast<const int8_t *>(seq + (L + 1) / 2);
-                const long long q_lo = a.dist > 0 ? a.dist : 0;            // pileup.py:67-72
-                const long long q_hi = a.dist > 0 ? (long long)L - a.dist : (long long)L;
-                long long ref = pos, qp = 0;                                // pileup.py:52-53
-                for (int ci = 0; ci < ncig; ci++) {
-                    const u32 w = __ldg(cig + ci);
-                    const int op = w & 15;
-                    const long long n = w >> 4;
-                    if (op == 0 || op == 7 || op == 8) {                    // pileup.py:56
-                        long long i_lo = max(max(0ll, (long long)T0 - ref), q_lo - qp);
-                        long long i_hi = min(min(n, (long long)T1c - ref), q_hi - qp);
-                        if (i_hi > ring_end - ref) { i_hi = ring_end - ref; extent_err = true; }
-                        if (i_hi > i_lo) {
-                            dirty_hi = max(dirty_hi, (int)(ref + i_hi));
-                            const uint8_t *sq = seq; const int8_t *ql = qual;
-                            for (long long i0 = i_lo; i0 < i_hi; i0 += 32) {
-                                const long long ii = i0 + lane;
-                                if (ii < i_hi) {
-                                    const long long q = qp + ii;            // pileup.py:75
-                                    const int qv = __ldg(ql + q);           // int8 compare, pileup.py:80
-                                    const u32 nib = (__ldg(sq + (q >> 1)) >> ((~q & 1) << 2)) & 15u;
-                                    if (qv >= a.min_baseq && __popc(nib) == 1) {   // A,C,G,T = 1,2,4,8 (pileup.py:83-86)
-                                        const int code = 31 - __clz(nib);
-                                        ring[(code * 2 + strand) * R + ((int)(ref + ii) & (R - 1))] += 1;  // :88
-                                    }
+                // aligned blocks overlapping this chunk; a read can contribute several (indels), one per round
+                const int q_hi = a.dist > 0 ? L - a.dist : L;
+                int ci = 0, ref = pos, qp = 0;
+                bool has = cand;
+                for (;;) {
+                    int pa = 0, span = 0, q0 = 0;
+                    bool blk = false;
+                    if (has) {
+                        while (ci < ncig) {
+                            const u32 w = __ldg(cig + ci);
+                            const int op = w & 15;
+                            const int n = min((int)(w >> 4), kOpCap);
+                            ci++;
+                            if (op == 0 || op == 7 || op == 8) {             // pileup.py:56
+                                const int va = max(q_lo - qp, 0), vb = min(q_hi - qp, n);
+                                const int r0 = ref;
+                                const int q00 = qp;
+                                ref += n; qp = min(qp + n, kOpCap);          // pileup.py:90-91
+                                if (vb > va && r0 + va < c1 && r0 + vb > c0) {
+                                    pa = r0 + va - c0; span = vb - va; q0 = q00 + va; blk = true;
+                                    break;
                                 }
-                            }
+                            } else if (op == 2 || op == 3) ref += n;         // pileup.py:92-93
+                            else if (op == 4) qp = min(qp + n, kOpCap);      // pileup.py:94-95; I, H, P: nothing (sic)
+                            if (ref >= c1) { ci = ncig; break; }             // blocks only move right
                         }
-                        ref += n; qp += n;                                   // pileup.py:90-91
-                    } else if (op == 2 || op == 3) ref += n;                 // :92-93
-                    else if (op == 4) qp += n;                               // :94-95 (I, H, P: nothing, sic)
+                        has = blk;
+                    }
+                    u32 mv = __ballot_sync(kFull, blk);
+                    if (!mv) break;
+                    // owner lanes publish: first position (chunk relative), span | qual offset, q - lane, SEQ address | strand
+                    const int qd = q0 - pa;
+                    const u32 sp = (u32)span | ((u32)((L + 1) >> 1) << 16);
+                    const u64 sb = (u64)(a.blob + 16 * (size_t)off + 4 * ncig) | (u64)strand;
+                    if (nacc + __popc(mv) > 255) { spill_packed(cnt, accf, accr); nacc = 0; }
+                    nacc += __popc(mv);
+                    while (mv) {                              // two visits in flight
+                        const int j0 = __ffs(mv) - 1;
+                        mv &= mv - 1;
+                        const bool two = mv != 0;
+                        const int j1 = two ? __ffs(mv) - 1 : j0;
+                        mv &= mv - 1;
+                        uint2 inc0, inc1;
+                        {
+                            const int pa_j = __shfl_sync(kFull, pa, j0);
+                            const u32 sp_j = __shfl_sync(kFull, sp, j0);
+                            const int qd_j = __shfl_sync(kFull, qd, j0);
+                            const u64 sb_j = __shfl_sync(kFull, sb, j0);
+                            inc0 = visit(sb_j, pa_j, sp_j, qd_j, lane, a.min_baseq, lut_addr);
+                        }
+                        {
+                            const int pa_j = __shfl_sync(kFull, pa, j1);
+                            const u32 sp_j = two ? __shfl_sync(kFull, sp, j1) : 0u;
+                            const int qd_j = __shfl_sync(kFull, qd, j1);
+                            const u64 sb_j = __shfl_sync(kFull, sb, j1);
+                            inc1 = visit(sb_j, pa_j, sp_j, qd_j, lane, a.min_baseq, lut_addr);
+                        }
+                        accf += inc0.x + inc1.x;                                      // pileup.py:88
+                        accr += inc0.y + inc1.y;
+                    }
                 }
-                __syncwarp();
+                if (m_after) break;
+            }
+            spill_packed(cnt, accf, accr);
+
+            // ---- counts of this chunk are final: filter, reduce, write ----
+            const int p = c0 + lane;
+            if (p >= a.P) {                                  // pileup.py:58 end_refpos = min(.., mito_length): padding stays zero
+#pragma unroll
+                for (int k = 0; k < 8; k++) cnt[k] = 0;
+            }
+            u32 cov = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                u32 f = cnt[2 * b], r = cnt[2 * b + 1];
+                const u32 t = f + r;
+                if (a.apply_bias && t > 0) {                 // pileup.py:143-148, IEEE double, strict >
+                    const double bias = (double)max(f, r) / (double)t;
+                    if (bias > a.max_bias) { cnt[2 * b] = 0; cnt[2 * b + 1] = 0; f = 0; r = 0; }
+                }
+                cov += f + r;                                // pileup.py:150
+            }
+            if (cov == 0) { tn5f = 0; tn5r = 0; }            // pileup.py:152-153: dropped with its Tn5 counts
+            else { sum += cov; covered++; maxd = max(maxd, cov); }
+            u32 vals[MGATK_N_PLANES];
+#pragma unroll
+            for (int k = 0; k < 8; k++) vals[k] = cnt[k];
+            vals[8] = tn5f; vals[9] = tn5r; vals[10] = cov;
+#pragma unroll
+            for (int pl = 0; pl < MGATK_N_PLANES; pl++) {
+                u32 v = vals[pl];
+                if (v > 65535u) {                            // writers.py:205-218 saturation; exact value kept aside
+                    const u64 idx = atomicAdd((u64 *)&a.stats->n_overflow, 1ull);
+                    if ((int64_t)idx < a.ovf_cap) {
+                        a.ovf[idx].cell = un.cell;
+                        a.ovf[idx].plane_pos = ((u32)pl << 24) | (u32)p;
+                        a.ovf[idx].value = v;
+                    } else atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_OVERFLOW_CAP);
+                    v = 65535u;
+                }
+                out_cell[(size_t)pl * a.ppad + p] = (uint16_t)v;
             }
         }
-        while (base < T1) {
-            flush_chunk<R>(a, ring, un.cell, base, base < dirty_hi, sum, covered, maxd);
-            base += 64;
-        }
-        __syncwarp();
         // per-cell depth statistics (processors.py:36-39, writers.py:187-193)
         for (int o = 16; o; o >>= 1) {
             sum += __shfl_xor_sync(kFull, sum, o);
@@ -542,7 +613,7 @@ k_pileup(PileupArgs a) {
             atomicAdd(&a.qc[un.cell].covered, covered);
             atomicMax(&a.qc[un.cell].max_depth, maxd);
         }
-        if (extent_err && lane == 0) atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_EXTENT);
+        if (__any_sync(kFull, extent_err) && lane == 0) atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_EXTENT);
     }
 }
 
