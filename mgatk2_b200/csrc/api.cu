@@ -14,8 +14,8 @@ using namespace mgatk;
 
 namespace {
 
-constexpr int kMaxChunks = 148 * 3 * kWarpsPerCta;   // one wave of partition warps at 3 CTAs/SM
-constexpr int kMaxDigitBits = 11;                    // 2048 bins * 4 B * 8 warps = 64 KB of shared memory per CTA
+constexpr int kMaxChunks = 148 * 4;                  // partition CTAs: one wave at 4 CTAs/SM (bounds the open write heads)
+constexpr int kMaxDigitBits = 12;                    // 4096 bins * 4 B = 16 KB of shared memory per CTA
 constexpr int kMaxStages = 16;
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -29,19 +29,13 @@ struct Layout {          // carve-up of the caller's workspace
     size_t recs, mat, part, cell_start, unit_start, units, scalars, total;
 };
 
-int unit_reads_setting() {
-    const char *e = getenv("MGATK_UNIT_READS");
-    int v = e ? atoi(e) : 0;
-    return v > 0 ? v : 768;
-}
-
 bool make_layout(int64_t n, int32_t n_cells, Layout &L) {
     if (n < 0 || n_cells < 0 || n >= (int64_t)0x7fffff00) return false;
     L.n = n; L.n_cells = n_cells;
-    int64_t nch = (n + 1023) / 1024;
+    int64_t nch = (n + 4095) / 4096;
     L.nchunks = (int)(nch < 1 ? 1 : nch > kMaxChunks ? kMaxChunks : nch);
-    L.chunk = ((n + L.nchunks - 1) / L.nchunks + 31) / 32 * 32;
-    if (L.chunk < 32) L.chunk = 32;
+    L.chunk = ((n + L.nchunks - 1) / L.nchunks + kPartThreads - 1) / kPartThreads * kPartThreads;
+    if (L.chunk < kPartThreads) L.chunk = kPartThreads;
     L.ngroups = (L.nchunks + kScanGroup - 1) / kScanGroup;
     int bits = 1;
     while ((1ll << bits) < n_cells) bits++;
@@ -49,7 +43,7 @@ bool make_layout(int64_t n, int32_t n_cells, Layout &L) {
     L.passes = bits <= kMaxDigitBits ? 1 : 2;
     if (L.passes == 1) { L.bits[0] = bits; L.shift[0] = 0; L.bits[1] = 0; L.shift[1] = 0; }
     else { L.bits[0] = (bits + 1) / 2; L.shift[0] = 0; L.bits[1] = bits - L.bits[0]; L.shift[1] = L.bits[0]; }
-    L.unit_reads = unit_reads_setting();
+    L.unit_reads = 32;                                   // lower bound: sizes the unit table for any setting
     L.max_units = (int64_t)n_cells + n / L.unit_reads + 1;
     const int max_bins = 1 << (L.bits[0] > L.bits[1] ? L.bits[0] : L.bits[1]);
     size_t o = 0;
@@ -127,29 +121,41 @@ int partition_pass(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout
                    const int32_t *sorted_pos, u64 *error_bits, int64_t *m_out, const Grouped &dst) {
     const int bins = 1 << L.bits[pass];
     u32 *mat = (u32 *)(ws + L.mat), *part = (u32 *)(ws + L.part);
-    const int grid = (L.nchunks + kWarpsPerCta - 1) / kWarpsPerCta;
-    const size_t smem = (size_t)kWarpsPerCta * bins * 4;
-    CU(cudaFuncSetAttribute(k_hist<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(k_scatter<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_hist<Src><<<grid, kThreads, smem, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, sorted_pos, error_bits);
+    const int grid = L.nchunks;
+    const size_t smem_h = (size_t)bins * 4, smem = ((size_t)bins + 2 * kPartThreads) * 4;
+    k_hist<Src><<<grid, kPartThreads, smem_h, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, sorted_pos, error_bits);
     dim3 sg((bins + 255) / 256, L.ngroups);
     k_scan_group_sums<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part);
     k_scan_bases<<<1, 1024, 0, s>>>(part, L.ngroups, bins, m_out);
     k_scan_apply<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part);
-    k_scatter<Src><<<grid, kThreads, smem, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, dst);
+    k_scatter<Src><<<grid, kPartThreads, smem, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, dst);
     h->launches += 5;
     CU(cudaGetLastError());
     return MGATK_OK;
 }
 
+constexpr int kStageBlobBytes = 32 * 1024;              // staged blob bytes per CTA: 4 CTAs of 8 warps per SM
+
 int launch_pileup(mgatk_handle *h, cudaStream_t s, const PileupArgs &a) {
+    const size_t smem = pileup_smem_bytes(kStageBlobBytes);
+    CU(cudaFuncSetAttribute(k_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup, kThreads, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    k_pileup<<<h->sm_count * per_sm, kThreads, 0, s>>>(a);    // persistent warps pulling units
+    k_pileup<<<h->sm_count * per_sm, kThreads, smem, s>>>(a, kStageBlobBytes);    // persistent CTAs pulling units
     h->launches += 1;
     CU(cudaGetLastError());
     return MGATK_OK;
+}
+
+// reads per unit: what the staging area holds for this batch's average blob size
+int unit_reads_for(const mgatk_batch *b) {
+    const char *e = getenv("MGATK_UNIT_READS");
+    const int v = e ? atoi(e) : 0;
+    if (v > 0) return v < 32 ? 32 : v > kStageReads ? kStageReads : v;
+    const int64_t avg = b->n_records > 0 ? (b->blob_bytes / b->n_records + 15) / 16 * 16 : 96;
+    int64_t k = (int64_t)(0.9 * kStageBlobBytes) / (avg > 16 ? avg : 16);
+    return (int)(k < 64 ? 64 : k > 384 ? 384 : k);
 }
 
 int validate(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, const mgatk_outputs *o) {
@@ -179,6 +185,7 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     Layout L;
     if (!make_layout(b->n_records, p->n_cells, L)) return fail(h, MGATK_ERR_RANGE, "n_records / n_cells outside limits");
     if ((int64_t)L.total > ws_bytes || !ws_v) return fail(h, MGATK_ERR_WORKSPACE, "workspace too small");
+    L.unit_reads = unit_reads_for(b);
     char *ws = (char *)ws_v;
     CU(cudaSetDevice(h->device));
     if (!h->events_ready) {

@@ -6,9 +6,9 @@
 //   2  k_cell_start, k_dedup          stage 2 (dedup, readers.py:118-150) on (cell,start) runs, per-cell
 //                                     n_reads / n_paired (processors.py:33-34), global counters (readers.py:193-199)
 //   3  k_plan*                        cut every cell into position tiles ("units") of bounded read count
-//   4  k_pileup                       stages 3-6: CIGAR walk, base-quality / distance-from-end masks, per-base
-//                                     per-strand counting and Tn5 sites (pileup.py:32-95) gathered per position
-//                                     in registers; strand-bias filter, coverage, Tn5 gating (pileup.py:128-154)
+//   4  k_pileup                       stages 3-6: a CTA stages the reads of a (cell, tile) in shared memory (cp.async);
+//                                     CIGAR walk, base-quality / distance-from-end masks, per-base per-strand counting
+//                                     and Tn5 sites (pileup.py:32-95) gathered per position in registers; strand-bias filter, coverage, Tn5 gating (pileup.py:128-154)
 //                                     and depth statistics in the same pass; planes written once
 //   5  k_base_totals, k_median        reference-allele vote input and median depth (writers.py:187-197,220-222)
 #pragma once
@@ -85,29 +85,27 @@ struct SrcGrouped {       // pass 1 of a two-digit partition: already filtered, 
     __device__ __forceinline__ Item load(int64_t i) const { Item it; it.k = a.key[i]; it.l = a.loc[i]; return it; }
 };
 
-constexpr int kHistAhead = 8;     // 32-record steps loaded before ranking (k_hist)
-constexpr int kScatAhead = 4;     // same for k_scatter (full records)
+constexpr int kPartThreads = 256;  // records per CTA step
+constexpr int kHistAhead = 4;      // steps loaded before counting (k_hist)
 
+// Per-CTA digit histogram of a contiguous chunk of records (order does not matter for counting).
 template <class Src>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kPartThreads)
 k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict__ mat,
        const int32_t *__restrict__ sorted_check_pos, u64 *__restrict__ error_bits) {
     extern __shared__ u32 smem[];
-    const int w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    if (w >= nchunks) return;
-    const int lane = lane_id();
-    u32 *h = smem + (threadIdx.x >> 5) * bins;
-    for (int b = lane; b < bins; b += 32) h[b] = 0;
-    __syncwarp();
+    u32 *h = smem;
+    for (int b = threadIdx.x; b < bins; b += kPartThreads) h[b] = 0;
+    __syncthreads();
     const int64_t n = src.count();
-    int64_t beg = (int64_t)w * chunk, end = beg + chunk;
+    int64_t beg = (int64_t)blockIdx.x * chunk, end = beg + chunk;
     if (end > n) end = n;
     bool unsorted = false;
-    for (int64_t i0 = beg; i0 < end; i0 += 32 * kHistAhead) {
+    for (int64_t i0 = beg + threadIdx.x; i0 < end; i0 += kPartThreads * kHistAhead) {
         int d[kHistAhead];
 #pragma unroll
         for (int k = 0; k < kHistAhead; k++) {
-            const int64_t i = i0 + 32 * k + lane;
+            const int64_t i = i0 + (int64_t)kPartThreads * k;
             d[k] = -1;
             if (i < end) {
                 const int c = src.cell(i);
@@ -116,15 +114,12 @@ k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict
             }
         }
 #pragma unroll
-        for (int k = 0; k < kHistAhead; k++) {
-            const u32 peers = __match_any_sync(kFull, d[k]);
-            if (d[k] >= 0 && lane == __ffs(peers) - 1) h[d[k]] += __popc(peers);
-            __syncwarp();
-        }
+        for (int k = 0; k < kHistAhead; k++) if (d[k] >= 0) atomicAdd(&h[d[k]], 1u);
     }
     if (unsorted) atomicOr(error_bits, (u64)ERR_UNSORTED);
-    u32 *row = mat + (size_t)w * bins;
-    for (int b = lane; b < bins; b += 32) row[b] = h[b];
+    __syncthreads();
+    u32 *row = mat + (size_t)blockIdx.x * bins;
+    for (int b = threadIdx.x; b < bins; b += kPartThreads) row[b] = h[b];
 }
 
 // scan of mat[chunk][bin] in (bin, chunk) order: S1 group sums, S2 bases, S3 in-place exclusive prefixes
@@ -178,44 +173,54 @@ __global__ void k_scan_apply(u32 *__restrict__ mat, int nchunks, int bins, const
     for (int w = w0; w < w1; w++) { u32 v = mat[(size_t)w * bins + b]; mat[(size_t)w * bins + b] = run; run += v; }
 }
 
+// Stable scatter. A CTA walks its chunk in steps of 256 records in BAM order: every thread loads one
+// record (the next step's loads are issued before the current one is ranked), warp 0 turns the 256
+// digits into destination slots against the CTA's running offsets (match_any per 32 records, in
+// order, so ranks follow record order without atomics), then every thread stores its own record.
+// One running-offset table per CTA keeps the number of open write heads small enough for L2 to
+// merge the 16-byte stores into full sectors.
 template <class Src>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kPartThreads)
 k_scatter(Src src, int64_t chunk, int nchunks, int shift, int bins, const u32 *__restrict__ mat, Grouped dst) {
     extern __shared__ u32 smem[];
-    const int w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    if (w >= nchunks) return;
-    const int lane = lane_id();
-    u32 *off = smem + (threadIdx.x >> 5) * bins;
-    const u32 *row = mat + (size_t)w * bins;
-    for (int b = lane; b < bins; b += 32) off[b] = row[b];
-    __syncwarp();
+    u32 *off = smem;                                       // [bins] running destination offsets
+    int *sdig = reinterpret_cast<int *>(smem + bins);      // [256] digit of each record of the step
+    u32 *sslot = smem + bins + kPartThreads;               // [256] destination slot
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const u32 *row = mat + (size_t)blockIdx.x * bins;
+    for (int b = t; b < bins; b += kPartThreads) off[b] = row[b];
     const int64_t n = src.count();
-    int64_t beg = (int64_t)w * chunk, end = beg + chunk;
+    int64_t beg = (int64_t)blockIdx.x * chunk, end = beg + chunk;
     if (end > n) end = n;
     const u32 lt = (1u << lane) - 1;
-    for (int64_t i0 = beg; i0 < end; i0 += 32 * kScatAhead) {
-        Item it[kScatAhead];
+    Item nxt; nxt.k.cell = -1;
+    if (beg + t < end) nxt = src.load(beg + t);
+    for (int64_t i0 = beg; i0 < end; i0 += kPartThreads) {
+        const Item cur = nxt;
+        nxt.k.cell = -1;
+        if (i0 + kPartThreads + t < end) nxt = src.load(i0 + kPartThreads + t);
+        const int c = cur.k.cell;
+        const int d = c >= 0 ? (c >> shift) & (bins - 1) : -1;
+        sdig[t] = d;
+        __syncthreads();
+        if (wid == 0) {
 #pragma unroll
-        for (int k = 0; k < kScatAhead; k++) {
-            const int64_t i = i0 + 32 * k + lane;
-            it[k].k.cell = -1;
-            if (i < end) it[k] = src.load(i);
-        }
-#pragma unroll
-        for (int k = 0; k < kScatAhead; k++) {
-            const int c = it[k].k.cell;
-            const int d = c >= 0 ? (c >> shift) & (bins - 1) : -1;
-            const u32 peers = __match_any_sync(kFull, d);
-            u32 base = 0;
-            if (d >= 0) base = off[d];
-            __syncwarp();
-            if (d >= 0 && lane == __ffs(peers) - 1) off[d] = base + __popc(peers);
-            __syncwarp();
-            if (d >= 0) {
-                const size_t dd = (size_t)base + __popc(peers & lt);
-                dst.key[dd] = it[k].k;                   // one 16-byte and one 8-byte store per record
-                dst.loc[dd] = it[k].l;
+            for (int k = 0; k < kPartThreads / 32; k++) {
+                const int dk = sdig[32 * k + lane];
+                const u32 peers = __match_any_sync(kFull, dk);
+                u32 base = 0;
+                if (dk >= 0) base = off[dk];
+                __syncwarp();
+                if (dk >= 0 && lane == __ffs(peers) - 1) off[dk] = base + __popc(peers);
+                __syncwarp();
+                sslot[32 * k + lane] = base + __popc(peers & lt);
             }
+        }
+        __syncthreads();
+        if (d >= 0) {
+            const size_t dd = sslot[t];
+            dst.key[dd] = cur.k;                           // one 16-byte and one 8-byte store per record
+            dst.loc[dd] = cur.l;
         }
     }
 }
@@ -376,16 +381,17 @@ __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stages 3-6 as a gather. One warp per unit (cell, position tile); the warp walks the tile in chunks
-// of 32 positions, lane = position. For a chunk, the candidate reads are those starting in
-// (chunk - extent, chunk + 32): lanes first take one candidate read each and walk its CIGAR in
-// parallel (pileup.py:52-95) to the aligned block(s) overlapping the chunk; every such block is then
-// broadcast by shuffle and each lane picks the base / quality of its own position, accumulating the
-// eight base x strand counters in registers (byte-packed, spilled every 255 visits). Nothing is
-// shared between warps, so there are no atomics and no shared-memory counters; when the chunk's
-// reads are exhausted the counts are final and the strand-bias filter, coverage, Tn5 gating
-// (pileup.py:128-154) and the depth statistics are applied in registers and the 11 planes are
-// written once.
+// Stages 3-6 as a gather. One CTA per unit (cell, position tile): the records and cigar|seq|qual
+// blobs of the unit's reads are staged once in shared memory with cp.async (L2 -> shared, no L1
+// pollution), then the warps take chunks of 32 positions of the tile, lane = position. For a chunk,
+// the candidate reads are those starting in (chunk - extent, chunk + 32): lanes first take one
+// candidate read each and walk its CIGAR in parallel (pileup.py:52-95) to the aligned block(s)
+// overlapping the chunk; every such block is then broadcast by shuffle and each lane picks the base /
+// quality of its own position from shared memory, accumulating the eight base x strand counters in
+// registers (byte-packed, spilled every 254 visits). Nothing is shared between warps, so there are no
+// atomics on counters; when the chunk's reads are exhausted the counts are final and the strand-bias
+// filter, coverage, Tn5 gating (pileup.py:128-154) and the depth statistics are applied in registers
+// and the 11 planes are written once. Reads beyond the staging capacity are read from global memory.
 // ---------------------------------------------------------------------------------------------
 struct PileupArgs {
     const ReadRec *recs;
@@ -409,7 +415,8 @@ __device__ __forceinline__ void spill_packed(u32 (&cnt)[8], u32 &accf, u32 &accr
 }
 
 // One lane's share of one aligned block: the base and quality at its own position -> (fwd, rev) increment.
-__device__ __forceinline__ uint2 visit(u64 sb, int pa, u32 sp, int qd, int lane, int min_baseq, u32 lut_addr) {
+// Global-memory form (reads whose blob is not staged in shared memory).
+__device__ __forceinline__ uint2 visit_global(u64 sb, int pa, u32 sp, int qd, int lane, int min_baseq, u32 lut_addr) {
     const bool valid = (unsigned)(lane - pa) < (sp & 0xffffu);
     const int q = valid ? lane + qd : 0;                      // pileup.py:75; lanes outside the block read base 0
     const uint8_t *seq = reinterpret_cast<const uint8_t *>(sb & ~(u64)3);
@@ -422,85 +429,173 @@ __device__ __forceinline__ uint2 visit(u64 sb, int pa, u32 sp, int qd, int lane,
     return r;
 }
 
+// Shared-memory form: ss = shared address of the read's SEQ (4-byte aligned) | strand.
+__device__ __forceinline__ uint2 visit_staged(u32 ss, int pa, u32 sp, int qd, int lane, int min_baseq, u32 lut_addr) {
+    const bool valid = (unsigned)(lane - pa) < (sp & 0xffffu);
+    const int q = valid ? lane + qd : 0;
+    const u32 seq = ss & ~3u;
+    u32 by; int ql;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(by) : "r"(seq + (u32)(q >> 1)));
+    asm volatile("ld.shared.s8 %0, [%1];" : "=r"(ql) : "r"(seq + (sp >> 16) + (u32)q));
+    if (!valid || ql < min_baseq) by = 0;
+    const u32 addr = lut_addr + (((ss & 1u) << 12) | (((u32)q & 1u) << 11) | (by << 3));
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+
+__device__ __forceinline__ void cp_async16(u32 dst_shared, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+constexpr int kStageReads = 512;     // reads of a unit whose record (and, space permitting, blob) is staged in shared memory
+constexpr int kStageMaxBlob = 512;   // larger blobs are read from global memory
+constexpr u32 kUnstaged = 0xffffffffu;
+
+// dynamic shared memory of k_pileup: staged records, their blob offsets, the blob bytes
+__host__ __device__ inline size_t pileup_smem_bytes(int blob_bytes) { return (size_t)kStageReads * (sizeof(ReadRec) + 4) + blob_bytes; }
+
 __global__ void __launch_bounds__(kThreads)
-k_pileup(PileupArgs a) {
+k_pileup(PileupArgs a, int blob_cap) {
     // (fwd, rev) byte-packed increments indexed by [strand][q parity][SEQ byte]: the BAM base code
     // 1,2,4,8 = A,C,G,T of the addressed nibble selects byte 0..3, anything else adds nothing
     // (pileup.py:83-86); the pair form lets the visit add to both accumulators without a branch.
     __shared__ uint2 lut[2 * 2 * 256];
+    __shared__ u32 tn5s[kWarpsPerCta][64];                    // per warp: Tn5 hits of the current chunk, [strand][position]
+    __shared__ int s_unit, s_chunk;
+    extern __shared__ __align__(16) uint8_t dyn[];
+    ReadRec *s_rec = reinterpret_cast<ReadRec *>(dyn);                                  // [kStageReads]
+    u32 *s_so = reinterpret_cast<u32 *>(dyn + kStageReads * sizeof(ReadRec));           // [kStageReads] blob offset in s_blob or kUnstaged
+    uint8_t *s_blob = dyn + kStageReads * (sizeof(ReadRec) + 4);                        // [blob_cap]
     for (int e = threadIdx.x; e < 1024; e += blockDim.x) {
         const int by = e & 255, odd = (e >> 8) & 1, st = e >> 9;
         const int n = odd ? (by & 15) : (by >> 4);
         const u32 inc = n == 1 ? 1u : n == 2 ? 1u << 8 : n == 4 ? 1u << 16 : n == 8 ? 1u << 24 : 0u;
         lut[e] = st ? make_uint2(0u, inc) : make_uint2(inc, 0u);
     }
-    __syncthreads();
+    for (int e = threadIdx.x; e < kWarpsPerCta * 64; e += blockDim.x) (&tn5s[0][0])[e] = 0;
     const u32 lut_addr = (u32)__cvta_generic_to_shared(lut);
-    const int lane = lane_id();
+    const u32 blob_addr = (u32)__cvta_generic_to_shared(s_blob);
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
+    u32 *my_tn5 = tn5s[wid];
     const int n_units = *a.n_units;
     const int q_lo = a.dist > 0 ? a.dist : 0;                // pileup.py:67-72
     for (;;) {
-        int u = 0;
-        if (lane == 0) u = atomicAdd(a.work_counter, 1);
-        u = __shfl_sync(kFull, u, 0);
+        __syncthreads();                                     // previous unit fully consumed (also covers the table init)
+        if (threadIdx.x == 0) { s_unit = atomicAdd(a.work_counter, 1); s_chunk = 0; }
+        __syncthreads();
+        const int u = s_unit;
         if (u >= n_units) break;
         const Unit un = a.units[u];
-        int ra = un.rbeg;
+        const int n_reads = un.rend - un.rbeg;
+        const int ns = min(n_reads, kStageReads);            // reads with a staged record
+
+        // ---- stage: records, then blob offsets (warp 0 scans the sizes), then the blobs with cp.async ----
+        for (int j = threadIdx.x; j < ns; j += kThreads) s_rec[j] = a.recs[un.rbeg + j];
+        __syncthreads();
+        if (wid == 0) {
+            u32 carry = 0;
+            for (int j0 = 0; j0 < ns; j0 += 32) {
+                const int j = j0 + lane;
+                u32 sz = 0;
+                if (j < ns) {
+                    const ReadRec rr = s_rec[j];
+                    const int L = rr.len & 0xffff, nbytes = 4 * (int)(rr.len >> 16) + ((L + 1) >> 1) + L;
+                    if ((rr.flags & GF_PROCESS) && nbytes <= kStageMaxBlob) sz = (u32)((nbytes + 15) & ~15);
+                }
+                u32 incl = sz;
+                for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+                const u32 start = carry + incl - sz;
+                if (j < ns) s_so[j] = (sz && start + sz <= (u32)blob_cap) ? start : (u32)kUnstaged;
+                carry += __shfl_sync(kFull, incl, 31);
+            }
+        }
+        __syncthreads();
+        for (int j = wid; j < ns; j += kWarpsPerCta) {       // one 16-byte cp.async per lane and blob
+            const u32 so = s_so[j];
+            if (so == kUnstaged) continue;
+            const ReadRec rr = s_rec[j];
+            const int L = rr.len & 0xffff, nbytes = 4 * (int)(rr.len >> 16) + ((L + 1) >> 1) + L;
+            if (lane * 16 < nbytes) cp_async16(blob_addr + so + lane * 16, a.blob + 16 * (size_t)rr.off + lane * 16);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+
+        // ---- chunks of 32 positions, handed out to the warps ----
         u64 sum = 0; u32 covered = 0, maxd = 0;
         bool extent_err = false;
         uint16_t *out_cell = a.planes + (size_t)un.cell * MGATK_N_PLANES * a.ppad;
-
-        for (int c0 = un.t0; c0 < un.t1; c0 += 32) {
-            const int c1 = c0 + 32;
-            u32 cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            u32 accf = 0, accr = 0, tn5f = 0, tn5r = 0;
-            int nacc = 0;
+        const int n_chunks = (un.t1 - un.t0) >> 5;
+        for (;;) {
+            int ch = 0;
+            if (lane == 0) ch = atomicAdd(&s_chunk, 1);
+            ch = __shfl_sync(kFull, ch, 0);
+            if (ch >= n_chunks) break;
+            const int c0 = un.t0 + 32 * ch, c1 = c0 + 32;
             const int skip_le = c0 - a.extent;               // reads starting at or before this cannot reach the chunk
-            bool prefix = true;
-            for (int r = ra; r < un.rend; r += 32) {
-                const int i = r + lane;
-                ReadRec rr; rr.pos = 0x7fffffff; rr.off = 0; rr.len = 0; rr.flags = 0;
-                if (i < un.rend) rr = a.recs[i];             // one 16-byte load per candidate
-                const int pos = rr.pos;
-                const bool before = pos <= skip_le;
-                const u32 m_after = __ballot_sync(kFull, pos >= c1);
-                if (prefix) {                                // reads are sorted by start: "before" is a prefix
-                    const int nb = __popc(__ballot_sync(kFull, before));
-                    ra += nb;
-                    prefix = nb == 32;
+            // first candidate: reads are sorted by start; two 32-way probes over the unit's reads
+            int ra;
+            {
+                const int step = (n_reads + 31) >> 5;
+                int j = lane * step;
+                int pj = 0x7fffffff;
+                if (j < n_reads) pj = j < ns ? s_rec[j].pos : a.recs[un.rbeg + j].pos;
+                const int seg = __popc(__ballot_sync(kFull, pj <= skip_le));      // probes <= skip_le form a prefix
+                const int base = seg ? (seg - 1) * step : 0;
+                j = base + lane;
+                int cntb = 0;
+                for (int k = 0; k < step; k += 32) {
+                    const int jj = j + k;
+                    int pp = 0x7fffffff;
+                    if (jj < n_reads && jj < base + step) pp = jj < ns ? s_rec[jj].pos : a.recs[un.rbeg + jj].pos;
+                    cntb += __popc(__ballot_sync(kFull, pp <= skip_le));
                 }
-                const bool live = pos < c1 && (rr.flags & GF_PROCESS);   // implies i < rend
-                const bool cand = live && !before;
-                const bool chk = live && (pos >= c0 || c0 == un.t0);     // once per read and unit: verify the declared extent
+                ra = seg ? base + cntb : 0;
+            }
+
+            u32 cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            u32 accf = 0, accr = 0;
+            int nacc = 0;
+            bool any_tn5 = false;
+            for (int r = ra; r < n_reads; r += 32) {
+                const int j = r + lane;
+                ReadRec rr; rr.pos = 0x7fffffff; rr.off = 0; rr.len = 0; rr.flags = 0;
+                u32 so = kUnstaged;
+                if (j < ns) { rr = s_rec[j]; so = s_so[j]; }
+                else if (j < n_reads) rr = a.recs[un.rbeg + j];
+                const int pos = rr.pos;
+                const u32 m_after = __ballot_sync(kFull, pos >= c1);
+                const bool cand = pos < c1 && pos > skip_le && (rr.flags & GF_PROCESS);   // implies j < n_reads
+                const bool chk = cand && (pos >= c0 || ch == 0);           // once per read and unit: verify the declared extent
                 const u32 off = rr.off, ln = rr.len;
                 const int strand = (rr.flags & GF_STRAND) ? 1 : 0;
                 const int L = ln & 0xffff, ncig = ln >> 16;
+                const bool staged = so != kUnstaged;
+                const u32 sb_addr = blob_addr + (staged ? so : 0u);         // shared address of the staged blob
                 const u32 *cig = reinterpret_cast<const u32 *>(a.blob + 16 * (size_t)off);
-                const int t5 = strand ? pos + L - 1 : pos;   // pileup.py:43-50
                 if (chk) {
-                    const int nbytes = 4 * ncig + ((L + 1) >> 1) + L;  // pull the whole blob towards L1 once
-                    for (int o = 32; o < nbytes && o < 512; o += 32)
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(cig) + o));
                     if (L > a.extent) extent_err = true;
                     int span = 0;
                     for (int ci = 0; ci < ncig; ci++) {
-                        const u32 w = __ldg(cig + ci);
+                        u32 w;
+                        if (staged) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sb_addr + 4 * ci));
+                        else w = __ldg(cig + ci);
                         const int op = w & 15;
                         if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += min((int)(w >> 4), kOpCap);
                         if (span > a.extent) { extent_err = true; break; }
                     }
                 }
-                // Tn5 sites falling into this chunk
-                u32 mt = __ballot_sync(kFull, cand && t5 >= c0 && t5 < c1 && t5 < a.P);
-                while (mt) {
-                    const int j = __ffs(mt) - 1;
-                    mt &= mt - 1;
-                    const int x = __shfl_sync(kFull, t5, j) - c0;
-                    const int s = __shfl_sync(kFull, strand, j);
-                    if (lane == x) { if (s) tn5r++; else tn5f++; }
-                }
+                // Tn5 site (pileup.py:43-50): reverse = start + len(SEQ) - 1, forward = start
+                const int t5 = strand ? pos + L - 1 : pos;
+                const bool hit = cand && t5 >= c0 && t5 < c1 && t5 < a.P;
+                if (hit) atomicAdd(&my_tn5[(strand << 5) + (t5 - c0)], 1u);
+                any_tn5 |= __any_sync(kFull, hit);
                 // aligned blocks overlapping this chunk; a read can contribute several (indels), one per round
                 const int q_hi = a.dist > 0 ? L - a.dist : L;
+                const u64 sb = (u64)(a.blob + 16 * (size_t)off + 4 * ncig) | (u64)strand;
+                const u32 ss = (sb_addr + 4 * ncig) | (u32)strand;
+                const u32 sp_hi = (u32)((L + 1) >> 1) << 16;
                 int ci = 0, ref = pos, qp = 0;
                 bool has = cand;
                 for (;;) {
@@ -508,7 +603,9 @@ k_pileup(PileupArgs a) {
                     bool blk = false;
                     if (has) {
                         while (ci < ncig) {
-                            const u32 w = __ldg(cig + ci);
+                            u32 w;
+                            if (staged) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sb_addr + 4 * ci));
+                            else w = __ldg(cig + ci);
                             const int op = w & 15;
                             const int n = min((int)(w >> 4), kOpCap);
                             ci++;
@@ -525,40 +622,40 @@ k_pileup(PileupArgs a) {
                             else if (op == 4) qp = min(qp + n, kOpCap);      // pileup.py:94-95; I, H, P: nothing (sic)
                             if (ref >= c1) { ci = ncig; break; }             // blocks only move right
                         }
-                        has = blk;
+                        has = blk && ci < ncig;
                     }
-                    u32 mv = __ballot_sync(kFull, blk);
-                    if (!mv) break;
+                    const u32 m_blk = __ballot_sync(kFull, blk);
+                    if (!m_blk) break;
                     // owner lanes publish: first position (chunk relative), span | qual offset, q - lane, SEQ address | strand
                     const int qd = q0 - pa;
-                    const u32 sp = (u32)span | ((u32)((L + 1) >> 1) << 16);
-                    const u64 sb = (u64)(a.blob + 16 * (size_t)off + 4 * ncig) | (u64)strand;
-                    if (nacc + __popc(mv) > 255) { spill_packed(cnt, accf, accr); nacc = 0; }
-                    nacc += __popc(mv);
-                    while (mv) {                              // two visits in flight
+                    const u32 sp = blk ? ((u32)span | sp_hi) : 0u;
+                    const int nv = __popc(m_blk);
+                    if (nacc + nv > 254) { spill_packed(cnt, accf, accr); nacc = 0; }
+                    nacc += nv;
+                    u32 mv = __ballot_sync(kFull, blk && staged);
+                    u32 mg = m_blk & ~mv;
+                    while (mv) {                                             // two visits in flight
                         const int j0 = __ffs(mv) - 1;
                         mv &= mv - 1;
-                        const bool two = mv != 0;
-                        const int j1 = two ? __ffs(mv) - 1 : j0;
+                        const int j1 = mv ? __ffs(mv) - 1 : j0;
+                        const u32 keep1 = mv ? ~0u : 0u;
                         mv &= mv - 1;
-                        uint2 inc0, inc1;
-                        {
-                            const int pa_j = __shfl_sync(kFull, pa, j0);
-                            const u32 sp_j = __shfl_sync(kFull, sp, j0);
-                            const int qd_j = __shfl_sync(kFull, qd, j0);
-                            const u64 sb_j = __shfl_sync(kFull, sb, j0);
-                            inc0 = visit(sb_j, pa_j, sp_j, qd_j, lane, a.min_baseq, lut_addr);
-                        }
-                        {
-                            const int pa_j = __shfl_sync(kFull, pa, j1);
-                            const u32 sp_j = two ? __shfl_sync(kFull, sp, j1) : 0u;
-                            const int qd_j = __shfl_sync(kFull, qd, j1);
-                            const u64 sb_j = __shfl_sync(kFull, sb, j1);
-                            inc1 = visit(sb_j, pa_j, sp_j, qd_j, lane, a.min_baseq, lut_addr);
-                        }
-                        accf += inc0.x + inc1.x;                                      // pileup.py:88
-                        accr += inc0.y + inc1.y;
+                        const uint2 i0 = visit_staged(__shfl_sync(kFull, ss, j0), __shfl_sync(kFull, pa, j0), __shfl_sync(kFull, sp, j0),
+                                                      __shfl_sync(kFull, qd, j0), lane, a.min_baseq, lut_addr);
+                        const uint2 i1 = visit_staged(__shfl_sync(kFull, ss, j1), __shfl_sync(kFull, pa, j1), __shfl_sync(kFull, sp, j1) & keep1,
+                                                      __shfl_sync(kFull, qd, j1), lane, a.min_baseq, lut_addr);
+                        accf += i0.x + i1.x;                                 // pileup.py:88
+                        accr += i0.y + i1.y;
                     }
+                    while (mg) {                                             // blobs that did not fit the staging area
+                        const int j0 = __ffs(mg) - 1;
+                        mg &= mg - 1;
+                        const uint2 i0 = visit_global(__shfl_sync(kFull, sb, j0), __shfl_sync(kFull, pa, j0), __shfl_sync(kFull, sp, j0),
+                                                      __shfl_sync(kFull, qd, j0), lane, a.min_baseq, lut_addr);
+                        accf += i0.x;
+                        accr += i0.y;
+                    }
+                    if (!__any_sync(kFull, has)) break;
                 }
                 if (m_after) break;
             }
@@ -566,41 +663,50 @@ k_pileup(PileupArgs a) {
 
             // ---- counts of this chunk are final: filter, reduce, write ----
             const int p = c0 + lane;
+            u32 tn5f = 0, tn5r = 0;
+            if (any_tn5) {                                   // warp-uniform
+                __syncwarp();
+                tn5f = my_tn5[lane]; tn5r = my_tn5[32 + lane];
+                my_tn5[lane] = 0; my_tn5[32 + lane] = 0;
+                __syncwarp();
+            }
             if (p >= a.P) {                                  // pileup.py:58 end_refpos = min(.., mito_length): padding stays zero
 #pragma unroll
                 for (int k = 0; k < 8; k++) cnt[k] = 0;
             }
-            u32 cov = 0;
+            if (a.apply_bias) {
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                u32 f = cnt[2 * b], r = cnt[2 * b + 1];
-                const u32 t = f + r;
-                if (a.apply_bias && t > 0) {                 // pileup.py:143-148, IEEE double, strict >
-                    const double bias = (double)max(f, r) / (double)t;
-                    if (bias > a.max_bias) { cnt[2 * b] = 0; cnt[2 * b + 1] = 0; f = 0; r = 0; }
+                for (int b = 0; b < 4; b++) {
+                    const u32 f = cnt[2 * b], r = cnt[2 * b + 1], t = f + r;
+                    if (t > 0) {                             // pileup.py:143-148, IEEE double, strict >
+                        const double bias = (double)max(f, r) / (double)t;
+                        if (bias > a.max_bias) { cnt[2 * b] = 0; cnt[2 * b + 1] = 0; }
+                    }
                 }
-                cov += f + r;                                // pileup.py:150
             }
+            const u32 cov = ((cnt[0] + cnt[1]) + (cnt[2] + cnt[3])) + ((cnt[4] + cnt[5]) + (cnt[6] + cnt[7]));  // pileup.py:150
             if (cov == 0) { tn5f = 0; tn5r = 0; }            // pileup.py:152-153: dropped with its Tn5 counts
             else { sum += cov; covered++; maxd = max(maxd, cov); }
             u32 vals[MGATK_N_PLANES];
 #pragma unroll
             for (int k = 0; k < 8; k++) vals[k] = cnt[k];
             vals[8] = tn5f; vals[9] = tn5r; vals[10] = cov;
+            if (max(max(cov, tn5f), tn5r) > 65535u) {        // rare: writers.py:205-218 saturation; exact value kept aside
 #pragma unroll
-            for (int pl = 0; pl < MGATK_N_PLANES; pl++) {
-                u32 v = vals[pl];
-                if (v > 65535u) {                            // writers.py:205-218 saturation; exact value kept aside
-                    const u64 idx = atomicAdd((u64 *)&a.stats->n_overflow, 1ull);
-                    if ((int64_t)idx < a.ovf_cap) {
-                        a.ovf[idx].cell = un.cell;
-                        a.ovf[idx].plane_pos = ((u32)pl << 24) | (u32)p;
-                        a.ovf[idx].value = v;
-                    } else atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_OVERFLOW_CAP);
-                    v = 65535u;
+                for (int pl = 0; pl < MGATK_N_PLANES; pl++) {
+                    if (vals[pl] > 65535u) {
+                        const u64 idx = atomicAdd((u64 *)&a.stats->n_overflow, 1ull);
+                        if ((int64_t)idx < a.ovf_cap) {
+                            a.ovf[idx].cell = un.cell;
+                            a.ovf[idx].plane_pos = ((u32)pl << 24) | (u32)p;
+                            a.ovf[idx].value = vals[pl];
+                        } else atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_OVERFLOW_CAP);
+                        vals[pl] = 65535u;
+                    }
                 }
-                out_cell[(size_t)pl * a.ppad + p] = (uint16_t)v;
             }
+#pragma unroll
+            for (int pl = 0; pl < MGATK_N_PLANES; pl++) out_cell[(size_t)pl * a.ppad + p] = (uint16_t)vals[pl];
         }
         // per-cell depth statistics (processors.py:36-39, writers.py:187-193)
         for (int o = 16; o; o >>= 1) {
