@@ -63,7 +63,7 @@ def algorithmic_bytes(batch, n_cells, P=16569):
 
 def default_params(n_cells, extent):
     from mgatk2_b200._lib import ParamsC
-    return ParamsC(20, 30, 5, 0, 1.0, 1, 16569, n_cells, extent)
+    return ParamsC(20, 30, 5, 0, 1.0, 1, 16569, n_cells, extent, 0)
 
 
 # --------------------------------------------------------------------------- CPU arm

@@ -88,7 +88,13 @@ typedef struct mgatk_params {
     int32_t n_cells;             /* whitelist length; bc_idx in [0,n_cells) or -1              */
     int32_t max_read_extent;     /* upper bound on max(reference span, l_seq) over the batch;
                                     verified on the device (MGATK_ERR_EXTENT)                  */
+    int32_t flags;               /* MGATK_FLAG_*                                               */
 } mgatk_params;
+
+/* generate_pileup() without filter_strand_bias(): no strand-bias zeroing and Tn5 counts are
+ * kept at positions without coverage, i.e. the dict PileupGenerator.generate_pileup returns
+ * (pileup.py:100-124) before pileup.py:128-154 is applied. */
+#define MGATK_FLAG_RAW_PILEUP 1
 
 /* ---- one batch of records, structure-of-arrays, BAM (coordinate) order ---- */
 /* One entry per record returned by fetch(chrM) (readers.py:87-93), i.e. also
@@ -176,6 +182,12 @@ int mgatk_pileup_device(mgatk_handle *h, const mgatk_params *params,
                         void *workspace_dev, int64_t workspace_bytes, void *stream);
 
 int mgatk_check_stats(const mgatk_stats *stats_host);
+
+/* PileupGenerator.filter_strand_bias (pileup.py:128-154) on raw planes, in place:
+ * planes_dev is [n_cells][MGATK_N_PLANES][MGATK_POS_PAD(P)] as written with MGATK_FLAG_RAW_PILEUP
+ * (values above 65535 are not representable here; use the fused path for those). */
+int mgatk_filter_strand_bias_device(mgatk_handle *h, uint16_t *planes_dev, int32_t n_cells, int32_t mito_length,
+                                    double max_strand_bias, void *stream);
 
 /* Same, but batch and outputs are HOST buffers (pinned for full speed): H2D copy,
  * kernels, D2H copy, synchronise. Device buffers are cached inside the handle. */

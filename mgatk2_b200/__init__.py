@@ -1,0 +1,31 @@
+"""mgatk2_b200 — B200-native per-cell chrM pileup hot path of ollieeknight/mgatk2.
+
+The package mirrors the reference's seam (`BAMReader`, `CellProcessor`, `process_barcode_worker`,
+`PileupGenerator`, `PipelineConfig`) over hand-written sm_100a kernels behind a C ABI
+(include/mgatk2_b200.h). Importing the package does not need a GPU; constructing a `PileupEngine` does.
+"""
+from .batch import ReadBatch
+from .config import DeduplicationConfig, PerformanceConfig, PipelineConfig, QualityThresholds
+from .exceptions import (BAMReadError, InvalidInputError, MgatkError, NoBarcodeTagsError, PileupKernelError,
+                         ProcessingError)
+
+__all__ = ["ReadBatch", "PipelineConfig", "QualityThresholds", "DeduplicationConfig", "PerformanceConfig",
+           "MgatkError", "InvalidInputError", "ProcessingError", "BAMReadError", "NoBarcodeTagsError",
+           "PileupKernelError", "BAMReader", "CellProcessor", "process_barcode_worker", "PileupGenerator",
+           "PileupEngine"]
+
+
+def __getattr__(name):        # heavy pieces (ctypes library, torch) load on first use
+    if name == "BAMReader":
+        from .readers import BAMReader
+        return BAMReader
+    if name in ("CellProcessor", "process_barcode_worker"):
+        from . import processors
+        return getattr(processors, name)
+    if name == "PileupGenerator":
+        from .pileup import PileupGenerator
+        return PileupGenerator
+    if name == "PileupEngine":
+        from .engine import PileupEngine
+        return PileupEngine
+    raise AttributeError(name)

@@ -13,10 +13,12 @@ LIB_PATH = os.path.join(HERE, "libmgatk2_b200.so")
 EXPORTS = (
     "mgatk_abi_version", "mgatk_status_string", "mgatk_create", "mgatk_destroy", "mgatk_last_error",
     "mgatk_workspace_bytes", "mgatk_pileup_device", "mgatk_check_stats", "mgatk_pileup_host",
+    "mgatk_filter_strand_bias_device",
     "mgatk_last_launch_count", "mgatk_last_stage_times",
 )
 
 N_PLANES = 11
+FLAG_RAW_PILEUP = 1
 ABI_VERSION = 1
 
 
@@ -26,6 +28,7 @@ class ParamsC(ctypes.Structure):
         ("min_distance_from_end", ctypes.c_int32), ("dedup_mode", ctypes.c_int32),
         ("max_strand_bias", ctypes.c_double), ("min_reads_per_cell", ctypes.c_int32),
         ("mito_length", ctypes.c_int32), ("n_cells", ctypes.c_int32), ("max_read_extent", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
     ]
 
 
@@ -66,6 +69,8 @@ def load():
     lib.mgatk_pileup_device.argtypes = [ctypes.c_void_p, ctypes.POINTER(ParamsC), ctypes.POINTER(MgatkBatchC),
                                         ctypes.POINTER(OutputsC), ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     lib.mgatk_check_stats.argtypes = [ctypes.c_void_p]
+    lib.mgatk_filter_strand_bias_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                                    ctypes.c_double, ctypes.c_void_p]
     lib.mgatk_pileup_host.argtypes = [ctypes.c_void_p, ctypes.POINTER(ParamsC), ctypes.POINTER(MgatkBatchC),
                                       ctypes.POINTER(OutputsC)]
     lib.mgatk_last_launch_count.restype = ctypes.c_int64

@@ -70,9 +70,9 @@ class PipelineConfig:
         self.performance = PerformanceConfig(self.n_cores, self.worker_batch_size or self.n_cores,
                                              self.io_batch_size or 100, self.max_memory_gb, self.sequential)
 
-    def to_params(self, n_cells: int, max_read_extent: int):
+    def to_params(self, n_cells: int, max_read_extent: int, flags: int = 0):
         from ._lib import ParamsC
         q = self.quality
         return ParamsC(int(q.min_baseq), int(q.min_mapq), int(q.min_distance_from_end), int(self.dedup.mode),
                        float(q.max_strand_bias), int(self.min_reads_per_cell), int(self.mito_length),
-                       int(n_cells), int(max_read_extent))
+                       int(n_cells), int(max_read_extent), int(flags))

@@ -251,7 +251,8 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     a.planes = o->planes; a.qc = o->cell_qc; a.stats = o->stats; a.ovf = o->overflow; a.ovf_cap = o->overflow_capacity;
     a.P = P; a.ppad = ppad; a.min_baseq = p->min_baseq; a.dist = p->min_distance_from_end;
     a.max_bias = p->max_strand_bias;
-    a.apply_bias = !(p->max_strand_bias >= 1.0);          // max(f,r)/total never exceeds 1.0
+    a.raw = (p->flags & MGATK_FLAG_RAW_PILEUP) ? 1 : 0;
+    a.apply_bias = !a.raw && !(p->max_strand_bias >= 1.0);   // max(f,r)/total never exceeds 1.0
     a.extent = p->max_read_extent;
     rc = launch_pileup(h, s, a);
     if (rc) return rc;
@@ -342,6 +343,20 @@ int mgatk_pileup_device(mgatk_handle *h, const mgatk_params *params, const mgatk
     if (!h) return MGATK_ERR_BAD_ARG;
     h->err.clear();
     return run_device(h, params, batch_dev, out_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+int mgatk_filter_strand_bias_device(mgatk_handle *h, uint16_t *planes_dev, int32_t n_cells, int32_t mito_length,
+                                    double max_strand_bias, void *stream) {
+    if (!h) return MGATK_ERR_BAD_ARG;
+    h->err.clear();
+    if (!planes_dev || n_cells < 0 || mito_length <= 0) return fail(h, MGATK_ERR_BAD_ARG, "bad argument");
+    if (n_cells == 0) return MGATK_OK;
+    CU(cudaSetDevice(h->device));
+    dim3 grid((mito_length + 255) / 256, n_cells);
+    k_filter_planes<<<grid, 256, 0, (cudaStream_t)stream>>>(planes_dev, n_cells, mito_length, (int)MGATK_POS_PAD(mito_length), max_strand_bias);
+    h->launches = 1;
+    CU(cudaGetLastError());
+    return MGATK_OK;
 }
 
 int mgatk_check_stats(const mgatk_stats *st) {

@@ -399,7 +399,7 @@ struct PileupArgs {
     const Unit *units; const int32_t *n_units; int32_t *work_counter;
     uint16_t *planes; mgatk_cell_qc *qc; mgatk_stats *stats;
     mgatk_overflow *ovf; int64_t ovf_cap;
-    int P, ppad, min_baseq, dist, apply_bias, extent;
+    int P, ppad, min_baseq, dist, apply_bias, extent, raw;
     double max_bias;
 };
 
@@ -464,6 +464,7 @@ k_pileup(PileupArgs a, int blob_cap) {
     __shared__ uint2 lut[2 * 2 * 256];
     __shared__ u32 tn5s[kWarpsPerCta][64];                    // per warp: Tn5 hits of the current chunk, [strand][position]
     __shared__ int s_unit, s_chunk;
+    __shared__ u32 s_wsum[2 * kWarpsPerCta];
     extern __shared__ __align__(16) uint8_t dyn[];
     ReadRec *s_rec = reinterpret_cast<ReadRec *>(dyn);                                  // [kStageReads]
     u32 *s_so = reinterpret_cast<u32 *>(dyn + kStageReads * sizeof(ReadRec));           // [kStageReads] blob offset in s_blob or kUnstaged
@@ -491,33 +492,38 @@ k_pileup(PileupArgs a, int blob_cap) {
         const int n_reads = un.rend - un.rbeg;
         const int ns = min(n_reads, kStageReads);            // reads with a staged record
 
-        // ---- stage: records, then blob offsets (warp 0 scans the sizes), then the blobs with cp.async ----
-        for (int j = threadIdx.x; j < ns; j += kThreads) s_rec[j] = a.recs[un.rbeg + j];
-        __syncthreads();
-        if (wid == 0) {
-            u32 carry = 0;
-            for (int j0 = 0; j0 < ns; j0 += 32) {
-                const int j = j0 + lane;
-                u32 sz = 0;
-                if (j < ns) {
-                    const ReadRec rr = s_rec[j];
-                    const int L = rr.len & 0xffff, nbytes = 4 * (int)(rr.len >> 16) + ((L + 1) >> 1) + L;
-                    if ((rr.flags & GF_PROCESS) && nbytes <= kStageMaxBlob) sz = (u32)((nbytes + 15) & ~15);
-                }
-                u32 incl = sz;
-                for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
-                const u32 start = carry + incl - sz;
-                if (j < ns) s_so[j] = (sz && start + sz <= (u32)blob_cap) ? start : (u32)kUnstaged;
-                carry += __shfl_sync(kFull, incl, 31);
+        // ---- stage: every thread owns up to two reads (j = tid, tid + 256): record to shared memory, blob
+        //      offset from a block-wide exclusive scan of the blob sizes, blob with 16-byte cp.async ----
+        ReadRec rr2[2];
+        u32 sz2[2], incl2[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int j = threadIdx.x + k * kThreads;
+            sz2[k] = 0;
+            if (j < ns) {
+                rr2[k] = a.recs[un.rbeg + j];
+                s_rec[j] = rr2[k];
+                const int L = rr2[k].len & 0xffff, nbytes = 4 * (int)(rr2[k].len >> 16) + ((L + 1) >> 1) + L;
+                if ((rr2[k].flags & GF_PROCESS) && nbytes <= kStageMaxBlob) sz2[k] = (u32)((nbytes + 15) & ~15);
             }
+            u32 incl = sz2[k];
+            for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+            incl2[k] = incl;
+            if (lane == 31) s_wsum[k * kWarpsPerCta + wid] = incl;
         }
         __syncthreads();
-        for (int j = wid; j < ns; j += kWarpsPerCta) {       // one 16-byte cp.async per lane and blob
-            const u32 so = s_so[j];
-            if (so == kUnstaged) continue;
-            const ReadRec rr = s_rec[j];
-            const int L = rr.len & 0xffff, nbytes = 4 * (int)(rr.len >> 16) + ((L + 1) >> 1) + L;
-            if (lane * 16 < nbytes) cp_async16(blob_addr + so + lane * 16, a.blob + 16 * (size_t)rr.off + lane * 16);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int j = threadIdx.x + k * kThreads;
+            u32 before = 0;                                  // blob bytes of all reads in earlier warps / the earlier half
+            for (int w = 0; w < k * kWarpsPerCta + wid; w++) before += s_wsum[w];
+            const u32 start = before + incl2[k] - sz2[k];
+            const bool st = sz2[k] && start + sz2[k] <= (u32)blob_cap;
+            if (j < ns) s_so[j] = st ? start : (u32)kUnstaged;
+            if (st) {
+                const uint8_t *src = a.blob + 16 * (size_t)rr2[k].off;
+                for (u32 o = 0; o < sz2[k]; o += 16) cp_async16(blob_addr + start + o, src + o);
+            }
         }
         cp_async_wait_all();
         __syncthreads();
@@ -685,12 +691,13 @@ k_pileup(PileupArgs a, int blob_cap) {
                 }
             }
             const u32 cov = ((cnt[0] + cnt[1]) + (cnt[2] + cnt[3])) + ((cnt[4] + cnt[5]) + (cnt[6] + cnt[7]));  // pileup.py:150
-            if (cov == 0) { tn5f = 0; tn5r = 0; }            // pileup.py:152-153: dropped with its Tn5 counts
+            if (cov == 0) { if (!a.raw) { tn5f = 0; tn5r = 0; } }   // pileup.py:152-153: dropped with its Tn5 counts
             else { sum += cov; covered++; maxd = max(maxd, cov); }
             u32 vals[MGATK_N_PLANES];
 #pragma unroll
             for (int k = 0; k < 8; k++) vals[k] = cnt[k];
             vals[8] = tn5f; vals[9] = tn5r; vals[10] = cov;
+            if (p >= a.P) { tn5f = 0; tn5r = 0; }
             if (max(max(cov, tn5f), tn5r) > 65535u) {        // rare: writers.py:205-218 saturation; exact value kept aside
 #pragma unroll
                 for (int pl = 0; pl < MGATK_N_PLANES; pl++) {
@@ -759,6 +766,29 @@ __global__ void k_base_totals_overflow(const mgatk_overflow *__restrict__ ovf, c
         const int pl = ovf[k].plane_pos >> 24, p = ovf[k].plane_pos & 0xffffff;
         if (pl < 8 && p < P) atomicAdd(&totals[(size_t)p * 4 + pl / 2], (u64)(ovf[k].value - 65535u));
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PileupGenerator.filter_strand_bias (pileup.py:128-154) as a stand-alone pass over raw planes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_filter_planes(uint16_t *__restrict__ planes, int n_cells, int P, int ppad, double max_bias) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (p >= P || c >= n_cells) return;
+    uint16_t *row = planes + (size_t)c * MGATK_N_PLANES * ppad + p;
+    u32 cov = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        u32 f = row[(size_t)(2 * b) * ppad], r = row[(size_t)(2 * b + 1) * ppad];
+        const u32 t = f + r;
+        if (t > 0) {
+            const double bias = (double)max(f, r) / (double)t;
+            if (bias > max_bias) { f = 0; r = 0; row[(size_t)(2 * b) * ppad] = 0; row[(size_t)(2 * b + 1) * ppad] = 0; }
+        }
+        cov += f + r;
+    }
+    row[(size_t)MGATK_PLANE_COVERAGE * ppad] = (uint16_t)min(cov, 65535u);
+    if (cov == 0) { row[(size_t)MGATK_PLANE_TN5_FWD * ppad] = 0; row[(size_t)MGATK_PLANE_TN5_REV * ppad] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,119 @@
+"""`BAMReader` — the first call of the drop-in seam (reference src/processing/readers.py:22-201).
+
+Same constructor and `collect_reads_by_barcode() -> (reads_by_barcode, stats)` contract. The reference
+materialises one `SimpleRead` per kept record; here the records stay in a structure-of-arrays batch and
+stages 1-6 run on the GPU inside this call (dedup cannot be separated from the device pipeline).
+`reads_by_barcode` is a read-only mapping barcode -> `CellReads` whose `len()` is the number of kept
+reads, iterated in first-seen (BAM) order like the reference's dict; `CellProcessor` consumes it.
+"""
+from __future__ import annotations
+
+import logging
+from collections.abc import Mapping
+from pathlib import Path
+
+import numpy as np
+
+from .batch import ReadBatch
+from .engine import PileupResult
+from .exceptions import BAMReadError
+from .pileup import get_engine
+
+logger = logging.getLogger(__name__)
+
+
+class CellReads:
+    """Stand-in for the reference's per-barcode list of reads: sized, and carries the device result."""
+
+    __slots__ = ("barcode", "index", "n_reads", "result")
+
+    def __init__(self, barcode: str, index: int, n_reads: int, result: PileupResult):
+        self.barcode, self.index, self.n_reads, self.result = barcode, index, n_reads, result
+
+    def __len__(self):
+        return self.n_reads
+
+    def __bool__(self):
+        return self.n_reads > 0
+
+
+class ReadsByBarcode(Mapping):
+    def __init__(self, barcode_list: list[str], order: np.ndarray, result: PileupResult):
+        self.result = result
+        self._cells = {barcode_list[c]: CellReads(barcode_list[c], int(c), int(result.cell_qc["n_reads"][c]), result)
+                       for c in order.tolist()}
+
+    def __getitem__(self, k):
+        return self._cells[k]
+
+    def __iter__(self):
+        return iter(self._cells)
+
+    def __len__(self):
+        return len(self._cells)
+
+    def pop(self, k, *default):          # the reference's processors pop cells as they go (processors.py:70,125)
+        return self._cells.pop(k, *default)
+
+
+def whitelist_index(barcode_list: list[str]) -> dict[str, int]:
+    """Barcode -> column. Duplicated whitelist entries: the last index wins (writers.py:41)."""
+    return {bc: i for i, bc in enumerate(barcode_list)}
+
+
+class BAMReader:
+    def __init__(self, bam_path: str, config, barcodes, *, barcode_list: list[str] | None = None,
+                 batch: ReadBatch | None = None, device: int = 0):
+        """`barcodes` is the set the reference passes (pipeline.py:80); `barcode_list` (pipeline.barcode_list)
+        fixes the column order. `batch` supplies already-decoded records (tests, synthetic data); without it
+        the BAM at `bam_path` is decoded by `mgatk2_b200.bamio`."""
+        self.bam_path = Path(bam_path)
+        self.config = config
+        self.barcodes = barcodes
+        self.barcode_list = list(barcode_list) if barcode_list is not None else sorted(barcodes)
+        self.device = device
+        self._batch = batch
+        if batch is None and not self.bam_path.exists():
+            raise BAMReadError(str(bam_path), "File does not exist")
+
+    def _load_batch(self) -> ReadBatch:
+        if self._batch is not None:
+            return self._batch
+        from .bamio import read_bam_chrM
+        batch, mito_chr = read_bam_chrM(str(self.bam_path), self.config, whitelist_index(self.barcode_list))
+        if mito_chr != self.config.mito_chr:            # readers.py:43-48
+            logger.info("Using mitochondrial chromosome: %s", mito_chr)
+            self.config.mito_chr = mito_chr
+        return batch
+
+    def collect_reads_by_barcode(self):
+        try:
+            batch = self._load_batch()
+            if not batch.is_sorted():
+                raise ValueError("records are not sorted by reference_start")
+            params = self.config.to_params(len(self.barcode_list), batch.max_read_extent())
+            res = get_engine(self.device).run_host(batch, params, overflow_capacity=1 << 16)
+            if res.stats["n_empty_seq"]:
+                raise ValueError("record without SEQ passed the filters")       # readers.py:157 raises here
+        except BAMReadError:
+            raise
+        except Exception as e:
+            raise BAMReadError(str(self.bam_path), f"Read error: {e}") from e
+
+        # first-seen order of barcodes with kept reads: a barcode's first stage-1 record is never a duplicate
+        ok = ((batch.flag & 0x904) == 0) & (batch.bc_idx >= 0) & (batch.bc_idx < len(self.barcode_list))
+        cells, first = np.unique(batch.bc_idx[ok], return_index=True)
+        order = cells[np.argsort(first, kind="stable")]
+        order = order[res.cell_qc["n_reads"][order] > 0]
+        reads_by_barcode = ReadsByBarcode(self.barcode_list, order, res)
+
+        st = res.stats
+        if not self.config.dedup.skip and st["total_reads"]:                      # readers.py:170-180
+            removed = st["dup_with_length"] if self.config.dedup.use_fragment_length else st["dup_position_only"]
+            logger.info("%d duplicate reads removed (%.1f%%)", removed, removed / st["total_reads"] * 100)
+        logger.info("Kept %s reads from %s barcodes", f"{st['filtered_reads']:,}", f"{len(reads_by_barcode):,}")
+        stats = {"total_reads": st["total_reads"], "filtered_reads": st["filtered_reads"],
+                 "n_barcodes": len(reads_by_barcode),
+                 "duplicate_reads_with_length": st["dup_with_length"],
+                 "duplicate_reads_position_only": st["dup_position_only"]}
+        return reads_by_barcode, stats

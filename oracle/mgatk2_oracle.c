@@ -170,6 +170,7 @@ static void process_cell(job_t *J, int64_t c, uint32_t *base_counts, uint32_t *t
     /* pileup.py:100-124 (sparse dict) + :128-154 (strand filter), done densely:
        an entry exists iff depth>0 or tn5>0; the filter drops entries whose filtered depth is 0. */
     const double max_bias = p->max_strand_bias;
+    const int raw = (p->flags & MGATK_FLAG_RAW_PILEUP) != 0;   /* generate_pileup() only, no filter_strand_bias() */
     uint64_t sum_depth = 0; uint32_t covered = 0, max_depth = 0;
     uint32_t *out_counts = J->o->counts ? J->o->counts + c * P * 8 : NULL;
     uint32_t *out_tn5 = J->o->tn5 ? J->o->tn5 + c * P * 2 : NULL;
@@ -182,7 +183,7 @@ static void process_cell(job_t *J, int64_t c, uint32_t *base_counts, uint32_t *t
             uint32_t total = fwd + rev;
             if (total > 0) {
                 double bias = (double)(fwd > rev ? fwd : rev) / (double)total;
-                if (bias > max_bias) { bc[base * 2] = 0; bc[base * 2 + 1] = 0; }
+                if (!raw && bias > max_bias) { bc[base * 2] = 0; bc[base * 2 + 1] = 0; }
             }
             depth += bc[base * 2] + bc[base * 2 + 1];      /* :150 */
         }
@@ -190,14 +191,14 @@ static void process_cell(job_t *J, int64_t c, uint32_t *base_counts, uint32_t *t
             sum_depth += depth; depth_buf[covered++] = depth;
             if (depth > max_depth) max_depth = depth;
             for (int base = 0; base < 4; base++) bt_local[pos * 4 + base] += (int64_t)bc[base * 2] + bc[base * 2 + 1];
-        } else {
+        } else if (!raw) {
             tn5_cuts[pos * 2] = tn5_cuts[pos * 2 + 1] = 0; /* position dropped with its Tn5 counts */
             memset(bc, 0, 8 * sizeof(uint32_t));
         }
         if (out_cov) out_cov[pos] = depth;
     }
 
-    if (covered == 0) {                                    /* processors.py:30-31 if not pileup: return None */
+    if (covered == 0 && !raw) {                            /* processors.py:30-31 if not pileup: return None */
         /* undo nothing: bt_local only received covered positions */
         return;
     }
@@ -208,8 +209,8 @@ static void process_cell(job_t *J, int64_t c, uint32_t *base_counts, uint32_t *t
     qc->sum_depth = sum_depth;
     qc->covered = covered;
     qc->max_depth = max_depth;
-    qc->median_lo = depth_buf[(covered - 1) / 2];
-    qc->median_hi = depth_buf[covered / 2];
+    qc->median_lo = covered ? depth_buf[(covered - 1) / 2] : 0;
+    qc->median_hi = covered ? depth_buf[covered / 2] : 0;
 }
 
 static void *worker(void *arg) {

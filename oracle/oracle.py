@@ -23,6 +23,7 @@ class ParamsC(ctypes.Structure):
         ("min_distance_from_end", ctypes.c_int32), ("dedup_mode", ctypes.c_int32),
         ("max_strand_bias", ctypes.c_double), ("min_reads_per_cell", ctypes.c_int32),
         ("mito_length", ctypes.c_int32), ("n_cells", ctypes.c_int32), ("max_read_extent", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
     ]
 
 
@@ -69,10 +70,10 @@ class OracleResult:
 
 
 def make_params(n_cells, min_baseq=20, min_mapq=30, min_distance_from_end=5, dedup_mode=0,
-                max_strand_bias=1.0, min_reads_per_cell=1, mito_length=16569, max_read_extent=0) -> ParamsC:
+                max_strand_bias=1.0, min_reads_per_cell=1, mito_length=16569, max_read_extent=0, flags=0) -> ParamsC:
     return ParamsC(int(min_baseq), int(min_mapq), int(min_distance_from_end), int(dedup_mode),
                    float(max_strand_bias), int(min_reads_per_cell), int(mito_length), int(n_cells),
-                   int(max_read_extent))
+                   int(max_read_extent), int(flags))
 
 
 def run_oracle(batch, params: ParamsC, n_threads: int = 1, dense: bool = True) -> OracleResult:

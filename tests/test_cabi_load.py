@@ -31,7 +31,7 @@ def test_struct_sizes():
     from mgatk2_b200._lib import OutputsC, ParamsC
     from mgatk2_b200.batch import MgatkBatchC
     from mgatk2_b200.engine import CELL_QC_DTYPE, OVERFLOW_DTYPE
-    assert ctypes.sizeof(ParamsC) == 40 and ctypes.sizeof(MgatkBatchC) == 88 and ctypes.sizeof(OutputsC) == 48
+    assert ctypes.sizeof(ParamsC) == 48 and ctypes.sizeof(MgatkBatchC) == 88 and ctypes.sizeof(OutputsC) == 48
     assert CELL_QC_DTYPE.itemsize == 32 and OVERFLOW_DTYPE.itemsize == 12
 
 

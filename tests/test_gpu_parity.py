@@ -64,6 +64,7 @@ CASES = {
     "atac70_d0": dict(profile="atac70", n_cells=64, n=80_000, kw=dict(min_distance_from_end=0, max_strand_bias=0.6)),
     "two_pass_partition": dict(profile="atac50", n_cells=5000, n=250_000, kw=dict()),
     "one_cell": dict(profile="atac50", n_cells=1, n=60_000, kw=dict(dedup_mode=1)),
+    "raw_pileup_flag": dict(profile="atac70", n_cells=40, n=30_000, kw=dict(max_strand_bias=0.7, flags=1)),
 }
 
 
