@@ -134,7 +134,7 @@ int partition_pass(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout
     return MGATK_OK;
 }
 
-constexpr int kStageBlobBytes = 32 * 1024;              // staged blob bytes per CTA: 4 CTAs of 8 warps per SM
+constexpr int kStageBlobBytes = 30 * 1024;              // staged blob bytes per CTA: 4 CTAs of 8 warps per SM
 
 int launch_pileup(mgatk_handle *h, cudaStream_t s, const PileupArgs &a) {
     const size_t smem = pileup_smem_bytes(kStageBlobBytes);

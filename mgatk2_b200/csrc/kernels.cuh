@@ -452,6 +452,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 constexpr int kStageReads = 512;     // reads of a unit whose record (and, space permitting, blob) is staged in shared memory
 constexpr int kStageMaxBlob = 512;   // larger blobs are read from global memory
 constexpr u32 kUnstaged = 0xffffffffu;
+constexpr int kSplitChunks = 4;      // units with at most this many chunks split every chunk's reads over several warps
 
 // dynamic shared memory of k_pileup: staged records, their blob offsets, the blob bytes
 __host__ __device__ inline size_t pileup_smem_bytes(int blob_bytes) { return (size_t)kStageReads * (sizeof(ReadRec) + 4) + blob_bytes; }
@@ -464,6 +465,7 @@ k_pileup(PileupArgs a, int blob_cap) {
     __shared__ uint2 lut[2 * 2 * 256];
     __shared__ u32 tn5s[kWarpsPerCta][64];                    // per warp: Tn5 hits of the current chunk, [strand][position]
     __shared__ int s_unit, s_chunk;
+    __shared__ u32 s_scratch[kSplitChunks * 320 + kSplitChunks];   // split mode: partial counts [chunk][10][32], arrival counters
     __shared__ u32 s_wsum[2 * kWarpsPerCta];
     extern __shared__ __align__(16) uint8_t dyn[];
     ReadRec *s_rec = reinterpret_cast<ReadRec *>(dyn);                                  // [kStageReads]
@@ -476,6 +478,7 @@ k_pileup(PileupArgs a, int blob_cap) {
         lut[e] = st ? make_uint2(0u, inc) : make_uint2(inc, 0u);
     }
     for (int e = threadIdx.x; e < kWarpsPerCta * 64; e += blockDim.x) (&tn5s[0][0])[e] = 0;
+    for (int e = threadIdx.x; e < kSplitChunks * 320 + kSplitChunks; e += blockDim.x) s_scratch[e] = 0;
     const u32 lut_addr = (u32)__cvta_generic_to_shared(lut);
     const u32 blob_addr = (u32)__cvta_generic_to_shared(s_blob);
     const int lane = lane_id(), wid = threadIdx.x >> 5;
@@ -533,11 +536,19 @@ k_pileup(PileupArgs a, int blob_cap) {
         bool extent_err = false;
         uint16_t *out_cell = a.planes + (size_t)un.cell * MGATK_N_PLANES * a.ppad;
         const int n_chunks = (un.t1 - un.t0) >> 5;
+        // few chunks (deep cell): every chunk's candidate reads are split over `nparts` warps, partial counts meet
+        // in s_scratch and the warp that arrives last finishes the chunk
+        int nparts = 1;
+        if (n_chunks <= kSplitChunks) while (nparts * 2 * n_chunks <= kWarpsPerCta) nparts *= 2;
+        const int n_items = n_chunks * nparts;
         for (;;) {
-            int ch = 0;
-            if (lane == 0) ch = atomicAdd(&s_chunk, 1);
-            ch = __shfl_sync(kFull, ch, 0);
-            if (ch >= n_chunks) break;
+            int item = 0;
+            if (lane == 0) item = atomicAdd(&s_chunk, 1);
+            item = __shfl_sync(kFull, item, 0);
+            if (item >= n_items) break;
+            const int ch = item / nparts, part = item - ch * nparts;
+            u32 *acc = s_scratch + ch * 320;
+            u32 *tn5_acc = nparts > 1 ? acc + 256 : my_tn5;
             const int c0 = un.t0 + 32 * ch, c1 = c0 + 32;
             const int skip_le = c0 - a.extent;               // reads starting at or before this cannot reach the chunk
             // first candidate: reads are sorted by start; two 32-way probes over the unit's reads
@@ -564,7 +575,7 @@ k_pileup(PileupArgs a, int blob_cap) {
             u32 accf = 0, accr = 0;
             int nacc = 0;
             bool any_tn5 = false;
-            for (int r = ra; r < n_reads; r += 32) {
+            for (int r = ra + 32 * part; r < n_reads; r += 32 * nparts) {
                 const int j = r + lane;
                 ReadRec rr; rr.pos = 0x7fffffff; rr.off = 0; rr.len = 0; rr.flags = 0;
                 u32 so = kUnstaged;
@@ -595,7 +606,7 @@ k_pileup(PileupArgs a, int blob_cap) {
                 // Tn5 site (pileup.py:43-50): reverse = start + len(SEQ) - 1, forward = start
                 const int t5 = strand ? pos + L - 1 : pos;
                 const bool hit = cand && t5 >= c0 && t5 < c1 && t5 < a.P;
-                if (hit) atomicAdd(&my_tn5[(strand << 5) + (t5 - c0)], 1u);
+                if (hit) atomicAdd(&tn5_acc[(strand << 5) + (t5 - c0)], 1u);
                 any_tn5 |= __any_sync(kFull, hit);
                 // aligned blocks overlapping this chunk; a read can contribute several (indels), one per round
                 const int q_hi = a.dist > 0 ? L - a.dist : L;
@@ -666,14 +677,28 @@ k_pileup(PileupArgs a, int blob_cap) {
                 if (m_after) break;
             }
             spill_packed(cnt, accf, accr);
+            if (nparts > 1) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) if (cnt[k]) atomicAdd(&acc[k * 32 + lane], cnt[k]);
+                __threadfence_block();
+                int arrived = 0;
+                if (lane == 0) arrived = atomicAdd(&s_scratch[kSplitChunks * 320 + ch], 1u) + 1;
+                arrived = __shfl_sync(kFull, arrived, 0);
+                if (arrived != nparts) continue;             // another warp finishes this chunk
+                __threadfence_block();
+#pragma unroll
+                for (int k = 0; k < 8; k++) { cnt[k] = *(volatile u32 *)&acc[k * 32 + lane]; acc[k * 32 + lane] = 0; }
+                if (lane == 0) s_scratch[kSplitChunks * 320 + ch] = 0;
+                any_tn5 = true;
+            }
 
             // ---- counts of this chunk are final: filter, reduce, write ----
             const int p = c0 + lane;
             u32 tn5f = 0, tn5r = 0;
             if (any_tn5) {                                   // warp-uniform
                 __syncwarp();
-                tn5f = my_tn5[lane]; tn5r = my_tn5[32 + lane];
-                my_tn5[lane] = 0; my_tn5[32 + lane] = 0;
+                tn5f = *(volatile u32 *)&tn5_acc[lane]; tn5r = *(volatile u32 *)&tn5_acc[32 + lane];
+                tn5_acc[lane] = 0; tn5_acc[32 + lane] = 0;
                 __syncwarp();
             }
             if (p >= a.P) {                                  // pileup.py:58 end_refpos = min(.., mito_length): padding stays zero
@@ -697,7 +722,6 @@ k_pileup(PileupArgs a, int blob_cap) {
 #pragma unroll
             for (int k = 0; k < 8; k++) vals[k] = cnt[k];
             vals[8] = tn5f; vals[9] = tn5r; vals[10] = cov;
-            if (p >= a.P) { tn5f = 0; tn5r = 0; }
             if (max(max(cov, tn5f), tn5r) > 65535u) {        // rare: writers.py:205-218 saturation; exact value kept aside
 #pragma unroll
                 for (int pl = 0; pl < MGATK_N_PLANES; pl++) {

@@ -79,7 +79,10 @@ class BAMReader:
     def _load_batch(self) -> ReadBatch:
         if self._batch is not None:
             return self._batch
-        from .bamio import read_bam_chrM
+        try:
+            from .bamio import read_bam_chrM
+        except ImportError as e:      # pysam is absent from this image; the native BGZF/BAM decoder is SURVEY §8 f-1
+            raise BAMReadError(str(self.bam_path), "no BAM decoder available: pass batch=ReadBatch(...)") from e
         batch, mito_chr = read_bam_chrM(str(self.bam_path), self.config, whitelist_index(self.barcode_list))
         if mito_chr != self.config.mito_chr:            # readers.py:43-48
             logger.info("Using mitochondrial chromosome: %s", mito_chr)
