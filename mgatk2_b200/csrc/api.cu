@@ -26,7 +26,8 @@ struct Layout {          // carve-up of the caller's workspace
     int passes, bits[2], shift[2];
     int unit_reads; int64_t max_units;
     size_t key[2], loc[2];   // grouped records (two generations for a two-digit partition)
-    size_t recs, mat, part, cell_start, unit_start, units, scalars, total;
+    size_t recs, mat, part, cell_start, unit_start, units, scan_state, scalars, total;
+    int64_t dedup_blocks;
 };
 
 bool make_layout(int64_t n, int32_t n_cells, Layout &L) {
@@ -58,6 +59,8 @@ bool make_layout(int64_t n, int32_t n_cells, Layout &L) {
     L.cell_start = o; o += align_up(((size_t)n_cells + 1) * 4);
     L.unit_start = o; o += align_up(((size_t)n_cells + 1) * 4);
     L.units = o; o += align_up((size_t)L.max_units * sizeof(Unit));
+    L.dedup_blocks = (n + kDedupThreads - 1) / kDedupThreads + 1;
+    L.scan_state = o; o += align_up((size_t)L.dedup_blocks * 8);
     L.scalars = o; o += 256;
     L.total = o;
     return true;
@@ -100,11 +103,12 @@ int fail(mgatk_handle *h, int code, const std::string &msg) { if (h) h->err = ms
             return fail(h, MGATK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
     } while (0)
 
-__global__ void k_init(mgatk_stats *stats, int64_t n_records, int32_t *work_counter) {
+__global__ void k_init(mgatk_stats *stats, int64_t n_records, int32_t *work_counter, u32 *ticket) {
     stats->total_reads = (uint64_t)n_records;            // readers.py:93 counts every fetched record
     stats->stage1_reads = 0; stats->filtered_reads = 0; stats->dup_with_length = 0;
     stats->dup_position_only = 0; stats->n_empty_seq = 0; stats->n_overflow = 0; stats->error_bits = 0;
     *work_counter = 0;
+    *ticket = 0;
 }
 __global__ void k_publish_m(mgatk_stats *stats, const int64_t *m) { stats->stage1_reads = (uint64_t)*m; }
 
@@ -134,15 +138,15 @@ int partition_pass(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout
     return MGATK_OK;
 }
 
-constexpr int kStageBlobBytes = 30 * 1024;              // staged blob bytes per CTA: 4 CTAs of 8 warps per SM
+constexpr int kStageBlobBytes = 38 * 1024;              // staged blob + query-mask bytes per CTA: 4 CTAs of 8 warps per SM
 
-int launch_pileup(mgatk_handle *h, cudaStream_t s, const PileupArgs &a) {
+int launch_pileup(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, int batch_reads) {
     const size_t smem = pileup_smem_bytes(kStageBlobBytes);
     CU(cudaFuncSetAttribute(k_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    k_pileup<<<h->sm_count * per_sm, kThreads, smem, s>>>(a, kStageBlobBytes);    // persistent CTAs pulling units
+    k_pileup<<<h->sm_count * per_sm, kThreads, smem, s>>>(a, kStageBlobBytes, batch_reads);    // persistent CTAs pulling units
     h->launches += 1;
     CU(cudaGetLastError());
     return MGATK_OK;
@@ -153,8 +157,9 @@ int unit_reads_for(const mgatk_batch *b) {
     const char *e = getenv("MGATK_UNIT_READS");
     const int v = e ? atoi(e) : 0;
     if (v > 0) return v < 32 ? 32 : v > kStageReads ? kStageReads : v;
-    const int64_t avg = b->n_records > 0 ? (b->blob_bytes / b->n_records + 15) / 16 * 16 : 96;
-    int64_t k = (int64_t)(0.9 * kStageBlobBytes) / (avg > 16 ? avg : 16);
+    int64_t avg = b->n_records > 0 ? (b->blob_bytes / b->n_records + 15) / 16 * 16 : 96;
+    avg += 16 * (avg * 2 / 3 / 32 + 1);                  // query masks: 16 bytes per 32 bases, l_seq ~ 2/3 of the blob
+    int64_t k = (int64_t)(0.75 * kStageBlobBytes) / (avg > 16 ? avg : 16);
     return (int)(k < 64 ? 64 : k > 384 ? 384 : k);
 }
 
@@ -199,9 +204,11 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     int64_t *m_ptr = (int64_t *)(ws + L.scalars);
     int32_t *n_units = (int32_t *)(ws + L.scalars + 8);
     int32_t *work_counter = (int32_t *)(ws + L.scalars + 16);
+    u32 *ticket = (u32 *)(ws + L.scalars + 20);
+    int64_t *n_proc = (int64_t *)(ws + L.scalars + 24);
     u64 *error_bits = (u64 *)&o->stats->error_bits;
 
-    k_init<<<1, 1, 0, s>>>(o->stats, b->n_records, work_counter);
+    k_init<<<1, 1, 0, s>>>(o->stats, b->n_records, work_counter, ticket);
     h->launches++;
     CU(cudaMemsetAsync(o->base_totals, 0, sizeof(int64_t) * (size_t)P * 4, s));
     if (C > 0) CU(cudaMemsetAsync(o->cell_qc, 0, sizeof(mgatk_cell_qc) * (size_t)C, s));
@@ -221,17 +228,17 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
         g = g1;
     }
     k_publish_m<<<1, 1, 0, s>>>(o->stats, m_ptr);
-    int32_t *cell_start = (int32_t *)(ws + L.cell_start);
-    k_cell_start<<<(C + 1 + 255) / 256, 256, 0, s>>>(g.key, m_ptr, C, cell_start);
-    h->launches += 2;
+    h->launches += 1;
     mark(h, s, "filter+partition");
 
-    // ---- stage 2: dedup ----
+    // ---- stage 2: dedup, mapq gate, compaction of the reads to pile up ----
     ReadRec *recs = (ReadRec *)(ws + L.recs);
-    if (b->n_records > 0) {
-        k_dedup<<<(unsigned)((b->n_records + 255) / 256), 256, 0, s>>>(g, m_ptr, recs, p->dedup_mode, p->min_mapq, o->cell_qc, o->stats);
-        h->launches++;
-    }
+    int32_t *cell_start = (int32_t *)(ws + L.cell_start);
+    CU(cudaMemsetAsync(ws + L.scan_state, 0, (size_t)L.dedup_blocks * 8, s));
+    k_dedup<<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(g, m_ptr, recs, p->dedup_mode, p->min_mapq, o->cell_qc, o->stats,
+                                                              ticket, (u64 *)(ws + L.scan_state), n_proc);
+    k_cell_start<<<(C + 1 + 255) / 256, 256, 0, s>>>(recs, n_proc, C, cell_start);
+    h->launches += 2;
     mark(h, s, "dedup");
 
     // ---- units ----
@@ -254,7 +261,7 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     a.raw = (p->flags & MGATK_FLAG_RAW_PILEUP) ? 1 : 0;
     a.apply_bias = !a.raw && !(p->max_strand_bias >= 1.0);   // max(f,r)/total never exceeds 1.0
     a.extent = p->max_read_extent;
-    rc = launch_pileup(h, s, a);
+    rc = launch_pileup(h, s, a, L.unit_reads);
     if (rc) return rc;
     mark(h, s, "pileup");
 

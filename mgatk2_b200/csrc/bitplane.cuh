@@ -1,0 +1,162 @@
+// mgatk2_b200 — word-parallel helpers of the bit-plane pileup (stage 3 of the hot path).
+//
+// A read's bases are turned once into four bit masks in QUERY coordinates (bit q of mask X is set iff
+// SEQ[q] == X, the base quality passes and q lies inside the distance-from-end window,
+// pileup.py:67-86). Counting a chunk of 32 reference positions then reduces to picking a 32-bit
+// window out of these masks per aligned block (pileup.py:55-65) and a 32x32 bit transpose across the
+// warp, so that each lane (= position) can popcount the reads that carry a given base there.
+//
+// Everything here is plain integer arithmetic and compiles for the host too: tests/test_bitplane_host.py
+// checks each helper exhaustively / on random words against the obvious per-base loop.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MG_HD __host__ __device__ __forceinline__
+#else
+#define MG_HD inline
+#endif
+
+namespace mgatk {
+
+typedef unsigned int u32;
+
+MG_HD u32 funnel_r(u32 lo, u32 hi, u32 sh) {            // low word of (hi:lo) >> sh, sh in [0, 31]
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+
+MG_HD u32 rotl32(u32 x, u32 n) {                        // n in [0, 31]
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(x, x, n);
+#else
+    return n ? (x << n) | (x >> (32 - n)) : x;
+#endif
+}
+
+// bits [lo, hi) of a 32-bit word; lo/hi may lie outside [0, 32]
+MG_HD u32 bit_range(int lo, int hi) {
+    if (lo < 0) lo = 0;
+    if (hi > 32) hi = 32;
+    if (hi <= lo) return 0u;
+    const u32 upto = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+    return upto & (0xffffffffu << lo);
+}
+
+// ---- base quality: (int8)qual >= min_baseq (pileup.py:80-81; quals are stored np.int8, readers.py:158) ----
+// Compare on u = q ^ 0x80 (unsigned order == signed order) against t = min_baseq + 128, four bytes per word.
+struct QualGe { u32 add, sel; int none; };
+
+MG_HD QualGe make_qual_ge(int min_baseq) {
+    QualGe g;
+    int t = min_baseq + 128;
+    g.none = t > 255;                                   // nothing passes: the caller empties the window instead
+    if (t > 255) t = 255;
+    if (t < 0) t = 0;                                   // everything passes
+    g.add = (u32)(0x80 - (t & 0x7f)) * 0x01010101u;     // bit 7 of (low7 + add) set iff low7 >= t's low seven bits
+    g.sel = (t & 0x80) ? 0u : 0xffffffffu;              // t >= 128: need the top bit AND the low part; else OR
+    return g;
+}
+
+// bit 7 of each byte set iff that quality passes
+MG_HD u32 qual_ge4(u32 q, QualGe g) {
+    const u32 a = (q & 0x7f7f7f7fu) + g.add;
+    const u32 u = ~q;                                   // bit 7 of q ^ 0x80
+    return ((u & a) | ((u | a) & g.sel)) & 0x80808080u;
+}
+
+// bits 7, 15, 23, 31 -> bits 28..31 (in byte order)
+MG_HD u32 pack_byte_flags_top(u32 ge) { return ((ge >> 7) * 0x10204080u) & 0xf0000000u; }
+
+// pass flags of eight consecutive quality bytes (two words) as the top byte: bit 24+i = byte i passes
+MG_HD u32 qual_ok8_top(u32 q0, u32 q1, QualGe g) {
+    return (pack_byte_flags_top(qual_ge4(q0, g)) >> 4) | pack_byte_flags_top(qual_ge4(q1, g));
+}
+
+// ---- bases: one little-endian word of BAM 4-bit SEQ = eight bases, high nibble first in every byte ----
+// Returns, per base X in A,C,G,T (BAM codes 1,2,4,8), the eight "SEQ[i] == X" flags as the top byte
+// (bit 24+i = base i). Any other code (=, N, IUPAC) matches nothing (pileup.py:83-86).
+struct Eq8 { u32 a, c, g, t; };
+
+MG_HD u32 pack_nibble_flags_top(u32 e) {                // flags at bits 4n (n = 0..7) -> bits 24..31
+    u32 y = e & 0x11111111u;
+    y = (y | (y >> 3)) & 0x03030303u;                   // byte k: bits 0,1 = nibbles 2k, 2k+1
+    return (y * 0x01041040u) & 0xff000000u;
+}
+
+MG_HD Eq8 seq_eq8_top(u32 s) {
+    const u32 t0 = ((s & 0x0f0f0f0fu) << 4) | ((s >> 4) & 0x0f0f0f0fu);   // nibble n now holds base n
+    const u32 t1 = t0 >> 1, t2 = t0 >> 2, t3 = t0 >> 3;
+    Eq8 r;
+    r.a = pack_nibble_flags_top(t0 & ~t1 & ~t2 & ~t3);   // 0001
+    r.c = pack_nibble_flags_top(~t0 & t1 & ~t2 & ~t3);   // 0010
+    r.g = pack_nibble_flags_top(~t0 & ~t1 & t2 & ~t3);   // 0100
+    r.t = pack_nibble_flags_top(~t0 & ~t1 & ~t2 & t3);   // 1000
+    return r;
+}
+
+// ---- 32x32 bit transpose across a warp: one butterfly stage ----
+// Lane r holds row r; after the five stages (j = 16, 8, 4, 2, 1) lane p holds column p (bit r = row r's bit p).
+// `mine` is the word of this lane, `other` the word of lane ^ j.
+MG_HD u32 transpose_stage(u32 mine, u32 other, int lane, int j) {
+    const u32 m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+    const bool upper = (lane & j) != 0;
+    const u32 keep = upper ? ~m : m;
+    const u32 moved = rotl32(other, upper ? 32 - j : j);   // wrapped-around bits fall outside ~keep
+    return (mine & keep) | (moved & ~keep);
+}
+
+}  // namespace mgatk
+
+// ---------------------------------------------------------------------------------------------
+// Query masks of one read. `M` gives word access to the staging memory holding the read's
+// cigar|seq|qual blob (shared memory on the device, a byte array in the host test):
+//     u32  ld32(u32 addr)                    4-byte aligned load
+//     void st128(u32 addr, u32 a, u32 c, u32 g, u32 t)   16-byte aligned store
+//     void ld128(u32 addr, u32 (&v)[4])      16-byte aligned load
+// Layout written at `out`: ceil(L/32) groups of four words (A, C, G, T masks of query bases 32w..32w+31).
+// Loads may run up to 40 bytes past the end of QUAL; whatever they return is masked by the window.
+// ---------------------------------------------------------------------------------------------
+namespace mgatk {
+
+template <class M>
+MG_HD void build_query_masks(const M &mem, u32 seq_addr /*4-aligned*/, u32 out /*16-aligned*/, int L, int q_lo, int q_hi, QualGe qg) {
+    const u32 qual_addr = seq_addr + (u32)((L + 1) >> 1);
+    const u32 qsh = (qual_addr & 3u) * 8u;
+    u32 qa = qual_addr & ~3u;
+    const int nq = (L + 31) >> 5;
+    for (int w = 0; w < nq; w++) {
+        u32 mA = 0, mC = 0, mG = 0, mT = 0;
+        u32 carry = mem.ld32(qa);
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const u32 s = mem.ld32(seq_addr + 16u * w + 4u * g);
+            const u32 w1 = mem.ld32(qa + 8u * g + 4u), w2 = mem.ld32(qa + 8u * g + 8u);
+            const u32 ok = qual_ok8_top(funnel_r(carry, w1, qsh), funnel_r(w1, w2, qsh), qg);
+            carry = w2;
+            const Eq8 e = seq_eq8_top(s);
+            const int sh = 24 - 8 * g;
+            mA |= (e.a & ok) >> sh; mC |= (e.c & ok) >> sh; mG |= (e.g & ok) >> sh; mT |= (e.t & ok) >> sh;
+        }
+        qa += 32u;
+        const u32 wm = bit_range(q_lo - 32 * w, q_hi - 32 * w);   // pileup.py:67-78 (also cuts bases >= L)
+        mem.st128(out + 16u * w, mA & wm, mC & wm, mG & wm, mT & wm);
+    }
+}
+
+// 32-bit windows of the four query masks starting at query bit qb (may be negative or beyond the read)
+template <class M>
+MG_HD void query_window(const M &mem, u32 masks /*16-aligned*/, int nq, int qb, u32 (&out)[4]) {
+    const int w0 = qb >> 5;                                // floor
+    const u32 sh = (u32)qb & 31u;
+    u32 lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+    if (w0 >= 0 && w0 < nq) mem.ld128(masks + 16u * (u32)w0, lo);
+    if (w0 + 1 >= 0 && w0 + 1 < nq) mem.ld128(masks + 16u * (u32)(w0 + 1), hi);
+#pragma unroll
+    for (int x = 0; x < 4; x++) out[x] = funnel_r(lo[x], hi[x], sh);
+}
+
+}  // namespace mgatk

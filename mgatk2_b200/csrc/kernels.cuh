@@ -16,10 +16,10 @@
 #include <stdint.h>
 
 #include "../../include/mgatk2_b200.h"
+#include "bitplane.cuh"
 
 namespace mgatk {
 
-typedef unsigned int u32;
 typedef unsigned long long u64;
 
 constexpr int kWarpsPerCta = 8;
@@ -30,7 +30,7 @@ constexpr u32 kFull = 0xffffffffu;
 constexpr u32 ERR_UNSORTED = 1, ERR_EXTENT = 2, ERR_OVERFLOW_CAP = 4;
 
 // ReadRec.flags bits written by k_dedup, read by k_pileup
-constexpr int GF_PROCESS = 1, GF_STRAND = 2, GF_KEEP = 4;
+constexpr int GF_PROCESS = 1, GF_STRAND = 2, GF_KEEP = 4, GF_CELL_SHIFT = 8;   // cell index in bits 8..31
 // KeyRec.mq layout: mapq | strand<<8 | paired<<9
 constexpr int GMQ_STRAND = 0x100, GMQ_PAIRED = 0x200;
 
@@ -225,34 +225,37 @@ k_scatter(Src src, int64_t chunk, int nchunks, int shift, int bins, const u32 *_
     }
 }
 
-// first grouped index of every cell: lower_bound on the cell column (records are grouped by cell)
-__global__ void k_cell_start(const KeyRec *__restrict__ key, const int64_t *__restrict__ m_ptr, int n_cells,
-                             int32_t *__restrict__ cell_start) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > n_cells) return;
-    int lo = 0, hi = (int)*m_ptr;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (key[mid].cell < c) lo = mid + 1; else hi = mid; }
-    cell_start[c] = lo;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Stage 2: dedup. Inside a cell the records are sorted by start, so all candidates for a duplicate
 // of record i sit directly before it in the same (cell, start) run; the first record of a key in
 // BAM order survives (readers.py:129-150). Both key sets are evaluated for every stage-1 survivor
 // (readers.py:128-144) so both duplicate counters are exact whichever strategy is selected.
-// The kernel also emits the 16-byte record k_pileup consumes.
+// The kernel also applies the mapq gate (pileup.py:33-34: after dedup, a low-mapq first read still
+// shadows its duplicates) and emits, compacted and in order, the 16-byte record k_pileup consumes:
+// one pass, block-wise exclusive scan chained over blocks by decoupled look-back (blocks take
+// their index from a ticket, so a block only ever waits for blocks that are already running).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int kDedupThreads = 512;
+constexpr u64 kScanAggregate = 1ull << 62, kScanPrefix = 2ull << 62, kScanValue = (1ull << 62) - 1;
+
+__global__ void __launch_bounds__(kDedupThreads)
 k_dedup(Grouped g, const int64_t *__restrict__ m_ptr, ReadRec *__restrict__ recs, int dedup_mode, int min_mapq,
-        mgatk_cell_qc *__restrict__ qc, mgatk_stats *__restrict__ stats) {
+        mgatk_cell_qc *__restrict__ qc, mgatk_stats *__restrict__ stats, u32 *__restrict__ ticket,
+        u64 *__restrict__ scan_state, int64_t *__restrict__ n_proc_out) {
     __shared__ u32 s_cnt[4];
+    __shared__ u32 s_warp[kDedupThreads / 32];
+    __shared__ u32 s_blk;
+    __shared__ u64 s_prefix;
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1u);
     __syncthreads();
+    const u32 blk = s_blk;
     const int64_t m = *m_ptr;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = lane_id();
+    const int64_t i = (int64_t)blk * kDedupThreads + threadIdx.x;
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
     int cell = -1;
-    bool keep = false, paired = false;
+    bool keep = false, paired = false, process = false;
+    ReadRec rr; rr.pos = 0; rr.off = 0; rr.len = 0; rr.flags = 0;
     if (i < m) {
         const KeyRec me = g.key[i];
         const LocRec lc = g.loc[i];
@@ -273,11 +276,9 @@ k_dedup(Grouped g, const int64_t *__restrict__ m_ptr, ReadRec *__restrict__ recs
         keep = dedup_mode == MGATK_DEDUP_FRAGMENT_LENGTH ? !len_dup : dedup_mode == MGATK_DEDUP_POSITION_ONLY ? !pos_dup : true;
         // pileup.py:33-34 mapq gate (after dedup, Q2). An empty SEQ makes the reference raise
         // (readers.py:157); such survivors are reported in stats.n_empty_seq and not piled up.
-        const bool process = keep && (int)(me.mq & 0xff) >= min_mapq && (lc.len & 0xffff) != 0;
-        ReadRec rr;
+        process = keep && (int)(me.mq & 0xff) >= min_mapq && (lc.len & 0xffff) != 0;
         rr.pos = me.pos; rr.off = lc.off; rr.len = lc.len;
-        rr.flags = (process ? GF_PROCESS : 0) | (strand ? GF_STRAND : 0) | (keep ? GF_KEEP : 0);
-        recs[i] = rr;
+        rr.flags = GF_PROCESS | (strand ? GF_STRAND : 0) | GF_KEEP | ((u32)cell << GF_CELL_SHIFT);
         if (len_dup) atomicAdd(&s_cnt[1], 1u);
         if (pos_dup) atomicAdd(&s_cnt[2], 1u);
         if (keep) { atomicAdd(&s_cnt[0], 1u); if ((lc.len & 0xffff) == 0) atomicAdd(&s_cnt[3], 1u); }
@@ -290,27 +291,58 @@ k_dedup(Grouped g, const int64_t *__restrict__ m_ptr, ReadRec *__restrict__ recs
         if (nk) atomicAdd(&qc[cell].n_reads, nk);
         if (np) atomicAdd(&qc[cell].n_paired, np);
     }
+    // stable compaction of the reads that are piled up
+    const u32 pm = __ballot_sync(kFull, process);
+    if (lane == 0) s_warp[wid] = __popc(pm);
     __syncthreads();
+    u32 before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kDedupThreads / 32; w++) { const u32 v = s_warp[w]; if (w < wid) before += v; total += v; }
     if (threadIdx.x == 0) {
+        u64 prefix = 0;
+        if (blk == 0) {
+            atomicExch((unsigned long long *)&scan_state[0], kScanPrefix | (u64)total);
+        } else {
+            atomicExch((unsigned long long *)&scan_state[blk], kScanAggregate | (u64)total);
+            for (int64_t b = (int64_t)blk - 1; b >= 0; b--) {
+                u64 v;
+                do { v = *(volatile u64 *)&scan_state[b]; } while ((v & ~kScanValue) == 0);
+                prefix += v & kScanValue;
+                if (v & kScanPrefix) break;
+            }
+            atomicExch((unsigned long long *)&scan_state[blk], kScanPrefix | (prefix + total));
+        }
+        s_prefix = prefix;
+        if ((int64_t)(blk + 1) * kDedupThreads >= m && (int64_t)blk * kDedupThreads < (m > 0 ? m : 1)) *n_proc_out = (int64_t)(prefix + total);
         if (s_cnt[0]) atomicAdd((u64 *)&stats->filtered_reads, (u64)s_cnt[0]);
         if (s_cnt[1]) atomicAdd((u64 *)&stats->dup_with_length, (u64)s_cnt[1]);
         if (s_cnt[2]) atomicAdd((u64 *)&stats->dup_position_only, (u64)s_cnt[2]);
         if (s_cnt[3]) atomicAdd((u64 *)&stats->n_empty_seq, (u64)s_cnt[3]);
     }
+    __syncthreads();
+    if (process) recs[s_prefix + before + __popc(pm & ((1u << lane) - 1u))] = rr;
+}
+
+// first compacted index of every cell: lower_bound on the cell field (records are grouped by cell)
+__global__ void k_cell_start(const ReadRec *__restrict__ recs, const int64_t *__restrict__ n_ptr, int n_cells,
+                             int32_t *__restrict__ cell_start) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_cells) return;
+    int lo = 0, hi = (int)*n_ptr;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if ((int)(recs[mid].flags >> GF_CELL_SHIFT) < c) lo = mid + 1; else hi = mid; }
+    cell_start[c] = lo;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Work planning: a unit is (cell, position tile); the tile width shrinks with the cell's read count
-// so units carry a bounded number of reads. Dead cells (processors.py:22) get one empty unit that
-// only writes zeros.
+// Work planning: a unit is (cell, position tile). Tile borders sit at every `unit_reads`-th read of
+// the cell (rounded down to a chunk of 32 positions), so units carry about the same number of reads
+// wherever the cell's coverage is dense or sparse. Dead cells (processors.py:22) and cells without
+// reads to pile up get one unit that only writes zeros.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int tiles_for(int cnt, int unit_reads, int ppad, int *width_out) {
+__device__ __forceinline__ int tiles_for(int cnt, int unit_reads, int ppad) {
     int nt = cnt <= 0 ? 1 : (cnt + unit_reads - 1) / unit_reads;
-    const int max_nt = ppad / 64;
-    if (nt > max_nt) nt = max_nt;
-    int width = ((ppad + nt - 1) / nt + 63) / 64 * 64;
-    *width_out = width;
-    return (ppad + width - 1) / width;
+    const int max_nt = ppad / 32;
+    return nt > max_nt ? max_nt : nt;
 }
 
 __device__ __forceinline__ bool cell_dead(const mgatk_cell_qc &q, int min_reads) {
@@ -327,10 +359,10 @@ k_plan_scan(const int32_t *__restrict__ cell_start, const mgatk_cell_qc *__restr
     __syncthreads();
     for (int c0 = 0; c0 < n_cells; c0 += 1024) {
         const int c = c0 + t;
-        int nt = 0, width;
+        int nt = 0;
         if (c < n_cells) {
             const int cnt = cell_dead(qc[c], min_reads) ? 0 : cell_start[c + 1] - cell_start[c];
-            nt = tiles_for(cnt, unit_reads, ppad, &width);
+            nt = tiles_for(cnt, unit_reads, ppad);
         }
         int inc = nt;
         for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
@@ -361,16 +393,19 @@ __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk
     const int c = lo;
     const bool dead = cell_dead(qc[c], min_reads);
     const int cs = cell_start[c], ce = cell_start[c + 1];
-    int width;
-    tiles_for(dead ? 0 : ce - cs, unit_reads, ppad, &width);
+    const int cnt = dead ? 0 : ce - cs;
+    const int nt = tiles_for(cnt, unit_reads, ppad), k = u - unit_start[c];
+    const int per = cnt > 0 ? (cnt + nt - 1) / nt : 0;
     Unit un;
     un.cell = c;
-    un.t0 = (u - unit_start[c]) * width;
-    un.t1 = min(ppad, un.t0 + width);
-    if (dead) { un.rbeg = un.rend = 0; }
+    un.t0 = 0; un.t1 = ppad;
+    if (k > 0) un.t0 = min(max(recs[cs + min(k * per, cnt - 1)].pos, 0), ppad) & ~31;
+    if (k + 1 < nt) un.t1 = min(max(recs[cs + min((k + 1) * per, cnt - 1)].pos, 0), ppad) & ~31;
+    if (un.t1 < un.t0) un.t1 = un.t0;
+    if (cnt == 0) { un.rbeg = un.rend = 0; }
     else {
         const int first = un.t0 - halo + 1;                // reads starting before cannot reach t0
-        int a = cs, b = un.t0 == 0 ? cs : ce;              // tile 0 also takes (and extent-checks) reads left of 0
+        int a = cs, b = un.t0 == 0 ? cs : ce;              // the leftmost tile also takes (and extent-checks) reads left of 0
         while (a < b) { int mid = (a + b) >> 1; if (recs[mid].pos < first) a = mid + 1; else b = mid; }
         un.rbeg = a;
         b = ce;
@@ -381,17 +416,22 @@ __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stages 3-6 as a gather. One CTA per unit (cell, position tile): the records and cigar|seq|qual
-// blobs of the unit's reads are staged once in shared memory with cp.async (L2 -> shared, no L1
-// pollution), then the warps take chunks of 32 positions of the tile, lane = position. For a chunk,
-// the candidate reads are those starting in (chunk - extent, chunk + 32): lanes first take one
-// candidate read each and walk its CIGAR in parallel (pileup.py:52-95) to the aligned block(s)
-// overlapping the chunk; every such block is then broadcast by shuffle and each lane picks the base /
-// quality of its own position from shared memory, accumulating the eight base x strand counters in
-// registers (byte-packed, spilled every 254 visits). Nothing is shared between warps, so there are no
-// atomics on counters; when the chunk's reads are exhausted the counts are final and the strand-bias
-// filter, coverage, Tn5 gating (pileup.py:128-154) and the depth statistics are applied in registers
-// and the 11 planes are written once. Reads beyond the staging capacity are read from global memory.
+// Stages 3-6 as a bit-plane gather. One CTA per unit (cell, position tile):
+//   stage   the records and cigar|seq|qual blobs of the unit's reads go to shared memory once (cp.async,
+//           L2 -> shared, no L1 pollution);
+//   phase A one thread per read turns SEQ/QUAL into four bit masks in query coordinates (bitplane.cuh:
+//           base == A/C/G/T, base quality, distance-from-end window; pileup.py:67-86), word-parallel, and
+//           verifies the declared extent;
+//   phase B the warps take chunks of 32 positions. The candidate reads of a chunk are those starting in
+//           (chunk - extent, chunk + 32); 32 candidates at a time, one per lane: the lane walks its CIGAR
+//           (pileup.py:52-95) and cuts the 32-bit window of every aligned block out of its query masks, a
+//           32x32 bit transpose across the warp turns "lane = read" into "lane = position", and two
+//           popcounts per base (forward / reverse reads) add up the eight base x strand counters in
+//           registers; the Tn5 sites (pileup.py:43-50) travel as a fifth mask. Nothing is shared between
+//           warps, so there are no atomics on counters; when the chunk's reads are exhausted the counts are
+//           final and the strand-bias filter, coverage, Tn5 gating (pileup.py:128-154) and the depth
+//           statistics are applied in registers and the 11 planes are written once.
+// Reads that did not fit the staging area take a per-base path from global memory (same results).
 // ---------------------------------------------------------------------------------------------
 struct PileupArgs {
     const ReadRec *recs;
@@ -405,199 +445,107 @@ struct PileupArgs {
 
 constexpr int kOpCap = 1 << 20;     // cigar lengths above this cannot be valid for a short-read batch
 
-__device__ __forceinline__ void spill_packed(u32 (&cnt)[8], u32 &accf, u32 &accr) {
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-        cnt[2 * b] += (accf >> (8 * b)) & 255u;
-        cnt[2 * b + 1] += (accr >> (8 * b)) & 255u;
-    }
-    accf = 0; accr = 0;
-}
-
-// One lane's share of one aligned block: the base and quality at its own position -> (fwd, rev) increment.
-// Global-memory form (reads whose blob is not staged in shared memory).
-__device__ __forceinline__ uint2 visit_global(u64 sb, int pa, u32 sp, int qd, int lane, int min_baseq, u32 lut_addr) {
-    const bool valid = (unsigned)(lane - pa) < (sp & 0xffffu);
-    const int q = valid ? lane + qd : 0;                      // pileup.py:75; lanes outside the block read base 0
-    const uint8_t *seq = reinterpret_cast<const uint8_t *>(sb & ~(u64)3);
-    u32 by = __ldg(seq + (q >> 1));
-    const int ql = (int)__ldg(reinterpret_cast<const int8_t *>(seq) + (sp >> 16) + q);
-    if (!valid || ql < min_baseq) by = 0;                     // int8 compare, pileup.py:80
-    const u32 addr = lut_addr + ((((u32)sb & 1u) << 12) | (((u32)q & 1u) << 11) | (by << 3));
-    uint2 r;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
-    return r;
-}
-
-// Shared-memory form: ss = shared address of the read's SEQ (4-byte aligned) | strand.
-__device__ __forceinline__ uint2 visit_staged(u32 ss, int pa, u32 sp, int qd, int lane, int min_baseq, u32 lut_addr) {
-    const bool valid = (unsigned)(lane - pa) < (sp & 0xffffu);
-    const int q = valid ? lane + qd : 0;
-    const u32 seq = ss & ~3u;
-    u32 by; int ql;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(by) : "r"(seq + (u32)(q >> 1)));
-    asm volatile("ld.shared.s8 %0, [%1];" : "=r"(ql) : "r"(seq + (sp >> 16) + (u32)q));
-    if (!valid || ql < min_baseq) by = 0;
-    const u32 addr = lut_addr + (((ss & 1u) << 12) | (((u32)q & 1u) << 11) | (by << 3));
-    uint2 r;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
-    return r;
-}
-
 __device__ __forceinline__ void cp_async16(u32 dst_shared, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-constexpr int kStageReads = 512;     // reads of a unit whose record (and, space permitting, blob) is staged in shared memory
-constexpr int kStageMaxBlob = 512;   // larger blobs are read from global memory
-constexpr u32 kUnstaged = 0xffffffffu;
-constexpr int kSplitChunks = 4;      // units with at most this many chunks split every chunk's reads over several warps
-
-// dynamic shared memory of k_pileup: staged records, their blob offsets, the blob bytes
-__host__ __device__ inline size_t pileup_smem_bytes(int blob_bytes) { return (size_t)kStageReads * (sizeof(ReadRec) + 4) + blob_bytes; }
-
-__global__ void __launch_bounds__(kThreads)
-k_pileup(PileupArgs a, int blob_cap) {
-    // (fwd, rev) byte-packed increments indexed by [strand][q parity][SEQ byte]: the BAM base code
-    // 1,2,4,8 = A,C,G,T of the addressed nibble selects byte 0..3, anything else adds nothing
-    // (pileup.py:83-86); the pair form lets the visit add to both accumulators without a branch.
-    __shared__ uint2 lut[2 * 2 * 256];
-    __shared__ u32 tn5s[kWarpsPerCta][64];                    // per warp: Tn5 hits of the current chunk, [strand][position]
-    __shared__ int s_unit, s_chunk;
-    __shared__ u32 s_scratch[kSplitChunks * 320 + kSplitChunks];   // split mode: partial counts [chunk][10][32], arrival counters
-    __shared__ u32 s_wsum[2 * kWarpsPerCta];
-    extern __shared__ __align__(16) uint8_t dyn[];
-    ReadRec *s_rec = reinterpret_cast<ReadRec *>(dyn);                                  // [kStageReads]
-    u32 *s_so = reinterpret_cast<u32 *>(dyn + kStageReads * sizeof(ReadRec));           // [kStageReads] blob offset in s_blob or kUnstaged
-    uint8_t *s_blob = dyn + kStageReads * (sizeof(ReadRec) + 4);                        // [blob_cap]
-    for (int e = threadIdx.x; e < 1024; e += blockDim.x) {
-        const int by = e & 255, odd = (e >> 8) & 1, st = e >> 9;
-        const int n = odd ? (by & 15) : (by >> 4);
-        const u32 inc = n == 1 ? 1u : n == 2 ? 1u << 8 : n == 4 ? 1u << 16 : n == 8 ? 1u << 24 : 0u;
-        lut[e] = st ? make_uint2(0u, inc) : make_uint2(inc, 0u);
+struct SharedMem {                   // word access to shared memory by 32-bit shared address (bitplane.cuh's `M`)
+    __device__ __forceinline__ u32 ld32(u32 a) const { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+    __device__ __forceinline__ void st128(u32 a, u32 x, u32 y, u32 z, u32 w) const {
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
     }
-    for (int e = threadIdx.x; e < kWarpsPerCta * 64; e += blockDim.x) (&tn5s[0][0])[e] = 0;
-    for (int e = threadIdx.x; e < kSplitChunks * 320 + kSplitChunks; e += blockDim.x) s_scratch[e] = 0;
-    const u32 lut_addr = (u32)__cvta_generic_to_shared(lut);
-    const u32 blob_addr = (u32)__cvta_generic_to_shared(s_blob);
-    const int lane = lane_id(), wid = threadIdx.x >> 5;
-    u32 *my_tn5 = tn5s[wid];
-    const int n_units = *a.n_units;
-    const int q_lo = a.dist > 0 ? a.dist : 0;                // pileup.py:67-72
-    for (;;) {
-        __syncthreads();                                     // previous unit fully consumed (also covers the table init)
-        if (threadIdx.x == 0) { s_unit = atomicAdd(a.work_counter, 1); s_chunk = 0; }
-        __syncthreads();
-        const int u = s_unit;
-        if (u >= n_units) break;
-        const Unit un = a.units[u];
-        const int n_reads = un.rend - un.rbeg;
-        const int ns = min(n_reads, kStageReads);            // reads with a staged record
+    __device__ __forceinline__ void ld128(u32 a, u32 (&v)[4]) const {
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(a));
+    }
+};
 
-        // ---- stage: every thread owns up to two reads (j = tid, tid + 256): record to shared memory, blob
-        //      offset from a block-wide exclusive scan of the blob sizes, blob with 16-byte cp.async ----
-        ReadRec rr2[2];
-        u32 sz2[2], incl2[2];
+constexpr int kStageReads = 512;     // reads of a unit whose record is staged in shared memory
+constexpr int kStageMaxBytes = 1024; // blob + query masks of one read; larger reads take the per-base path
+constexpr int kStageSlack = 64;      // phase A may load this far past the last staged byte
+constexpr u32 kUnstaged = 0xffffffffu;
+constexpr int kSplitChunks = 4;      // "deep" units: at most this many chunks; their reads are staged in batches
+constexpr int kAccWords = 10 * 32;   // deep units: counts of one chunk, [8 base x strand + 2 Tn5][32]
+
+// dynamic shared memory of k_pileup: staged records, their blob offsets, the blob + mask bytes
+__host__ __device__ inline size_t pileup_smem_bytes(int blob_bytes) {
+    return (size_t)kStageReads * (sizeof(ReadRec) + 4) + blob_bytes + kStageSlack;
+}
+
+// Per-base form of one aligned block for a read whose blob is not staged: masks of chunk bits [pa, pa + span)
+// for query bases q0.. (already clipped to the distance-from-end window).
+__device__ __noinline__ void block_masks_global(const uint8_t *seq, int L, int pa, int span, int q0, int min_baseq, u32 (&m)[4]) {
+    const int8_t *qual = reinterpret_cast<const int8_t *>(seq) + ((L + 1) >> 1);
+    const int b0 = max(pa, 0), b1 = min(pa + span, 32);
+    for (int b = b0; b < b1; b++) {
+        const int q = q0 + (b - pa);                           // pileup.py:75
+        if ((int)__ldg(qual + q) < min_baseq) continue;        // int8 compare, pileup.py:80
+        const u32 by = __ldg(seq + (q >> 1));
+        const u32 nib = (q & 1) ? (by & 15u) : (by >> 4);
+        if (nib == 1) m[0] |= 1u << b;                         // pileup.py:83-86: A, C, G, T only
+        else if (nib == 2) m[1] |= 1u << b;
+        else if (nib == 4) m[2] |= 1u << b;
+        else if (nib == 8) m[3] |= 1u << b;
+    }
+}
+
+__device__ __forceinline__ u32 warp_transpose(u32 x, int lane) {
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int j = threadIdx.x + k * kThreads;
-            sz2[k] = 0;
-            if (j < ns) {
-                rr2[k] = a.recs[un.rbeg + j];
-                s_rec[j] = rr2[k];
-                const int L = rr2[k].len & 0xffff, nbytes = 4 * (int)(rr2[k].len >> 16) + ((L + 1) >> 1) + L;
-                if ((rr2[k].flags & GF_PROCESS) && nbytes <= kStageMaxBlob) sz2[k] = (u32)((nbytes + 15) & ~15);
-            }
-            u32 incl = sz2[k];
-            for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
-            incl2[k] = incl;
-            if (lane == 31) s_wsum[k * kWarpsPerCta + wid] = incl;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int j = threadIdx.x + k * kThreads;
-            u32 before = 0;                                  // blob bytes of all reads in earlier warps / the earlier half
-            for (int w = 0; w < k * kWarpsPerCta + wid; w++) before += s_wsum[w];
-            const u32 start = before + incl2[k] - sz2[k];
-            const bool st = sz2[k] && start + sz2[k] <= (u32)blob_cap;
-            if (j < ns) s_so[j] = st ? start : (u32)kUnstaged;
-            if (st) {
-                const uint8_t *src = a.blob + 16 * (size_t)rr2[k].off;
-                for (u32 o = 0; o < sz2[k]; o += 16) cp_async16(blob_addr + start + o, src + o);
-            }
-        }
-        cp_async_wait_all();
-        __syncthreads();
+    for (int j = 16; j >= 1; j >>= 1) x = transpose_stage(x, __shfl_xor_sync(kFull, x, j), lane, j);
+    return x;
+}
 
-        // ---- chunks of 32 positions, handed out to the warps ----
-        u64 sum = 0; u32 covered = 0, maxd = 0;
-        bool extent_err = false;
-        uint16_t *out_cell = a.planes + (size_t)un.cell * MGATK_N_PLANES * a.ppad;
-        const int n_chunks = (un.t1 - un.t0) >> 5;
-        // few chunks (deep cell): every chunk's candidate reads are split over `nparts` warps, partial counts meet
-        // in s_scratch and the warp that arrives last finishes the chunk
-        int nparts = 1;
-        if (n_chunks <= kSplitChunks) while (nparts * 2 * n_chunks <= kWarpsPerCta) nparts *= 2;
-        const int n_items = n_chunks * nparts;
-        for (;;) {
-            int item = 0;
-            if (lane == 0) item = atomicAdd(&s_chunk, 1);
-            item = __shfl_sync(kFull, item, 0);
-            if (item >= n_items) break;
-            const int ch = item / nparts, part = item - ch * nparts;
-            u32 *acc = s_scratch + ch * 320;
-            u32 *tn5_acc = nparts > 1 ? acc + 256 : my_tn5;
-            const int c0 = un.t0 + 32 * ch, c1 = c0 + 32;
-            const int skip_le = c0 - a.extent;               // reads starting at or before this cannot reach the chunk
-            // first candidate: reads are sorted by start; two 32-way probes over the unit's reads
-            int ra;
-            {
-                const int step = (n_reads + 31) >> 5;
-                int j = lane * step;
-                int pj = 0x7fffffff;
-                if (j < n_reads) pj = j < ns ? s_rec[j].pos : a.recs[un.rbeg + j].pos;
-                const int seg = __popc(__ballot_sync(kFull, pj <= skip_le));      // probes <= skip_le form a prefix
-                const int base = seg ? (seg - 1) * step : 0;
-                j = base + lane;
-                int cntb = 0;
-                for (int k = 0; k < step; k += 32) {
-                    const int jj = j + k;
-                    int pp = 0x7fffffff;
-                    if (jj < n_reads && jj < base + step) pp = jj < ns ? s_rec[jj].pos : a.recs[un.rbeg + jj].pos;
-                    cntb += __popc(__ballot_sync(kFull, pp <= skip_le));
-                }
-                ra = seg ? base + cntb : 0;
-            }
-
-            u32 cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            u32 accf = 0, accr = 0;
-            int nacc = 0;
-            bool any_tn5 = false;
-            for (int r = ra + 32 * part; r < n_reads; r += 32 * nparts) {
-                const int j = r + lane;
-                ReadRec rr; rr.pos = 0x7fffffff; rr.off = 0; rr.len = 0; rr.flags = 0;
-                u32 so = kUnstaged;
-                if (j < ns) { rr = s_rec[j]; so = s_so[j]; }
-                else if (j < n_reads) rr = a.recs[un.rbeg + j];
-                const int pos = rr.pos;
-                const u32 m_after = __ballot_sync(kFull, pos >= c1);
-                const bool cand = pos < c1 && pos > skip_le && (rr.flags & GF_PROCESS);   // implies j < n_reads
-                const bool chk = cand && (pos >= c0 || ch == 0);           // once per read and unit: verify the declared extent
-                const u32 off = rr.off, ln = rr.len;
-                const int strand = (rr.flags & GF_STRAND) ? 1 : 0;
-                const int L = ln & 0xffff, ncig = ln >> 16;
+// Counts of chunk `ch` of the unit from the reads [rb, rb + nb) of the unit (a batch whose first `ns`
+// records are staged), part `part` of `nparts`: lane = position on return.
+__device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un, const ReadRec *s_rec, const u32 *s_so,
+                                            u32 blob_addr, int rb, int nb, int ns, int ch, int part, int nparts,
+                                            int lane, int q_lo, u32 (&cnt)[10], bool &extent_err) {
+    const SharedMem smem;
+    const ReadRec *g_rec = a.recs + un.rbeg + rb;
+    const int c0 = un.t0 + 32 * ch, c1 = c0 + 32;
+    const int skip_le = c0 - a.extent;               // reads starting at or before this cannot reach the chunk
+    // first candidate: reads are sorted by start; two 32-way probes over the batch
+    int ra;
+    {
+        const int step = (nb + 31) >> 5;
+        int j = lane * step;
+        int pj = 0x7fffffff;
+        if (j < nb) pj = j < ns ? s_rec[j].pos : g_rec[j].pos;
+        const int seg = __popc(__ballot_sync(kFull, pj <= skip_le));      // probes <= skip_le form a prefix
+        const int base = seg ? (seg - 1) * step : 0;
+        j = base + lane;
+        int cntb = 0;
+        for (int k = 0; k < step; k += 32) {
+            const int jj = j + k;
+            int pp = 0x7fffffff;
+            if (jj < nb && jj < base + step) pp = jj < ns ? s_rec[jj].pos : g_rec[jj].pos;
+            cntb += __popc(__ballot_sync(kFull, pp <= skip_le));
+        }
+        ra = seg ? base + cntb : 0;
+    }
+    for (int r = ra + 32 * part; r < nb; r += 32 * nparts) {
+        const int j = r + lane;
+        ReadRec rr; rr.pos = 0x7fffffff; rr.off = 0; rr.len = 0; rr.flags = 0;
+        u32 so = kUnstaged;
+        if (j < ns) { rr = s_rec[j]; so = s_so[j]; }
+        else if (j < nb) rr = g_rec[j];
+        const int pos = rr.pos;
+        const u32 m_after = __ballot_sync(kFull, pos >= c1);
+        const bool cand = pos < c1 && pos > skip_le && (rr.flags & GF_PROCESS);   // implies j < nb
+        if (__ballot_sync(kFull, cand)) {
+            const int strand = (rr.flags & GF_STRAND) ? 1 : 0;
+            u32 m[4] = {0u, 0u, 0u, 0u};
+            u32 m5 = 0u;
+            if (cand) {
+                const int L = rr.len & 0xffff, ncig = rr.len >> 16;
                 const bool staged = so != kUnstaged;
-                const u32 sb_addr = blob_addr + (staged ? so : 0u);         // shared address of the staged blob
-                const u32 *cig = reinterpret_cast<const u32 *>(a.blob + 16 * (size_t)off);
-                if (chk) {
+                const u32 sb = blob_addr + (staged ? so : 0u);                   // shared address of the staged blob
+                const u32 *cig = reinterpret_cast<const u32 *>(a.blob + 16 * (size_t)rr.off);
+                if (j >= ns && (pos >= c0 || (ch == 0 && rb == 0))) {   // no staged record: verify the declared extent here
                     if (L > a.extent) extent_err = true;
                     int span = 0;
                     for (int ci = 0; ci < ncig; ci++) {
-                        u32 w;
-                        if (staged) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sb_addr + 4 * ci));
-                        else w = __ldg(cig + ci);
+                        const u32 w = __ldg(cig + ci);
                         const int op = w & 15;
                         if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += min((int)(w >> 4), kOpCap);
                         if (span > a.extent) { extent_err = true; break; }
@@ -605,139 +553,236 @@ k_pileup(PileupArgs a, int blob_cap) {
                 }
                 // Tn5 site (pileup.py:43-50): reverse = start + len(SEQ) - 1, forward = start
                 const int t5 = strand ? pos + L - 1 : pos;
-                const bool hit = cand && t5 >= c0 && t5 < c1 && t5 < a.P;
-                if (hit) atomicAdd(&tn5_acc[(strand << 5) + (t5 - c0)], 1u);
-                any_tn5 |= __any_sync(kFull, hit);
-                // aligned blocks overlapping this chunk; a read can contribute several (indels), one per round
+                if (t5 >= c0 && t5 < c1 && t5 < a.P) m5 = 1u << (t5 - c0);
+                // aligned blocks overlapping this chunk (pileup.py:55-95)
                 const int q_hi = a.dist > 0 ? L - a.dist : L;
-                const u64 sb = (u64)(a.blob + 16 * (size_t)off + 4 * ncig) | (u64)strand;
-                const u32 ss = (sb_addr + 4 * ncig) | (u32)strand;
-                const u32 sp_hi = (u32)((L + 1) >> 1) << 16;
-                int ci = 0, ref = pos, qp = 0;
-                bool has = cand;
-                for (;;) {
-                    int pa = 0, span = 0, q0 = 0;
-                    bool blk = false;
-                    if (has) {
-                        while (ci < ncig) {
-                            u32 w;
-                            if (staged) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sb_addr + 4 * ci));
-                            else w = __ldg(cig + ci);
-                            const int op = w & 15;
-                            const int n = min((int)(w >> 4), kOpCap);
-                            ci++;
-                            if (op == 0 || op == 7 || op == 8) {             // pileup.py:56
-                                const int va = max(q_lo - qp, 0), vb = min(q_hi - qp, n);
-                                const int r0 = ref;
-                                const int q00 = qp;
-                                ref += n; qp = min(qp + n, kOpCap);          // pileup.py:90-91
-                                if (vb > va && r0 + va < c1 && r0 + vb > c0) {
-                                    pa = r0 + va - c0; span = vb - va; q0 = q00 + va; blk = true;
-                                    break;
-                                }
-                            } else if (op == 2 || op == 3) ref += n;         // pileup.py:92-93
-                            else if (op == 4) qp = min(qp + n, kOpCap);      // pileup.py:94-95; I, H, P: nothing (sic)
-                            if (ref >= c1) { ci = ncig; break; }             // blocks only move right
+                const int nq = (L + 31) >> 5;
+                const u32 mask_s = sb + (u32)((4 * ncig + ((L + 1) >> 1) + L + 15) & ~15);
+                int ref = pos, qp = 0;
+                for (int ci = 0; ci < ncig; ci++) {
+                    const u32 w = staged ? smem.ld32(sb + 4 * ci) : __ldg(cig + ci);
+                    const int op = w & 15;
+                    const int n = min((int)(w >> 4), kOpCap);
+                    if (op == 0 || op == 7 || op == 8) {             // pileup.py:56
+                        const int va = max(q_lo - qp, 0), vb = min(q_hi - qp, n);
+                        const int r0 = ref, q00 = qp;
+                        ref += n; qp = min(qp + n, kOpCap);          // pileup.py:90-91
+                        if (vb > va && r0 + va < c1 && r0 + vb > c0) {
+                            const int pa = r0 + va - c0, span = vb - va, q0 = q00 + va;
+                            if (staged) {
+                                u32 wv[4];
+                                query_window(smem, mask_s, nq, q0 - pa, wv);
+                                const u32 rm = bit_range(pa, pa + span);
+                                m[0] |= wv[0] & rm; m[1] |= wv[1] & rm; m[2] |= wv[2] & rm; m[3] |= wv[3] & rm;
+                            } else {
+                                block_masks_global(reinterpret_cast<const uint8_t *>(cig + ncig), L, pa, span, q0, a.min_baseq, m);
+                            }
                         }
-                        has = blk && ci < ncig;
-                    }
-                    const u32 m_blk = __ballot_sync(kFull, blk);
-                    if (!m_blk) break;
-                    // owner lanes publish: first position (chunk relative), span | qual offset, q - lane, SEQ address | strand
-                    const int qd = q0 - pa;
-                    const u32 sp = blk ? ((u32)span | sp_hi) : 0u;
-                    const int nv = __popc(m_blk);
-                    if (nacc + nv > 254) { spill_packed(cnt, accf, accr); nacc = 0; }
-                    nacc += nv;
-                    u32 mv = __ballot_sync(kFull, blk && staged);
-                    u32 mg = m_blk & ~mv;
-                    while (mv) {                                             // two visits in flight
-                        const int j0 = __ffs(mv) - 1;
-                        mv &= mv - 1;
-                        const int j1 = mv ? __ffs(mv) - 1 : j0;
-                        const u32 keep1 = mv ? ~0u : 0u;
-                        mv &= mv - 1;
-                        const uint2 i0 = visit_staged(__shfl_sync(kFull, ss, j0), __shfl_sync(kFull, pa, j0), __shfl_sync(kFull, sp, j0),
-                                                      __shfl_sync(kFull, qd, j0), lane, a.min_baseq, lut_addr);
-                        const uint2 i1 = visit_staged(__shfl_sync(kFull, ss, j1), __shfl_sync(kFull, pa, j1), __shfl_sync(kFull, sp, j1) & keep1,
-                                                      __shfl_sync(kFull, qd, j1), lane, a.min_baseq, lut_addr);
-                        accf += i0.x + i1.x;                                 // pileup.py:88
-                        accr += i0.y + i1.y;
-                    }
-                    while (mg) {                                             // blobs that did not fit the staging area
-                        const int j0 = __ffs(mg) - 1;
-                        mg &= mg - 1;
-                        const uint2 i0 = visit_global(__shfl_sync(kFull, sb, j0), __shfl_sync(kFull, pa, j0), __shfl_sync(kFull, sp, j0),
-                                                      __shfl_sync(kFull, qd, j0), lane, a.min_baseq, lut_addr);
-                        accf += i0.x;
-                        accr += i0.y;
-                    }
-                    if (!__any_sync(kFull, has)) break;
+                    } else if (op == 2 || op == 3) ref += n;         // pileup.py:92-93
+                    else if (op == 4) qp = min(qp + n, kOpCap);      // pileup.py:94-95; I, H, P: nothing (sic)
+                    if (ref >= c1) break;                            // blocks only move right
                 }
-                if (m_after) break;
             }
-            spill_packed(cnt, accf, accr);
-            if (nparts > 1) {
+            // lane = read -> lane = position; forward and reverse reads counted apart (pileup.py:88)
+            const u32 rev = __ballot_sync(kFull, cand && strand);
 #pragma unroll
-                for (int k = 0; k < 8; k++) if (cnt[k]) atomicAdd(&acc[k * 32 + lane], cnt[k]);
-                __threadfence_block();
-                int arrived = 0;
-                if (lane == 0) arrived = atomicAdd(&s_scratch[kSplitChunks * 320 + ch], 1u) + 1;
-                arrived = __shfl_sync(kFull, arrived, 0);
-                if (arrived != nparts) continue;             // another warp finishes this chunk
-                __threadfence_block();
-#pragma unroll
-                for (int k = 0; k < 8; k++) { cnt[k] = *(volatile u32 *)&acc[k * 32 + lane]; acc[k * 32 + lane] = 0; }
-                if (lane == 0) s_scratch[kSplitChunks * 320 + ch] = 0;
-                any_tn5 = true;
+            for (int x = 0; x < 4; x++) {
+                const u32 t = warp_transpose(m[x], lane);
+                cnt[2 * x] += __popc(t & ~rev);
+                cnt[2 * x + 1] += __popc(t & rev);
             }
+            if (__any_sync(kFull, m5 != 0u)) {
+                const u32 t = warp_transpose(m5, lane);
+                cnt[8] += __popc(t & ~rev);
+                cnt[9] += __popc(t & rev);
+            }
+        }
+        if (m_after) break;
+    }
+}
 
-            // ---- counts of this chunk are final: filter, reduce, write ----
-            const int p = c0 + lane;
-            u32 tn5f = 0, tn5r = 0;
-            if (any_tn5) {                                   // warp-uniform
-                __syncwarp();
-                tn5f = *(volatile u32 *)&tn5_acc[lane]; tn5r = *(volatile u32 *)&tn5_acc[32 + lane];
-                tn5_acc[lane] = 0; tn5_acc[32 + lane] = 0;
-                __syncwarp();
-            }
-            if (p >= a.P) {                                  // pileup.py:58 end_refpos = min(.., mito_length): padding stays zero
+// The counts of a chunk are final: strand-bias filter, coverage, Tn5 gating (pileup.py:128-154), depth
+// statistics, saturation (writers.py:205-218) and the one write of the 11 planes.
+__device__ __forceinline__ void finish_chunk(const PileupArgs &a, int cell, int c0, int lane, u32 (&cnt)[10],
+                                             u64 &sum, u32 &covered, u32 &maxd) {
+    const int p = c0 + lane;
+    if (p >= a.P) {                                  // pileup.py:58 end_refpos = min(.., mito_length): padding stays zero
 #pragma unroll
-                for (int k = 0; k < 8; k++) cnt[k] = 0;
-            }
-            if (a.apply_bias) {
+        for (int k = 0; k < 10; k++) cnt[k] = 0;
+    }
+    if (a.apply_bias) {
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const u32 f = cnt[2 * b], r = cnt[2 * b + 1], t = f + r;
-                    if (t > 0) {                             // pileup.py:143-148, IEEE double, strict >
-                        const double bias = (double)max(f, r) / (double)t;
-                        if (bias > a.max_bias) { cnt[2 * b] = 0; cnt[2 * b + 1] = 0; }
-                    }
+        for (int b = 0; b < 4; b++) {
+            const u32 f = cnt[2 * b], r = cnt[2 * b + 1], t = f + r;
+            if (t > 0) {                             // pileup.py:143-148, IEEE double, strict >
+                const double bias = (double)max(f, r) / (double)t;
+                if (bias > a.max_bias) { cnt[2 * b] = 0; cnt[2 * b + 1] = 0; }
+            }
+        }
+    }
+    const u32 cov = ((cnt[0] + cnt[1]) + (cnt[2] + cnt[3])) + ((cnt[4] + cnt[5]) + (cnt[6] + cnt[7]));  // pileup.py:150
+    if (cov == 0) { if (!a.raw) { cnt[8] = 0; cnt[9] = 0; } }   // pileup.py:152-153: dropped with its Tn5 counts
+    else { sum += cov; covered++; maxd = max(maxd, cov); }
+    u32 vals[MGATK_N_PLANES];
+#pragma unroll
+    for (int k = 0; k < 10; k++) vals[k] = cnt[k];
+    vals[10] = cov;
+    if (max(max(cov, cnt[8]), cnt[9]) > 65535u) {    // rare: exact value kept aside
+#pragma unroll
+        for (int pl = 0; pl < MGATK_N_PLANES; pl++) {
+            if (vals[pl] > 65535u) {
+                const u64 idx = atomicAdd((u64 *)&a.stats->n_overflow, 1ull);
+                if ((int64_t)idx < a.ovf_cap) {
+                    a.ovf[idx].cell = cell;
+                    a.ovf[idx].plane_pos = ((u32)pl << 24) | (u32)p;
+                    a.ovf[idx].value = vals[pl];
+                } else atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_OVERFLOW_CAP);
+                vals[pl] = 65535u;
+            }
+        }
+    }
+    uint16_t *out = a.planes + (size_t)cell * MGATK_N_PLANES * a.ppad + p;
+#pragma unroll
+    for (int pl = 0; pl < MGATK_N_PLANES; pl++) out[(size_t)pl * a.ppad] = (uint16_t)vals[pl];
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
+k_pileup(PileupArgs a, int blob_cap, int batch_reads) {
+    __shared__ int s_unit, s_chunk;
+    __shared__ u32 s_acc[kSplitChunks * kAccWords];          // deep units: counts of every chunk, summed over warps and batches
+    __shared__ u32 s_wsum[2 * kWarpsPerCta];
+    extern __shared__ __align__(16) uint8_t dyn[];
+    ReadRec *s_rec = reinterpret_cast<ReadRec *>(dyn);                                  // [kStageReads]
+    u32 *s_so = reinterpret_cast<u32 *>(dyn + kStageReads * sizeof(ReadRec));           // [kStageReads] offset in s_blob or kUnstaged
+    uint8_t *s_blob = dyn + kStageReads * (sizeof(ReadRec) + 4);                        // [blob_cap + slack]
+    for (int e = threadIdx.x; e < kSplitChunks * kAccWords; e += blockDim.x) s_acc[e] = 0;
+    const u32 blob_addr = (u32)__cvta_generic_to_shared(s_blob);
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
+    const SharedMem smem;
+    const int n_units = *a.n_units;
+    QualGe qg = make_qual_ge(a.min_baseq);
+    const int q_lo = a.dist > 0 ? a.dist : 0;                // pileup.py:67-72
+    int next_unit = 0;
+    if (threadIdx.x == 0) next_unit = atomicAdd(a.work_counter, 1);
+    for (;;) {
+        __syncthreads();                                     // previous unit fully consumed (also covers the s_acc init)
+        if (threadIdx.x == 0) { s_unit = next_unit; s_chunk = 0; }
+        __syncthreads();
+        const int u = s_unit;
+        if (u >= n_units) break;
+        if (threadIdx.x == 0) next_unit = atomicAdd(a.work_counter, 1);   // in flight while this unit is processed
+        const Unit un = a.units[u];
+        const int n_chunks = (un.t1 - un.t0) >> 5;
+        if (n_chunks <= 0) continue;                         // empty tile (its reads belong to the tile before)
+        const int n_reads = un.rend - un.rbeg;
+        // deep unit (few chunks): the reads go through the staging area in batches and every chunk's candidates
+        // are split over `nparts` warps; partial counts meet in s_acc and are finished after the last batch
+        const bool deep = n_chunks <= kSplitChunks;
+        int nparts = 1;
+        if (deep) while (nparts * 2 * n_chunks <= kWarpsPerCta) nparts *= 2;
+        const int n_items = n_chunks * nparts;
+        bool extent_err = false;
+        u64 sum = 0; u32 covered = 0, maxd = 0;
+
+        for (int rb = 0; rb == 0 || rb < n_reads; ) {
+            const int nb = deep ? min(batch_reads, n_reads - rb) : n_reads;   // reads of this batch
+            const int ns = min(nb, kStageReads);                              // reads with a staged record
+            const ReadRec *g_rec = a.recs + un.rbeg + rb;
+            if (rb > 0) {
+                __syncthreads();                             // the previous batch is consumed
+                if (threadIdx.x == 0) s_chunk = 0;
+            }
+            // ---- stage: every thread owns up to two reads (j = tid, tid + 256): record to shared memory, blob
+            //      offset from a block-wide exclusive scan of the sizes (blob + query masks), blob with 16-byte cp.async ----
+            ReadRec rr2[2];
+            u32 sz2[2], incl2[2], bsz2[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int j = threadIdx.x + k * kThreads;
+                sz2[k] = 0; bsz2[k] = 0;
+                rr2[k].flags = 0; rr2[k].len = 0; rr2[k].off = 0; rr2[k].pos = 0;
+                if (j < ns) {
+                    rr2[k] = g_rec[j];
+                    s_rec[j] = rr2[k];
+                    const int L = rr2[k].len & 0xffff;
+                    const int nbytes = ((4 * (int)(rr2[k].len >> 16) + ((L + 1) >> 1) + L + 15) & ~15);
+                    const int total = nbytes + 16 * ((L + 31) >> 5);
+                    if ((rr2[k].flags & GF_PROCESS) && total <= kStageMaxBytes) { sz2[k] = (u32)total; bsz2[k] = (u32)nbytes; }
+                }
+                u32 incl = sz2[k];
+                for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+                incl2[k] = incl;
+                if (lane == 31) s_wsum[k * kWarpsPerCta + wid] = incl;
+            }
+            __syncthreads();
+            u32 start2[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int j = threadIdx.x + k * kThreads;
+                u32 before = 0;                              // bytes of all reads in earlier warps / the earlier half
+                for (int w = 0; w < k * kWarpsPerCta + wid; w++) before += s_wsum[w];
+                const u32 start = before + incl2[k] - sz2[k];
+                const bool st = sz2[k] && start + sz2[k] <= (u32)blob_cap;
+                start2[k] = st ? start : (u32)kUnstaged;
+                if (j < ns) s_so[j] = start2[k];
+                if (st) {
+                    const uint8_t *src = a.blob + 16 * (size_t)rr2[k].off;
+                    for (u32 o = 0; o < bsz2[k]; o += 16) cp_async16(blob_addr + start + o, src + o);
                 }
             }
-            const u32 cov = ((cnt[0] + cnt[1]) + (cnt[2] + cnt[3])) + ((cnt[4] + cnt[5]) + (cnt[6] + cnt[7]));  // pileup.py:150
-            if (cov == 0) { if (!a.raw) { tn5f = 0; tn5r = 0; } }   // pileup.py:152-153: dropped with its Tn5 counts
-            else { sum += cov; covered++; maxd = max(maxd, cov); }
-            u32 vals[MGATK_N_PLANES];
+            cp_async_wait_all();
+            __syncthreads();
+
+            // ---- phase A: query masks of the staged reads; declared extent of every read with a staged record ----
 #pragma unroll
-            for (int k = 0; k < 8; k++) vals[k] = cnt[k];
-            vals[8] = tn5f; vals[9] = tn5r; vals[10] = cov;
-            if (max(max(cov, tn5f), tn5r) > 65535u) {        // rare: writers.py:205-218 saturation; exact value kept aside
-#pragma unroll
-                for (int pl = 0; pl < MGATK_N_PLANES; pl++) {
-                    if (vals[pl] > 65535u) {
-                        const u64 idx = atomicAdd((u64 *)&a.stats->n_overflow, 1ull);
-                        if ((int64_t)idx < a.ovf_cap) {
-                            a.ovf[idx].cell = un.cell;
-                            a.ovf[idx].plane_pos = ((u32)pl << 24) | (u32)p;
-                            a.ovf[idx].value = vals[pl];
-                        } else atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_OVERFLOW_CAP);
-                        vals[pl] = 65535u;
-                    }
+            for (int k = 0; k < 2; k++) {
+                if (!(rr2[k].flags & GF_PROCESS)) continue;  // also covers j >= ns
+                const int L = rr2[k].len & 0xffff, ncig = rr2[k].len >> 16;
+                const bool staged = start2[k] != kUnstaged;
+                const u32 sb = blob_addr + (staged ? start2[k] : 0u);
+                const u32 *cig = reinterpret_cast<const u32 *>(a.blob + 16 * (size_t)rr2[k].off);
+                if (L > a.extent) extent_err = true;
+                int span = 0;
+                for (int ci = 0; ci < ncig; ci++) {
+                    const u32 w = staged ? smem.ld32(sb + 4 * ci) : __ldg(cig + ci);
+                    const int op = w & 15;
+                    if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += min((int)(w >> 4), kOpCap);
+                    if (span > a.extent) { extent_err = true; break; }
+                }
+                if (staged) {
+                    int q_hi = a.dist > 0 ? L - a.dist : L;
+                    if (qg.none) q_hi = q_lo;
+                    build_query_masks(smem, sb + 4 * ncig, sb + bsz2[k], L, q_lo, q_hi, qg);
                 }
             }
+            __syncthreads();
+
+            // ---- phase B: chunks of 32 positions (x parts), handed out to the warps ----
+            for (;;) {
+                int item = 0;
+                if (lane == 0) item = atomicAdd(&s_chunk, 1);
+                item = __shfl_sync(kFull, item, 0);
+                if (item >= n_items) break;
+                const int ch = item / nparts, part = item - ch * nparts;
+                u32 cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // 8 base x strand counters, Tn5 fwd / rev; lane = position
+                count_chunk(a, un, s_rec, s_so, blob_addr, rb, nb, ns, ch, part, nparts, lane, q_lo, cnt, extent_err);
+                if (deep) {
 #pragma unroll
-            for (int pl = 0; pl < MGATK_N_PLANES; pl++) out_cell[(size_t)pl * a.ppad + p] = (uint16_t)vals[pl];
+                    for (int k = 0; k < 10; k++) if (cnt[k]) atomicAdd(&s_acc[ch * kAccWords + k * 32 + lane], cnt[k]);
+                } else {
+                    finish_chunk(a, un.cell, un.t0 + 32 * ch, lane, cnt, sum, covered, maxd);
+                }
+            }
+            rb += nb > 0 ? nb : 1;
+        }
+        if (deep) {
+            __syncthreads();                                 // all partial counts are in s_acc
+            if (wid < n_chunks) {
+                u32 cnt[10];
+#pragma unroll
+                for (int k = 0; k < 10; k++) { cnt[k] = s_acc[wid * kAccWords + k * 32 + lane]; s_acc[wid * kAccWords + k * 32 + lane] = 0; }
+                finish_chunk(a, un.cell, un.t0 + 32 * wid, lane, cnt, sum, covered, maxd);
+            }
         }
         // per-cell depth statistics (processors.py:36-39, writers.py:187-193)
         for (int o = 16; o; o >>= 1) {

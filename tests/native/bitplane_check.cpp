@@ -1,0 +1,72 @@
+// Host check of mgatk2_b200/csrc/bitplane.cuh against per-base loops. Exit code 0 = all good.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../../mgatk2_b200/csrc/bitplane.cuh"
+using namespace mgatk;
+
+static uint64_t rng = 0x9e3779b97f4a7c15ull;
+static u32 rnd() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return (u32)(rng >> 16); }
+
+int main() {
+    int bad = 0;
+    // qual compare: every threshold, every byte value in every byte lane
+    for (int minq = -200; minq <= 200 && !bad; minq++) {
+        QualGe g = make_qual_ge(minq);
+        for (int v = 0; v < 256; v++) {
+            const bool want = !g.none && (int)(int8_t)v >= minq;
+            if (g.none) { if ((int)(int8_t)v >= minq) { printf("none wrong minq=%d v=%d\n", minq, v); bad++; } continue; }
+            for (int lane = 0; lane < 4; lane++) {
+                u32 q = rnd(); q &= ~(0xffu << (8 * lane)); q |= (u32)v << (8 * lane);
+                const bool got = (qual_ge4(q, g) >> (8 * lane + 7)) & 1;
+                if (got != want) { printf("qual_ge4 minq=%d v=%d lane=%d\n", minq, v, lane); bad++; break; }
+            }
+        }
+    }
+    for (int it = 0; it < 2000000 && !bad; it++) {
+        const int minq = (int)(rnd() % 300) - 150;
+        QualGe g = make_qual_ge(minq);
+        if (g.none) continue;
+        const u32 q0 = rnd(), q1 = rnd();
+        u32 want = 0;
+        for (int i = 0; i < 8; i++) { const int8_t b = (int8_t)(((i < 4 ? q0 : q1) >> (8 * (i & 3))) & 255); if ((int)b >= minq) want |= 1u << (24 + i); }
+        if (qual_ok8_top(q0, q1, g) != want) { printf("qual_ok8_top mismatch\n"); bad++; }
+    }
+    // seq: all nibble patterns by random words + structured words
+    for (int it = 0; it < 4000000 && !bad; it++) {
+        u32 s = rnd();
+        if (it & 1) { u32 t = 0; for (int n = 0; n < 8; n++) t |= (1u << (rnd() & 3)) << (4 * n); s = (it & 2) ? t : (t ^ ((rnd() & rnd() & rnd()) & 0xffffffffu)); }
+        u32 want[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 8; i++) {
+            const u32 byte = (s >> (8 * (i >> 1))) & 255;
+            const u32 nib = (i & 1) ? (byte & 15) : (byte >> 4);
+            for (int x = 0; x < 4; x++) if (nib == (1u << x)) want[x] |= 1u << (24 + i);
+        }
+        const Eq8 e = seq_eq8_top(s);
+        if (e.a != want[0] || e.c != want[1] || e.g != want[2] || e.t != want[3]) { printf("seq_eq8_top mismatch %08x\n", s); bad++; }
+    }
+    // bit_range / funnel_r
+    for (int lo = -40; lo <= 40; lo++) for (int hi = -40; hi <= 72; hi++) {
+        u32 want = 0; for (int b = 0; b < 32; b++) if (b >= lo && b < hi) want |= 1u << b;
+        if (bit_range(lo, hi) != want) { printf("bit_range %d %d\n", lo, hi); bad++; }
+    }
+    for (int it = 0; it < 100000; it++) {
+        const u32 lo = rnd(), hi = rnd(), sh = rnd() & 31;
+        const uint64_t v = ((uint64_t)hi << 32) | lo;
+        if (funnel_r(lo, hi, sh) != (u32)(v >> sh)) { printf("funnel_r\n"); bad++; }
+    }
+    // transpose: simulate the 32 lanes
+    for (int it = 0; it < 2000 && !bad; it++) {
+        u32 x[32], y[32], org[32];
+        for (int l = 0; l < 32; l++) org[l] = x[l] = rnd() & ((it % 3) ? 0xffffffffu : rnd());
+        for (int j = 16; j >= 1; j >>= 1) {
+            for (int l = 0; l < 32; l++) y[l] = transpose_stage(x[l], x[l ^ j], l, j);
+            memcpy(x, y, sizeof(x));
+        }
+        for (int p = 0; p < 32; p++) for (int r = 0; r < 32; r++)
+            if (((x[p] >> r) & 1) != ((org[r] >> p) & 1)) { printf("transpose\n"); bad++; p = 32; break; }
+    }
+    if (bad) { printf("FAILED %d\n", bad); return 1; }
+    printf("bitplane helpers ok\n");
+    return 0;
+}
