@@ -15,7 +15,7 @@ using namespace mgatk;
 namespace {
 
 constexpr int kMaxChunks = 148 * 4;                  // partition CTAs: one wave at 4 CTAs/SM (bounds the open write heads)
-constexpr int kMaxDigitBits = 12;                    // 4096 bins * 4 B = 16 KB of shared memory per CTA
+constexpr int kMaxDigitBits = 11;                    // 2048 bins * 20 B = 40 KB of shared memory per scatter CTA
 constexpr int kMaxStages = 16;
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -25,7 +25,7 @@ struct Layout {          // carve-up of the caller's workspace
     int nchunks; int64_t chunk; int ngroups;
     int passes, bits[2], shift[2];
     int unit_reads; int64_t max_units;
-    size_t key[2], loc[2];   // grouped records (two generations for a two-digit partition)
+    size_t grp[2];           // grouped records (two generations for a two-digit partition)
     size_t recs, mat, part, cell_start, unit_start, units, scan_state, scalars, total;
     int64_t dedup_blocks;
 };
@@ -50,8 +50,7 @@ bool make_layout(int64_t n, int32_t n_cells, Layout &L) {
     size_t o = 0;
     const size_t cap = (size_t)(n > 0 ? n : 1);
     for (int gen = 0; gen < 2; gen++) {
-        L.key[gen] = o; if (gen < L.passes) o += align_up(cap * sizeof(KeyRec));
-        L.loc[gen] = o; if (gen < L.passes) o += align_up(cap * sizeof(LocRec));
+        L.grp[gen] = o; if (gen < L.passes) o += align_up(cap * sizeof(GroupRec));
     }
     L.recs = o; o += align_up(cap * sizeof(ReadRec));
     L.mat = o; o += align_up((size_t)L.nchunks * max_bins * 4);
@@ -59,19 +58,14 @@ bool make_layout(int64_t n, int32_t n_cells, Layout &L) {
     L.cell_start = o; o += align_up(((size_t)n_cells + 1) * 4);
     L.unit_start = o; o += align_up(((size_t)n_cells + 1) * 4);
     L.units = o; o += align_up((size_t)L.max_units * sizeof(Unit));
-    L.dedup_blocks = (n + kDedupThreads - 1) / kDedupThreads + 1;
+    L.dedup_blocks = (n + kDedupTile - 1) / kDedupTile + 1;
     L.scan_state = o; o += align_up((size_t)L.dedup_blocks * 8);
     L.scalars = o; o += 256;
     L.total = o;
     return true;
 }
 
-Grouped grouped_at(char *ws, const Layout &L, int gen) {
-    Grouped g;
-    g.key = (KeyRec *)(ws + L.key[gen]);
-    g.loc = (LocRec *)(ws + L.loc[gen]);
-    return g;
-}
+GroupRec *grouped_at(char *ws, const Layout &L, int gen) { return (GroupRec *)(ws + L.grp[gen]); }
 
 struct DevBuf { void *p = nullptr; size_t cap = 0; };
 
@@ -122,11 +116,11 @@ void mark(mgatk_handle *h, cudaStream_t s, const char *name) {
 
 template <class Src>
 int partition_pass(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout &L, int pass, char *ws,
-                   const int32_t *sorted_pos, u64 *error_bits, int64_t *m_out, const Grouped &dst) {
+                   const int32_t *sorted_pos, u64 *error_bits, int64_t *m_out, GroupRec *dst) {
     const int bins = 1 << L.bits[pass];
     u32 *mat = (u32 *)(ws + L.mat), *part = (u32 *)(ws + L.part);
     const int grid = L.nchunks;
-    const size_t smem_h = (size_t)bins * 4, smem = ((size_t)bins + 2 * kPartThreads) * 4;
+    const size_t smem_h = (size_t)bins * 4, smem = (size_t)bins * 20;
     k_hist<Src><<<grid, kPartThreads, smem_h, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, sorted_pos, error_bits);
     dim3 sg((bins + 255) / 256, L.ngroups);
     k_scan_group_sums<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part);
@@ -216,13 +210,13 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
 
     // ---- stage 1 + partition by cell ----
     SrcUser su; su.b = *b; su.n_cells = C;
-    Grouped g0 = grouped_at(ws, L, 0);
+    GroupRec *g0 = grouped_at(ws, L, 0);
     rc = partition_pass(h, s, su, L, 0, ws, b->pos, error_bits, m_ptr, g0);
     if (rc) return rc;
-    Grouped g = g0;
+    GroupRec *g = g0;
     if (L.passes == 2) {
         SrcGrouped sg; sg.a = g0; sg.m = m_ptr;
-        Grouped g1 = grouped_at(ws, L, 1);
+        GroupRec *g1 = grouped_at(ws, L, 1);
         rc = partition_pass(h, s, sg, L, 1, ws, nullptr, error_bits, nullptr, g1);
         if (rc) return rc;
         g = g1;

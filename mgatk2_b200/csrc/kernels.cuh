@@ -34,24 +34,22 @@ constexpr int GF_PROCESS = 1, GF_STRAND = 2, GF_KEEP = 4, GF_CELL_SHIFT = 8;   /
 // KeyRec.mq layout: mapq | strand<<8 | paired<<9
 constexpr int GMQ_STRAND = 0x100, GMQ_PAIRED = 0x200;
 
-// Records that passed stage 1, grouped by cell, BAM order inside a cell. 16-byte records so the
-// scattered side of the partition is one full-width store per record.
-struct __align__(16) KeyRec { int32_t cell; int32_t pos; u32 tlen; u32 mq; };   // dedup key (+mapq, strand, paired)
-struct __align__(8) LocRec { u32 off; u32 len; };                               // blob offset (16 B units), l_seq | n_cigar<<16
+// Records that passed stage 1, grouped by cell, BAM order inside a cell: one 32-byte sector per record, so
+// the scattered side of the partition writes whole sectors (no read-modify-write of partial sectors in L2).
+struct __align__(32) GroupRec {
+    int32_t cell; int32_t pos; u32 tlen; u32 mq;       // dedup key (+ mapq | strand << 8 | paired << 9)
+    u32 off; u32 len; u32 pad0; u32 pad1;              // blob offset (16 B units), l_seq | n_cigar << 16
+};
 struct __align__(16) ReadRec { int32_t pos; u32 off; u32 len; u32 flags; };     // what k_pileup consumes (from k_dedup)
-struct Grouped { KeyRec *key; LocRec *loc; };
-struct Item { KeyRec k; LocRec l; };
 
 struct Unit { int32_t cell, t0, t1, rbeg, rend; };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 // ---------------------------------------------------------------------------------------------
-// Stable counting partition by a digit of the cell index.
-// Each warp owns a contiguous chunk of records and a private histogram in shared memory, so ranks
-// follow record order without atomics: match_any groups the lanes of one 32-record step by digit,
-// the lowest lane of each group bumps the private counter. Loads run one group of steps ahead of
-// the ranking so several 128-byte requests per array are in flight per warp.
+// Stable counting partition by a digit of the cell index: per-CTA digit histograms of contiguous chunks
+// (k_hist), an exclusive scan in (digit, chunk) order (k_scan_*), then a scatter in which every CTA walks
+// its chunk in order against its own running offsets (k_scatter).
 // ---------------------------------------------------------------------------------------------
 struct SrcUser {          // pass 0: reads the caller's SoA batch and applies the stage-1 filter
     mgatk_batch b;
@@ -62,27 +60,34 @@ struct SrcUser {          // pass 0: reads the caller's SoA batch and applies th
         const int c = b.bc_idx[i];
         return ((b.flag[i] & 0x904) || c < 0 || c >= n_cells) ? -1 : c;
     }
-    __device__ __forceinline__ Item load(int64_t i) const {
-        Item it;
+    __device__ __forceinline__ GroupRec load(int64_t i) const {
+        GroupRec r;
         const int32_t t = b.tlen[i];
         const uint16_t f = b.flag[i];
         const int c = b.bc_idx[i];
-        it.k.cell = ((f & 0x904) || c < 0 || c >= n_cells) ? -1 : c;
-        it.k.pos = b.pos[i];
-        it.k.tlen = t < 0 ? (u32)(-(int64_t)t) : (u32)t;     // abs(read.template_length), readers.py:124
-        it.k.mq = (u32)b.mapq[i] | ((f & 0x10) ? GMQ_STRAND : 0) | ((f & 0x1) ? GMQ_PAIRED : 0);
-        it.l.off = b.blob_off[i];
-        it.l.len = (u32)b.l_seq[i] | ((u32)b.n_cigar[i] << 16);
-        return it;
+        r.cell = ((f & 0x904) || c < 0 || c >= n_cells) ? -1 : c;
+        r.pos = b.pos[i];
+        r.tlen = t < 0 ? (u32)(-(int64_t)t) : (u32)t;       // abs(read.template_length), readers.py:124
+        r.mq = (u32)b.mapq[i] | ((f & 0x10) ? GMQ_STRAND : 0) | ((f & 0x1) ? GMQ_PAIRED : 0);
+        r.off = b.blob_off[i];
+        r.len = (u32)b.l_seq[i] | ((u32)b.n_cigar[i] << 16);
+        r.pad0 = 0; r.pad1 = 0;
+        return r;
     }
 };
 
 struct SrcGrouped {       // pass 1 of a two-digit partition: already filtered, count on the device
-    Grouped a;
+    const GroupRec *a;
     const int64_t *m;
     __device__ __forceinline__ int64_t count() const { return *m; }
-    __device__ __forceinline__ int cell(int64_t i) const { return a.key[i].cell; }
-    __device__ __forceinline__ Item load(int64_t i) const { Item it; it.k = a.key[i]; it.l = a.loc[i]; return it; }
+    __device__ __forceinline__ int cell(int64_t i) const { return a[i].cell; }
+    __device__ __forceinline__ GroupRec load(int64_t i) const {
+        GroupRec r;
+        const uint4 lo = reinterpret_cast<const uint4 *>(a + i)[0], hi = reinterpret_cast<const uint4 *>(a + i)[1];
+        r.cell = (int32_t)lo.x; r.pos = (int32_t)lo.y; r.tlen = lo.z; r.mq = lo.w;
+        r.off = hi.x; r.len = hi.y; r.pad0 = 0; r.pad1 = 0;
+        return r;
+    }
 };
 
 constexpr int kPartThreads = 256;  // records per CTA step
@@ -173,54 +178,59 @@ __global__ void k_scan_apply(u32 *__restrict__ mat, int nchunks, int bins, const
     for (int w = w0; w < w1; w++) { u32 v = mat[(size_t)w * bins + b]; mat[(size_t)w * bins + b] = run; run += v; }
 }
 
-// Stable scatter. A CTA walks its chunk in steps of 256 records in BAM order: every thread loads one
-// record (the next step's loads are issued before the current one is ranked), warp 0 turns the 256
-// digits into destination slots against the CTA's running offsets (match_any per 32 records, in
-// order, so ranks follow record order without atomics), then every thread stores its own record.
-// One running-offset table per CTA keeps the number of open write heads small enough for L2 to
-// merge the 16-byte stores into full sectors.
+// Stable scatter. A CTA walks its chunk in steps of 256 records in BAM order, one record per thread (the
+// next step's loads are issued before the current one is ranked). Ranking is parallel over the warps:
+// match_any groups the lanes of a warp by digit, the group leaders add their group size into the byte of
+// their warp in a packed 64-bit per-digit counter (8 warps x 8 bits), and after one barrier every thread
+// reads "records of my digit in earlier warps" out of the lower bytes - ranks follow record order with
+// one shared-memory atomic per (warp, digit) and two barriers per step (the packed counters are double
+// buffered). Every record leaves as one full 32-byte sector.
+constexpr int kPartWarps = kPartThreads / 32;
+static_assert(kPartWarps == 8, "the packed per-digit counter holds one byte per warp");
+
+__device__ __forceinline__ u32 byte_sum(u64 v) {
+    return (u32)__dp4a((u32)v, 0x01010101u, __dp4a((u32)(v >> 32), 0x01010101u, 0u));
+}
+
 template <class Src>
 __global__ void __launch_bounds__(kPartThreads)
-k_scatter(Src src, int64_t chunk, int nchunks, int shift, int bins, const u32 *__restrict__ mat, Grouped dst) {
-    extern __shared__ u32 smem[];
-    u32 *off = smem;                                       // [bins] running destination offsets
-    int *sdig = reinterpret_cast<int *>(smem + bins);      // [256] digit of each record of the step
-    u32 *sslot = smem + bins + kPartThreads;               // [256] destination slot
+k_scatter(Src src, int64_t chunk, int nchunks, int shift, int bins, const u32 *__restrict__ mat, GroupRec *__restrict__ dst) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    u64 *packed = reinterpret_cast<u64 *>(smem_raw);                   // [2][bins] per-warp byte counters of the step
+    u32 *off = reinterpret_cast<u32 *>(smem_raw + (size_t)2 * bins * 8);   // [bins] running destination offsets
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const u32 *row = mat + (size_t)blockIdx.x * bins;
-    for (int b = t; b < bins; b += kPartThreads) off[b] = row[b];
+    for (int b = t; b < bins; b += kPartThreads) { off[b] = row[b]; packed[b] = 0; packed[bins + b] = 0; }
     const int64_t n = src.count();
     int64_t beg = (int64_t)blockIdx.x * chunk, end = beg + chunk;
     if (end > n) end = n;
     const u32 lt = (1u << lane) - 1;
-    Item nxt; nxt.k.cell = -1;
+    const u64 below = wid == 0 ? 0ull : (~0ull >> (64 - 8 * wid));     // bytes of the earlier warps
+    GroupRec nxt; nxt.cell = -1;
     if (beg + t < end) nxt = src.load(beg + t);
-    for (int64_t i0 = beg; i0 < end; i0 += kPartThreads) {
-        const Item cur = nxt;
-        nxt.k.cell = -1;
+    __syncthreads();
+    int buf = 0;
+    for (int64_t i0 = beg; i0 < end; i0 += kPartThreads, buf ^= 1) {
+        const GroupRec cur = nxt;
+        nxt.cell = -1;
         if (i0 + kPartThreads + t < end) nxt = src.load(i0 + kPartThreads + t);
-        const int c = cur.k.cell;
+        const int c = cur.cell;
         const int d = c >= 0 ? (c >> shift) & (bins - 1) : -1;
-        sdig[t] = d;
+        u64 *pk = packed + (size_t)buf * bins;
+        const u32 peers = __match_any_sync(kFull, d);
+        const bool leader = d >= 0 && lane == __ffs(peers) - 1;
+        if (leader) atomicAdd((unsigned long long *)&pk[d], (unsigned long long)__popc(peers) << (8 * wid));
         __syncthreads();
-        if (wid == 0) {
-#pragma unroll
-            for (int k = 0; k < kPartThreads / 32; k++) {
-                const int dk = sdig[32 * k + lane];
-                const u32 peers = __match_any_sync(kFull, dk);
-                u32 base = 0;
-                if (dk >= 0) base = off[dk];
-                __syncwarp();
-                if (dk >= 0 && lane == __ffs(peers) - 1) off[dk] = base + __popc(peers);
-                __syncwarp();
-                sslot[32 * k + lane] = base + __popc(peers & lt);
-            }
-        }
+        u64 v = 0; u32 base = 0;
+        if (d >= 0) { v = pk[d]; base = off[d]; }
         __syncthreads();
         if (d >= 0) {
-            const size_t dd = sslot[t];
-            dst.key[dd] = cur.k;                           // one 16-byte and one 8-byte store per record
-            dst.loc[dd] = cur.l;
+            const u64 lower = v & below;
+            if (leader && lower == 0) { off[d] = base + byte_sum(v); pk[d] = 0; }   // first warp that holds the digit
+            const size_t dd = (size_t)base + byte_sum(lower) + __popc(peers & lt);
+            uint4 *o = reinterpret_cast<uint4 *>(dst + dd);
+            o[0] = make_uint4((u32)cur.cell, (u32)cur.pos, cur.tlen, cur.mq);
+            o[1] = make_uint4(cur.off, cur.len, 0u, 0u);
         }
     }
 }
@@ -236,14 +246,16 @@ k_scatter(Src src, int64_t chunk, int nchunks, int shift, int bins, const u32 *_
 // their index from a ticket, so a block only ever waits for blocks that are already running).
 // ---------------------------------------------------------------------------------------------
 constexpr int kDedupThreads = 512;
+constexpr int kDedupRounds = 4;                              // records per thread
+constexpr int kDedupTile = kDedupThreads * kDedupRounds;
 constexpr u64 kScanAggregate = 1ull << 62, kScanPrefix = 2ull << 62, kScanValue = (1ull << 62) - 1;
 
 __global__ void __launch_bounds__(kDedupThreads)
-k_dedup(Grouped g, const int64_t *__restrict__ m_ptr, ReadRec *__restrict__ recs, int dedup_mode, int min_mapq,
+k_dedup(const GroupRec *__restrict__ g, const int64_t *__restrict__ m_ptr, ReadRec *__restrict__ recs, int dedup_mode, int min_mapq,
         mgatk_cell_qc *__restrict__ qc, mgatk_stats *__restrict__ stats, u32 *__restrict__ ticket,
         u64 *__restrict__ scan_state, int64_t *__restrict__ n_proc_out) {
     __shared__ u32 s_cnt[4];
-    __shared__ u32 s_warp[kDedupThreads / 32];
+    __shared__ u32 s_warp[kDedupRounds][kDedupThreads / 32];
     __shared__ u32 s_blk;
     __shared__ u64 s_prefix;
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
@@ -251,76 +263,101 @@ k_dedup(Grouped g, const int64_t *__restrict__ m_ptr, ReadRec *__restrict__ recs
     __syncthreads();
     const u32 blk = s_blk;
     const int64_t m = *m_ptr;
-    const int64_t i = (int64_t)blk * kDedupThreads + threadIdx.x;
     const int lane = lane_id(), wid = threadIdx.x >> 5;
-    int cell = -1;
-    bool keep = false, paired = false, process = false;
-    ReadRec rr; rr.pos = 0; rr.off = 0; rr.len = 0; rr.flags = 0;
-    if (i < m) {
-        const KeyRec me = g.key[i];
-        const LocRec lc = g.loc[i];
-        cell = me.cell;
-        const u32 strand = me.mq & GMQ_STRAND;
-        paired = me.mq & GMQ_PAIRED;
-        bool len_dup = false, pos_dup = false;
-        if (dedup_mode != MGATK_DEDUP_NONE) {
-            for (int64_t j = i - 1; j >= 0; j--) {
-                const KeyRec o = g.key[j];
-                if (o.pos != me.pos || o.cell != me.cell) break;
-                if ((o.mq & GMQ_STRAND) == strand) {
-                    pos_dup = true;
-                    if (o.tlen == me.tlen) { len_dup = true; break; }
+    ReadRec rr[kDedupRounds];
+    u32 pm[kDedupRounds];
+    u32 n_keep = 0, n_len = 0, n_pos = 0, n_empty = 0;
+#pragma unroll
+    for (int k = 0; k < kDedupRounds; k++) {
+        const int64_t i = (int64_t)blk * kDedupTile + k * kDedupThreads + threadIdx.x;
+        int cell = -1;
+        bool keep = false, paired = false, process = false;
+        rr[k].pos = 0; rr[k].off = 0; rr[k].len = 0; rr[k].flags = 0;
+        if (i < m) {
+            const uint4 me = reinterpret_cast<const uint4 *>(g + i)[0];      // cell, pos, |tlen|, mq
+            const uint2 lc = reinterpret_cast<const uint2 *>(g + i)[2];      // off, len
+            cell = (int)me.x;
+            const u32 strand = me.w & GMQ_STRAND;
+            paired = me.w & GMQ_PAIRED;
+            bool len_dup = false, pos_dup = false;
+            if (dedup_mode != MGATK_DEDUP_NONE) {
+                for (int64_t j = i - 1; j >= 0; j--) {
+                    const uint4 o = reinterpret_cast<const uint4 *>(g + j)[0];
+                    if (o.y != me.y || o.x != me.x) break;
+                    if ((o.w & GMQ_STRAND) == strand) {
+                        pos_dup = true;
+                        if (o.z == me.z) { len_dup = true; break; }
+                    }
                 }
             }
+            keep = dedup_mode == MGATK_DEDUP_FRAGMENT_LENGTH ? !len_dup : dedup_mode == MGATK_DEDUP_POSITION_ONLY ? !pos_dup : true;
+            // pileup.py:33-34 mapq gate (after dedup, Q2). An empty SEQ makes the reference raise
+            // (readers.py:157); such survivors are reported in stats.n_empty_seq and not piled up.
+            process = keep && (int)(me.w & 0xff) >= min_mapq && (lc.y & 0xffff) != 0;
+            rr[k].pos = (int32_t)me.y; rr[k].off = lc.x; rr[k].len = lc.y;
+            rr[k].flags = GF_PROCESS | (strand ? GF_STRAND : 0) | GF_KEEP | ((u32)cell << GF_CELL_SHIFT);
+            n_len += len_dup; n_pos += pos_dup; n_keep += keep; n_empty += keep && (lc.y & 0xffff) == 0;
         }
-        keep = dedup_mode == MGATK_DEDUP_FRAGMENT_LENGTH ? !len_dup : dedup_mode == MGATK_DEDUP_POSITION_ONLY ? !pos_dup : true;
-        // pileup.py:33-34 mapq gate (after dedup, Q2). An empty SEQ makes the reference raise
-        // (readers.py:157); such survivors are reported in stats.n_empty_seq and not piled up.
-        process = keep && (int)(me.mq & 0xff) >= min_mapq && (lc.len & 0xffff) != 0;
-        rr.pos = me.pos; rr.off = lc.off; rr.len = lc.len;
-        rr.flags = GF_PROCESS | (strand ? GF_STRAND : 0) | GF_KEEP | ((u32)cell << GF_CELL_SHIFT);
-        if (len_dup) atomicAdd(&s_cnt[1], 1u);
-        if (pos_dup) atomicAdd(&s_cnt[2], 1u);
-        if (keep) { atomicAdd(&s_cnt[0], 1u); if ((lc.len & 0xffff) == 0) atomicAdd(&s_cnt[3], 1u); }
+        // per-cell survivors: lanes of a warp mostly share one cell
+        const u32 peers = __match_any_sync(kFull, cell);
+        const u32 kept = __ballot_sync(kFull, keep), paird = __ballot_sync(kFull, keep && paired);
+        if (cell >= 0 && lane == __ffs(peers) - 1) {
+            const u32 nk = __popc(kept & peers), np = __popc(paird & peers);
+            if (nk) atomicAdd(&qc[cell].n_reads, nk);
+            if (np) atomicAdd(&qc[cell].n_paired, np);
+        }
+        pm[k] = __ballot_sync(kFull, process);
+        if (lane == 0) s_warp[k][wid] = __popc(pm[k]);
     }
-    // per-cell survivors: lanes of a warp mostly share one cell
-    const u32 peers = __match_any_sync(kFull, cell);
-    const u32 kept = __ballot_sync(kFull, keep), paird = __ballot_sync(kFull, keep && paired);
-    if (cell >= 0 && lane == __ffs(peers) - 1) {
-        const u32 nk = __popc(kept & peers), np = __popc(paird & peers);
-        if (nk) atomicAdd(&qc[cell].n_reads, nk);
-        if (np) atomicAdd(&qc[cell].n_paired, np);
+    for (int o = 16; o; o >>= 1) {
+        n_keep += __shfl_xor_sync(kFull, n_keep, o); n_len += __shfl_xor_sync(kFull, n_len, o);
+        n_pos += __shfl_xor_sync(kFull, n_pos, o); n_empty += __shfl_xor_sync(kFull, n_empty, o);
     }
-    // stable compaction of the reads that are piled up
-    const u32 pm = __ballot_sync(kFull, process);
-    if (lane == 0) s_warp[wid] = __popc(pm);
+    if (lane == 0) {
+        if (n_keep) atomicAdd(&s_cnt[0], n_keep);
+        if (n_len) atomicAdd(&s_cnt[1], n_len);
+        if (n_pos) atomicAdd(&s_cnt[2], n_pos);
+        if (n_empty) atomicAdd(&s_cnt[3], n_empty);
+    }
     __syncthreads();
-    u32 before = 0, total = 0;
+    // stable compaction of the reads that are piled up: position inside the tile, then the tile's prefix
+    u32 before[kDedupRounds], total = 0;
 #pragma unroll
-    for (int w = 0; w < kDedupThreads / 32; w++) { const u32 v = s_warp[w]; if (w < wid) before += v; total += v; }
-    if (threadIdx.x == 0) {
+    for (int k = 0; k < kDedupRounds; k++) {
+        before[k] = total;
+#pragma unroll
+        for (int w = 0; w < kDedupThreads / 32; w++) { const u32 v = s_warp[k][w]; if (w < wid) before[k] += v; total += v; }
+    }
+    if (wid == 0) {                                          // decoupled look-back, 32 predecessors at a time
         u64 prefix = 0;
-        if (blk == 0) {
-            atomicExch((unsigned long long *)&scan_state[0], kScanPrefix | (u64)total);
-        } else {
-            atomicExch((unsigned long long *)&scan_state[blk], kScanAggregate | (u64)total);
-            for (int64_t b = (int64_t)blk - 1; b >= 0; b--) {
-                u64 v;
-                do { v = *(volatile u64 *)&scan_state[b]; } while ((v & ~kScanValue) == 0);
-                prefix += v & kScanValue;
-                if (v & kScanPrefix) break;
-            }
-            atomicExch((unsigned long long *)&scan_state[blk], kScanPrefix | (prefix + total));
+        if (lane == 0) atomicExch((unsigned long long *)&scan_state[blk], (blk == 0 ? kScanPrefix : kScanAggregate) | (u64)total);
+        for (int64_t top = (int64_t)blk - 1; top >= 0; ) {
+            const int64_t b = top - lane;
+            u64 v = kScanPrefix;                             // below block 0: an empty prefix
+            if (b >= 0) do { v = *(volatile u64 *)&scan_state[b]; } while ((v & ~kScanValue) == 0);
+            const u32 has_prefix = __ballot_sync(kFull, (v & kScanPrefix) != 0);
+            const int stop = __ffs(has_prefix) - 1;          // nearest predecessor with a full prefix (or -1)
+            u64 add = (stop < 0 || lane <= stop) ? (v & kScanValue) : 0;
+            for (int o = 16; o; o >>= 1) add += __shfl_xor_sync(kFull, add, o);
+            prefix += add;
+            if (stop >= 0) break;
+            top -= 32;
         }
-        s_prefix = prefix;
-        if ((int64_t)(blk + 1) * kDedupThreads >= m && (int64_t)blk * kDedupThreads < (m > 0 ? m : 1)) *n_proc_out = (int64_t)(prefix + total);
-        if (s_cnt[0]) atomicAdd((u64 *)&stats->filtered_reads, (u64)s_cnt[0]);
-        if (s_cnt[1]) atomicAdd((u64 *)&stats->dup_with_length, (u64)s_cnt[1]);
-        if (s_cnt[2]) atomicAdd((u64 *)&stats->dup_position_only, (u64)s_cnt[2]);
-        if (s_cnt[3]) atomicAdd((u64 *)&stats->n_empty_seq, (u64)s_cnt[3]);
+        if (lane == 0) {
+            if (blk != 0) atomicExch((unsigned long long *)&scan_state[blk], kScanPrefix | (prefix + total));
+            s_prefix = prefix;
+            if ((int64_t)(blk + 1) * kDedupTile >= m && (int64_t)blk * kDedupTile < (m > 0 ? m : 1)) *n_proc_out = (int64_t)(prefix + total);
+            if (s_cnt[0]) atomicAdd((u64 *)&stats->filtered_reads, (u64)s_cnt[0]);
+            if (s_cnt[1]) atomicAdd((u64 *)&stats->dup_with_length, (u64)s_cnt[1]);
+            if (s_cnt[2]) atomicAdd((u64 *)&stats->dup_position_only, (u64)s_cnt[2]);
+            if (s_cnt[3]) atomicAdd((u64 *)&stats->n_empty_seq, (u64)s_cnt[3]);
+        }
     }
     __syncthreads();
-    if (process) recs[s_prefix + before + __popc(pm & ((1u << lane) - 1u))] = rr;
+    const u64 prefix = s_prefix;
+#pragma unroll
+    for (int k = 0; k < kDedupRounds; k++)
+        if ((pm[k] >> lane) & 1u) recs[prefix + before[k] + __popc(pm[k] & ((1u << lane) - 1u))] = rr[k];
 }
 
 // first compacted index of every cell: lower_bound on the cell field (records are grouped by cell)
