@@ -121,7 +121,7 @@ int partition_pass(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout
     u32 *mat = (u32 *)(ws + L.mat), *part = (u32 *)(ws + L.part);
     const int grid = L.nchunks;
     const size_t smem_h = (size_t)bins * 4, smem = (size_t)bins * 20;
-    k_hist<Src><<<grid, kPartThreads, smem_h, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, sorted_pos, error_bits);
+    k_hist<Src><<<grid, kHistThreads, smem_h, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, sorted_pos, error_bits);
     dim3 sg((bins + 255) / 256, L.ngroups);
     k_scan_group_sums<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part);
     k_scan_bases<<<1, 1024, 0, s>>>(part, L.ngroups, bins, m_out);

@@ -131,8 +131,10 @@ MG_HD void build_query_masks(const M &mem, u32 seq_addr /*4-aligned*/, u32 out /
     for (int w = 0; w < nq; w++) {
         u32 mA = 0, mC = 0, mG = 0, mT = 0;
         u32 carry = mem.ld32(qa);
+        const int rem = L - 32 * w;                          // bases left in this group of 32
 #pragma unroll
         for (int g = 0; g < 4; g++) {
+            if (8 * g >= rem) break;
             const u32 s = mem.ld32(seq_addr + 16u * w + 4u * g);
             const u32 w1 = mem.ld32(qa + 8u * g + 4u), w2 = mem.ld32(qa + 8u * g + 8u);
             const u32 ok = qual_ok8_top(funnel_r(carry, w1, qsh), funnel_r(w1, w2, qsh), qg);

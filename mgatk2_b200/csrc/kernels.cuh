@@ -24,13 +24,16 @@ typedef unsigned long long u64;
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kScanGroup = 64;        // chunks per scan group
+constexpr int kScanGroup = 16;        // chunks per scan group
 constexpr u32 kFull = 0xffffffffu;
 
 constexpr u32 ERR_UNSORTED = 1, ERR_EXTENT = 2, ERR_OVERFLOW_CAP = 4;
 
 // ReadRec.flags bits written by k_dedup, read by k_pileup
 constexpr int GF_PROCESS = 1, GF_STRAND = 2, GF_KEEP = 4, GF_CELL_SHIFT = 8;   // cell index in bits 8..31
+// set by k_pileup on its shared-memory copy: one aligned block covering all of SEQ; ReadRec.off then holds the
+// shared address of the read's query masks
+constexpr int GF_SIMPLE = 8;
 // KeyRec.mq layout: mapq | strand<<8 | paired<<9
 constexpr int GMQ_STRAND = 0x100, GMQ_PAIRED = 0x200;
 
@@ -60,17 +63,27 @@ struct SrcUser {          // pass 0: reads the caller's SoA batch and applies th
         const int c = b.bc_idx[i];
         return ((b.flag[i] & 0x904) || c < 0 || c >= n_cells) ? -1 : c;
     }
-    __device__ __forceinline__ GroupRec load(int64_t i) const {
+    struct Raw { int32_t pos, tlen, bc; u32 off; uint16_t flag, lseq, ncig; uint8_t mapq; bool valid; };
+    __device__ __forceinline__ Raw load_raw(int64_t i, bool valid) const {     // loads only; combined one step later
+        Raw r; r.valid = valid;
+        r.pos = 0; r.tlen = 0; r.bc = -1; r.off = 0; r.flag = 0x4; r.lseq = 0; r.ncig = 0; r.mapq = 0;
+        if (valid) {
+            r.pos = b.pos[i]; r.tlen = b.tlen[i]; r.bc = b.bc_idx[i]; r.off = b.blob_off[i];
+            r.flag = b.flag[i]; r.lseq = b.l_seq[i]; r.ncig = b.n_cigar[i]; r.mapq = b.mapq[i];
+        }
+        return r;
+    }
+    __device__ __forceinline__ GroupRec finish(const Raw &w) const {
         GroupRec r;
-        const int32_t t = b.tlen[i];
-        const uint16_t f = b.flag[i];
-        const int c = b.bc_idx[i];
-        r.cell = ((f & 0x904) || c < 0 || c >= n_cells) ? -1 : c;
-        r.pos = b.pos[i];
+        const int32_t t = w.tlen;
+        const uint16_t f = w.flag;
+        const int c = w.bc;
+        r.cell = (!w.valid || (f & 0x904) || c < 0 || c >= n_cells) ? -1 : c;
+        r.pos = w.pos;
         r.tlen = t < 0 ? (u32)(-(int64_t)t) : (u32)t;       // abs(read.template_length), readers.py:124
-        r.mq = (u32)b.mapq[i] | ((f & 0x10) ? GMQ_STRAND : 0) | ((f & 0x1) ? GMQ_PAIRED : 0);
-        r.off = b.blob_off[i];
-        r.len = (u32)b.l_seq[i] | ((u32)b.n_cigar[i] << 16);
+        r.mq = (u32)w.mapq | ((f & 0x10) ? GMQ_STRAND : 0) | ((f & 0x1) ? GMQ_PAIRED : 0);
+        r.off = w.off;
+        r.len = (u32)w.lseq | ((u32)w.ncig << 16);
         r.pad0 = 0; r.pad1 = 0;
         return r;
     }
@@ -81,11 +94,17 @@ struct SrcGrouped {       // pass 1 of a two-digit partition: already filtered, 
     const int64_t *m;
     __device__ __forceinline__ int64_t count() const { return *m; }
     __device__ __forceinline__ int cell(int64_t i) const { return a[i].cell; }
-    __device__ __forceinline__ GroupRec load(int64_t i) const {
+    struct Raw { uint4 lo, hi; bool valid; };
+    __device__ __forceinline__ Raw load_raw(int64_t i, bool valid) const {
+        Raw r; r.valid = valid;
+        r.lo = make_uint4(0xffffffffu, 0u, 0u, 0u); r.hi = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) { r.lo = reinterpret_cast<const uint4 *>(a + i)[0]; r.hi = reinterpret_cast<const uint4 *>(a + i)[1]; }
+        return r;
+    }
+    __device__ __forceinline__ GroupRec finish(const Raw &w) const {
         GroupRec r;
-        const uint4 lo = reinterpret_cast<const uint4 *>(a + i)[0], hi = reinterpret_cast<const uint4 *>(a + i)[1];
-        r.cell = (int32_t)lo.x; r.pos = (int32_t)lo.y; r.tlen = lo.z; r.mq = lo.w;
-        r.off = hi.x; r.len = hi.y; r.pad0 = 0; r.pad1 = 0;
+        r.cell = w.valid ? (int32_t)w.lo.x : -1; r.pos = (int32_t)w.lo.y; r.tlen = w.lo.z; r.mq = w.lo.w;
+        r.off = w.hi.x; r.len = w.hi.y; r.pad0 = 0; r.pad1 = 0;
         return r;
     }
 };
@@ -94,23 +113,24 @@ constexpr int kPartThreads = 256;  // records per CTA step
 constexpr int kHistAhead = 4;      // steps loaded before counting (k_hist)
 
 // Per-CTA digit histogram of a contiguous chunk of records (order does not matter for counting).
+constexpr int kHistThreads = 1024;
 template <class Src>
-__global__ void __launch_bounds__(kPartThreads)
+__global__ void __launch_bounds__(kHistThreads)
 k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict__ mat,
        const int32_t *__restrict__ sorted_check_pos, u64 *__restrict__ error_bits) {
     extern __shared__ u32 smem[];
     u32 *h = smem;
-    for (int b = threadIdx.x; b < bins; b += kPartThreads) h[b] = 0;
+    for (int b = threadIdx.x; b < bins; b += kHistThreads) h[b] = 0;
     __syncthreads();
     const int64_t n = src.count();
     int64_t beg = (int64_t)blockIdx.x * chunk, end = beg + chunk;
     if (end > n) end = n;
     bool unsorted = false;
-    for (int64_t i0 = beg + threadIdx.x; i0 < end; i0 += kPartThreads * kHistAhead) {
+    for (int64_t i0 = beg + threadIdx.x; i0 < end; i0 += kHistThreads * kHistAhead) {
         int d[kHistAhead];
 #pragma unroll
         for (int k = 0; k < kHistAhead; k++) {
-            const int64_t i = i0 + (int64_t)kPartThreads * k;
+            const int64_t i = i0 + (int64_t)kHistThreads * k;
             d[k] = -1;
             if (i < end) {
                 const int c = src.cell(i);
@@ -124,16 +144,20 @@ k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict
     if (unsorted) atomicOr(error_bits, (u64)ERR_UNSORTED);
     __syncthreads();
     u32 *row = mat + (size_t)blockIdx.x * bins;
-    for (int b = threadIdx.x; b < bins; b += kPartThreads) row[b] = h[b];
+    for (int b = threadIdx.x; b < bins; b += kHistThreads) row[b] = h[b];
 }
 
 // scan of mat[chunk][bin] in (bin, chunk) order: S1 group sums, S2 bases, S3 in-place exclusive prefixes
 __global__ void k_scan_group_sums(const u32 *__restrict__ mat, int nchunks, int bins, u32 *__restrict__ part) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
     if (b >= bins) return;
-    const int w0 = g * kScanGroup, w1 = min(nchunks, w0 + kScanGroup);
+    const int w0 = g * kScanGroup;
+    u32 v[kScanGroup];
+#pragma unroll
+    for (int k = 0; k < kScanGroup; k++) v[k] = w0 + k < nchunks ? mat[(size_t)(w0 + k) * bins + b] : 0u;
     u32 s = 0;
-    for (int w = w0; w < w1; w++) s += mat[(size_t)w * bins + b];
+#pragma unroll
+    for (int k = 0; k < kScanGroup; k++) s += v[k];
     part[(size_t)g * bins + b] = s;
 }
 
@@ -173,64 +197,68 @@ k_scan_bases(u32 *__restrict__ part, int ngroups, int bins, int64_t *__restrict_
 __global__ void k_scan_apply(u32 *__restrict__ mat, int nchunks, int bins, const u32 *__restrict__ part) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
     if (b >= bins) return;
-    const int w0 = g * kScanGroup, w1 = min(nchunks, w0 + kScanGroup);
+    const int w0 = g * kScanGroup;
+    u32 v[kScanGroup];
+#pragma unroll
+    for (int k = 0; k < kScanGroup; k++) v[k] = w0 + k < nchunks ? mat[(size_t)(w0 + k) * bins + b] : 0u;
     u32 run = part[(size_t)g * bins + b];
-    for (int w = w0; w < w1; w++) { u32 v = mat[(size_t)w * bins + b]; mat[(size_t)w * bins + b] = run; run += v; }
+#pragma unroll
+    for (int k = 0; k < kScanGroup; k++) if (w0 + k < nchunks) { mat[(size_t)(w0 + k) * bins + b] = run; run += v[k]; }
 }
 
 // Stable scatter. A CTA walks its chunk in steps of 256 records in BAM order, one record per thread (the
 // next step's loads are issued before the current one is ranked). Ranking is parallel over the warps:
 // match_any groups the lanes of a warp by digit, the group leaders add their group size into the byte of
-// their warp in a packed 64-bit per-digit counter (8 warps x 8 bits), and after one barrier every thread
+// their warp in a packed per-digit counter (8 warps x 8 bits, two words), and after one barrier every thread
 // reads "records of my digit in earlier warps" out of the lower bytes - ranks follow record order with
 // one shared-memory atomic per (warp, digit) and two barriers per step (the packed counters are double
 // buffered). Every record leaves as one full 32-byte sector.
 constexpr int kPartWarps = kPartThreads / 32;
 static_assert(kPartWarps == 8, "the packed per-digit counter holds one byte per warp");
 
-__device__ __forceinline__ u32 byte_sum(u64 v) {
-    return (u32)__dp4a((u32)v, 0x01010101u, __dp4a((u32)(v >> 32), 0x01010101u, 0u));
-}
-
 template <class Src>
 __global__ void __launch_bounds__(kPartThreads)
 k_scatter(Src src, int64_t chunk, int nchunks, int shift, int bins, const u32 *__restrict__ mat, GroupRec *__restrict__ dst) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    u64 *packed = reinterpret_cast<u64 *>(smem_raw);                   // [2][bins] per-warp byte counters of the step
+    uint2 *packed = reinterpret_cast<uint2 *>(smem_raw);               // [2][bins] per-warp byte counters of the step (x: warps 0-3, y: warps 4-7)
     u32 *off = reinterpret_cast<u32 *>(smem_raw + (size_t)2 * bins * 8);   // [bins] running destination offsets
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const u32 *row = mat + (size_t)blockIdx.x * bins;
-    for (int b = t; b < bins; b += kPartThreads) { off[b] = row[b]; packed[b] = 0; packed[bins + b] = 0; }
+    for (int b = t; b < bins; b += kPartThreads) { off[b] = row[b]; packed[b] = make_uint2(0u, 0u); packed[bins + b] = make_uint2(0u, 0u); }
     const int64_t n = src.count();
     int64_t beg = (int64_t)blockIdx.x * chunk, end = beg + chunk;
     if (end > n) end = n;
     const u32 lt = (1u << lane) - 1;
-    const u64 below = wid == 0 ? 0ull : (~0ull >> (64 - 8 * wid));     // bytes of the earlier warps
-    GroupRec nxt; nxt.cell = -1;
-    if (beg + t < end) nxt = src.load(beg + t);
+    const u32 below_x = wid >= 4 ? 0xffffffffu : wid == 0 ? 0u : (0xffffffffu >> (32 - 8 * wid));        // bytes of the earlier warps
+    const u32 below_y = wid <= 4 ? 0u : (0xffffffffu >> (32 - 8 * (wid - 4)));
+    typename Src::Raw r1 = src.load_raw(beg + t, beg + t < end);                        // two steps of loads in flight
+    typename Src::Raw r2 = src.load_raw(beg + kPartThreads + t, beg + kPartThreads + t < end);
     __syncthreads();
     int buf = 0;
     for (int64_t i0 = beg; i0 < end; i0 += kPartThreads, buf ^= 1) {
-        const GroupRec cur = nxt;
-        nxt.cell = -1;
-        if (i0 + kPartThreads + t < end) nxt = src.load(i0 + kPartThreads + t);
+        const GroupRec cur = src.finish(r1);
+        r1 = r2;
+        r2 = src.load_raw(i0 + 2 * kPartThreads + t, i0 + 2 * kPartThreads + t < end);
         const int c = cur.cell;
         const int d = c >= 0 ? (c >> shift) & (bins - 1) : -1;
-        u64 *pk = packed + (size_t)buf * bins;
+        uint2 *pk = packed + (size_t)buf * bins;
         const u32 peers = __match_any_sync(kFull, d);
         const bool leader = d >= 0 && lane == __ffs(peers) - 1;
-        if (leader) atomicAdd((unsigned long long *)&pk[d], (unsigned long long)__popc(peers) << (8 * wid));
+        if (leader) atomicAdd(wid < 4 ? &pk[d].x : &pk[d].y, (u32)__popc(peers) << (8 * (wid & 3)));
         __syncthreads();
-        u64 v = 0; u32 base = 0;
+        uint2 v = make_uint2(0u, 0u); u32 base = 0;
         if (d >= 0) { v = pk[d]; base = off[d]; }
         __syncthreads();
         if (d >= 0) {
-            const u64 lower = v & below;
-            if (leader && lower == 0) { off[d] = base + byte_sum(v); pk[d] = 0; }   // first warp that holds the digit
-            const size_t dd = (size_t)base + byte_sum(lower) + __popc(peers & lt);
-            uint4 *o = reinterpret_cast<uint4 *>(dst + dd);
-            o[0] = make_uint4((u32)cur.cell, (u32)cur.pos, cur.tlen, cur.mq);
-            o[1] = make_uint4(cur.off, cur.len, 0u, 0u);
+            const u32 lx = v.x & below_x, ly = v.y & below_y;
+            if (leader && (lx | ly) == 0) {                  // first warp that holds the digit
+                off[d] = base + __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, 0u));
+                pk[d] = make_uint2(0u, 0u);
+            }
+            const size_t dd = (size_t)base + __dp4a(lx, 0x01010101u, __dp4a(ly, 0x01010101u, 0u)) + __popc(peers & lt);
+            // one 256-bit store per record: a scattered store costs the LSU one pass per lane whatever its width
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + dd), "r"((u32)cur.cell), "r"((u32)cur.pos),
+                         "r"(cur.tlen), "r"(cur.mq), "r"(cur.off), "r"(cur.len), "r"(0u), "r"(0u) : "memory");
         }
     }
 }
@@ -502,6 +530,7 @@ constexpr int kStageMaxBytes = 1024; // blob + query masks of one read; larger r
 constexpr int kStageSlack = 64;      // phase A may load this far past the last staged byte
 constexpr u32 kUnstaged = 0xffffffffu;
 constexpr int kSplitChunks = 4;      // "deep" units: at most this many chunks; their reads are staged in batches
+constexpr int kChunkSeg = 576;       // chunks per pass over a unit (the 518 chunks of chrM in one)
 constexpr int kAccWords = 10 * 32;   // deep units: counts of one chunk, [8 base x strand + 2 Tn5][32]
 
 // dynamic shared memory of k_pileup: staged records, their blob offsets, the blob + mask bytes
@@ -533,34 +562,17 @@ __device__ __forceinline__ u32 warp_transpose(u32 x, int lane) {
 }
 
 // Counts of chunk `ch` of the unit from the reads [rb, rb + nb) of the unit (a batch whose first `ns`
-// records are staged), part `part` of `nparts`: lane = position on return.
+// records are staged), part `part` of `nparts`: lane = position on return. `first` is the first read of the
+// batch that can reach the chunk.
 __device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un, const ReadRec *s_rec, const u32 *s_so,
-                                            u32 blob_addr, int rb, int nb, int ns, int ch, int part, int nparts,
-                                            int lane, int q_lo, u32 (&cnt)[10], bool &extent_err) {
+                                            int first, u32 blob_addr, int rb, int nb, int ns, int ch, int part,
+                                            int nparts, int lane, int q_lo, u32 (&cnt)[10], bool &extent_err) {
     const SharedMem smem;
     const ReadRec *g_rec = a.recs + un.rbeg + rb;
     const int c0 = un.t0 + 32 * ch, c1 = c0 + 32;
     const int skip_le = c0 - a.extent;               // reads starting at or before this cannot reach the chunk
-    // first candidate: reads are sorted by start; two 32-way probes over the batch
-    int ra;
-    {
-        const int step = (nb + 31) >> 5;
-        int j = lane * step;
-        int pj = 0x7fffffff;
-        if (j < nb) pj = j < ns ? s_rec[j].pos : g_rec[j].pos;
-        const int seg = __popc(__ballot_sync(kFull, pj <= skip_le));      // probes <= skip_le form a prefix
-        const int base = seg ? (seg - 1) * step : 0;
-        j = base + lane;
-        int cntb = 0;
-        for (int k = 0; k < step; k += 32) {
-            const int jj = j + k;
-            int pp = 0x7fffffff;
-            if (jj < nb && jj < base + step) pp = jj < ns ? s_rec[jj].pos : g_rec[jj].pos;
-            cntb += __popc(__ballot_sync(kFull, pp <= skip_le));
-        }
-        ra = seg ? base + cntb : 0;
-    }
-    for (int r = ra + 32 * part; r < nb; r += 32 * nparts) {
+    first = min(max(first, 0), nb);                  // (stale table entries if the batch was not sorted: flagged elsewhere)
+    for (int r = first + 32 * part; r < nb; r += 32 * nparts) {
         const int j = r + lane;
         ReadRec rr; rr.pos = 0x7fffffff; rr.off = 0; rr.len = 0; rr.flags = 0;
         u32 so = kUnstaged;
@@ -571,53 +583,62 @@ __device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un,
         const bool cand = pos < c1 && pos > skip_le && (rr.flags & GF_PROCESS);   // implies j < nb
         if (__ballot_sync(kFull, cand)) {
             const int strand = (rr.flags & GF_STRAND) ? 1 : 0;
+            const int L = rr.len & 0xffff;
+            const int nq = (L + 31) >> 5;
+            const bool simple = (rr.flags & GF_SIMPLE) != 0;
             u32 m[4] = {0u, 0u, 0u, 0u};
             u32 m5 = 0u;
             if (cand) {
-                const int L = rr.len & 0xffff, ncig = rr.len >> 16;
-                const bool staged = so != kUnstaged;
-                const u32 sb = blob_addr + (staged ? so : 0u);                   // shared address of the staged blob
-                const u32 *cig = reinterpret_cast<const u32 *>(a.blob + 16 * (size_t)rr.off);
-                if (j >= ns && (pos >= c0 || (ch == 0 && rb == 0))) {   // no staged record: verify the declared extent here
-                    if (L > a.extent) extent_err = true;
-                    int span = 0;
-                    for (int ci = 0; ci < ncig; ci++) {
-                        const u32 w = __ldg(cig + ci);
-                        const int op = w & 15;
-                        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += min((int)(w >> 4), kOpCap);
-                        if (span > a.extent) { extent_err = true; break; }
-                    }
-                }
                 // Tn5 site (pileup.py:43-50): reverse = start + len(SEQ) - 1, forward = start
                 const int t5 = strand ? pos + L - 1 : pos;
                 if (t5 >= c0 && t5 < c1 && t5 < a.P) m5 = 1u << (t5 - c0);
-                // aligned blocks overlapping this chunk (pileup.py:55-95)
-                const int q_hi = a.dist > 0 ? L - a.dist : L;
-                const int nq = (L + 31) >> 5;
-                const u32 mask_s = sb + (u32)((4 * ncig + ((L + 1) >> 1) + L + 15) & ~15);
-                int ref = pos, qp = 0;
-                for (int ci = 0; ci < ncig; ci++) {
-                    const u32 w = staged ? smem.ld32(sb + 4 * ci) : __ldg(cig + ci);
-                    const int op = w & 15;
-                    const int n = min((int)(w >> 4), kOpCap);
-                    if (op == 0 || op == 7 || op == 8) {             // pileup.py:56
-                        const int va = max(q_lo - qp, 0), vb = min(q_hi - qp, n);
-                        const int r0 = ref, q00 = qp;
-                        ref += n; qp = min(qp + n, kOpCap);          // pileup.py:90-91
-                        if (vb > va && r0 + va < c1 && r0 + vb > c0) {
-                            const int pa = r0 + va - c0, span = vb - va, q0 = q00 + va;
-                            if (staged) {
-                                u32 wv[4];
-                                query_window(smem, mask_s, nq, q0 - pa, wv);
-                                const u32 rm = bit_range(pa, pa + span);
-                                m[0] |= wv[0] & rm; m[1] |= wv[1] & rm; m[2] |= wv[2] & rm; m[3] |= wv[3] & rm;
-                            } else {
-                                block_masks_global(reinterpret_cast<const uint8_t *>(cig + ncig), L, pa, span, q0, a.min_baseq, m);
-                            }
+                // one aligned block over all of SEQ: reference position p <-> query base p - pos; the masks are
+                // already empty outside the distance-from-end window and beyond SEQ
+                if (simple) query_window(smem, rr.off, nq, c0 - pos, m);
+            }
+            if (__any_sync(kFull, cand && !simple)) {        // soft clips, indels, reads outside the staging area
+                if (cand && !simple) {
+                    const int ncig = rr.len >> 16;
+                    const bool staged = so != kUnstaged;
+                    const u32 sb = blob_addr + (staged ? so : 0u);                   // shared address of the staged blob
+                    const u32 *cig = reinterpret_cast<const u32 *>(a.blob + 16 * (size_t)rr.off);
+                    if (j >= ns && (pos >= c0 || (ch == 0 && rb == 0))) {   // no staged record: verify the declared extent here
+                        if (L > a.extent) extent_err = true;
+                        int span = 0;
+                        for (int ci = 0; ci < ncig; ci++) {
+                            const u32 w = __ldg(cig + ci);
+                            const int op = w & 15;
+                            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += min((int)(w >> 4), kOpCap);
+                            if (span > a.extent) { extent_err = true; break; }
                         }
-                    } else if (op == 2 || op == 3) ref += n;         // pileup.py:92-93
-                    else if (op == 4) qp = min(qp + n, kOpCap);      // pileup.py:94-95; I, H, P: nothing (sic)
-                    if (ref >= c1) break;                            // blocks only move right
+                    }
+                    // aligned blocks overlapping this chunk (pileup.py:55-95)
+                    const int q_hi = a.dist > 0 ? L - a.dist : L;
+                    const u32 mask_s = sb + (u32)((4 * ncig + ((L + 1) >> 1) + L + 15) & ~15);
+                    int ref = pos, qp = 0;
+                    for (int ci = 0; ci < ncig; ci++) {
+                        const u32 w = staged ? smem.ld32(sb + 4 * ci) : __ldg(cig + ci);
+                        const int op = w & 15;
+                        const int n = min((int)(w >> 4), kOpCap);
+                        if (op == 0 || op == 7 || op == 8) {             // pileup.py:56
+                            const int va = max(q_lo - qp, 0), vb = min(q_hi - qp, n);
+                            const int r0 = ref, q00 = qp;
+                            ref += n; qp = min(qp + n, kOpCap);          // pileup.py:90-91
+                            if (vb > va && r0 + va < c1 && r0 + vb > c0) {
+                                const int pa = r0 + va - c0, span = vb - va, q0 = q00 + va;
+                                if (staged) {
+                                    u32 wv[4];
+                                    query_window(smem, mask_s, nq, q0 - pa, wv);
+                                    const u32 rm = bit_range(pa, pa + span);
+                                    m[0] |= wv[0] & rm; m[1] |= wv[1] & rm; m[2] |= wv[2] & rm; m[3] |= wv[3] & rm;
+                                } else {
+                                    block_masks_global(reinterpret_cast<const uint8_t *>(cig + ncig), L, pa, span, q0, a.min_baseq, m);
+                                }
+                            }
+                        } else if (op == 2 || op == 3) ref += n;         // pileup.py:92-93
+                        else if (op == 4) qp = min(qp + n, kOpCap);      // pileup.py:94-95; I, H, P: nothing (sic)
+                        if (ref >= c1) break;                            // blocks only move right
+                    }
                 }
             }
             // lane = read -> lane = position; forward and reverse reads counted apart (pileup.py:88)
@@ -685,9 +706,10 @@ __device__ __forceinline__ void finish_chunk(const PileupArgs &a, int cell, int 
 
 __global__ void __launch_bounds__(kThreads, 4)
 k_pileup(PileupArgs a, int blob_cap, int batch_reads) {
-    __shared__ int s_unit, s_chunk;
+    __shared__ int s_unit;
     __shared__ u32 s_acc[kSplitChunks * kAccWords];          // deep units: counts of every chunk, summed over warps and batches
     __shared__ u32 s_wsum[2 * kWarpsPerCta];
+    __shared__ int s_first[kChunkSeg];                       // per chunk of the segment: first read of the batch that can reach it
     extern __shared__ __align__(16) uint8_t dyn[];
     ReadRec *s_rec = reinterpret_cast<ReadRec *>(dyn);                                  // [kStageReads]
     u32 *s_so = reinterpret_cast<u32 *>(dyn + kStageReads * sizeof(ReadRec));           // [kStageReads] offset in s_blob or kUnstaged
@@ -703,7 +725,7 @@ k_pileup(PileupArgs a, int blob_cap, int batch_reads) {
     if (threadIdx.x == 0) next_unit = atomicAdd(a.work_counter, 1);
     for (;;) {
         __syncthreads();                                     // previous unit fully consumed (also covers the s_acc init)
-        if (threadIdx.x == 0) { s_unit = next_unit; s_chunk = 0; }
+        if (threadIdx.x == 0) s_unit = next_unit;
         __syncthreads();
         const int u = s_unit;
         if (u >= n_units) break;
@@ -715,9 +737,8 @@ k_pileup(PileupArgs a, int blob_cap, int batch_reads) {
         // deep unit (few chunks): the reads go through the staging area in batches and every chunk's candidates
         // are split over `nparts` warps; partial counts meet in s_acc and are finished after the last batch
         const bool deep = n_chunks <= kSplitChunks;
-        int nparts = 1;
-        if (deep) while (nparts * 2 * n_chunks <= kWarpsPerCta) nparts *= 2;
-        const int n_items = n_chunks * nparts;
+        int nparts = 1, part_shift = 0;
+        if (deep) while (nparts * 2 * n_chunks <= kWarpsPerCta) { nparts *= 2; part_shift++; }
         bool extent_err = false;
         u64 sum = 0; u32 covered = 0, maxd = 0;
 
@@ -725,10 +746,7 @@ k_pileup(PileupArgs a, int blob_cap, int batch_reads) {
             const int nb = deep ? min(batch_reads, n_reads - rb) : n_reads;   // reads of this batch
             const int ns = min(nb, kStageReads);                              // reads with a staged record
             const ReadRec *g_rec = a.recs + un.rbeg + rb;
-            if (rb > 0) {
-                __syncthreads();                             // the previous batch is consumed
-                if (threadIdx.x == 0) s_chunk = 0;
-            }
+            if (rb > 0) __syncthreads();                     // the previous batch is consumed
             // ---- stage: every thread owns up to two reads (j = tid, tid + 256): record to shared memory, blob
             //      offset from a block-wide exclusive scan of the sizes (blob + query masks), blob with 16-byte cp.async ----
             ReadRec rr2[2];
@@ -790,24 +808,49 @@ k_pileup(PileupArgs a, int blob_cap, int batch_reads) {
                     int q_hi = a.dist > 0 ? L - a.dist : L;
                     if (qg.none) q_hi = q_lo;
                     build_query_masks(smem, sb + 4 * ncig, sb + bsz2[k], L, q_lo, q_hi, qg);
+                    if (ncig == 1) {                         // one aligned block over all of SEQ: phase B needs no CIGAR walk
+                        const u32 w = smem.ld32(sb);
+                        const int op = w & 15;
+                        if ((op == 0 || op == 7 || op == 8) && (int)(w >> 4) >= L) {
+                            const int j = threadIdx.x + k * kThreads;
+                            s_rec[j].off = sb + bsz2[k];
+                            s_rec[j].flags = rr2[k].flags | GF_SIMPLE;
+                        }
+                    }
                 }
             }
-            __syncthreads();
 
-            // ---- phase B: chunks of 32 positions (x parts), handed out to the warps ----
-            for (;;) {
-                int item = 0;
-                if (lane == 0) item = atomicAdd(&s_chunk, 1);
-                item = __shfl_sync(kFull, item, 0);
-                if (item >= n_items) break;
-                const int ch = item / nparts, part = item - ch * nparts;
-                u32 cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // 8 base x strand counters, Tn5 fwd / rev; lane = position
-                count_chunk(a, un, s_rec, s_so, blob_addr, rb, nb, ns, ch, part, nparts, lane, q_lo, cnt, extent_err);
-                if (deep) {
+            // ---- phase B: chunks of 32 positions (x parts) dealt to the warps round-robin, kChunkSeg chunks per pass ----
+            for (int cs = 0; cs < n_chunks; cs += kChunkSeg) {
+                const int nseg = min(kChunkSeg, n_chunks - cs);
+                if (cs > 0) __syncthreads();                 // the previous pass no longer reads s_first
+                // s_first[ch] = first read j with pos_j + extent - 1 >= first position of chunk cs + ch (reads are sorted by start)
+                const int seg0 = un.t0 + 32 * cs;
+                if (nb == 0) for (int ch = threadIdx.x; ch < nseg; ch += kThreads) s_first[ch] = 0;
+                for (int j = threadIdx.x; j < nb; j += kThreads) {
+                    int prev = -1;
+                    if (j > 0) {
+                        const int pp = max(j - 1 < ns ? s_rec[j - 1].pos : g_rec[j - 1].pos, -a.extent - 1);
+                        const int v = pp + a.extent - 1 - seg0;
+                        prev = v < 0 ? -1 : min(v >> 5, nseg - 1);
+                    }
+                    const int pj = max(j < ns ? s_rec[j].pos : g_rec[j].pos, -a.extent - 1);
+                    const int vj = pj + a.extent - 1 - seg0;
+                    const int cur = vj < 0 ? -1 : min(vj >> 5, nseg - 1);
+                    for (int ch = prev + 1; ch <= cur; ch++) s_first[ch] = j;
+                    if (j == nb - 1) for (int ch = cur + 1; ch < nseg; ch++) s_first[ch] = nb;
+                }
+                __syncthreads();
+                for (int item = wid; item < nseg * nparts; item += kWarpsPerCta) {
+                    const int chl = item >> part_shift, part = item & (nparts - 1);
+                    u32 cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // 8 base x strand counters, Tn5 fwd / rev; lane = position
+                    count_chunk(a, un, s_rec, s_so, s_first[chl], blob_addr, rb, nb, ns, cs + chl, part, nparts, lane, q_lo, cnt, extent_err);
+                    if (deep) {
 #pragma unroll
-                    for (int k = 0; k < 10; k++) if (cnt[k]) atomicAdd(&s_acc[ch * kAccWords + k * 32 + lane], cnt[k]);
-                } else {
-                    finish_chunk(a, un.cell, un.t0 + 32 * ch, lane, cnt, sum, covered, maxd);
+                        for (int k = 0; k < 10; k++) if (cnt[k]) atomicAdd(&s_acc[chl * kAccWords + k * 32 + lane], cnt[k]);
+                    } else {
+                        finish_chunk(a, un.cell, un.t0 + 32 * (cs + chl), lane, cnt, sum, covered, maxd);
+                    }
                 }
             }
             rb += nb > 0 ? nb : 1;
