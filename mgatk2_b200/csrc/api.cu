@@ -132,29 +132,33 @@ int partition_pass(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout
     return MGATK_OK;
 }
 
-constexpr int kStageBlobBytes = 38 * 1024;              // staged blob + query-mask bytes per CTA: 4 CTAs of 8 warps per SM
-
 int launch_pileup(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, int batch_reads) {
-    const size_t smem = pileup_smem_bytes(kStageBlobBytes);
+    const size_t smem = pileup_smem_bytes();
     CU(cudaFuncSetAttribute(k_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    k_pileup<<<h->sm_count * per_sm, kThreads, smem, s>>>(a, kStageBlobBytes, batch_reads);    // persistent CTAs pulling units
+    k_pileup<<<h->sm_count * per_sm, kThreads, smem, s>>>(a, batch_reads);    // persistent CTAs pulling units
     h->launches += 1;
     CU(cudaGetLastError());
     return MGATK_OK;
 }
 
-// reads per unit: what the staging area holds for this batch's average blob size
-int unit_reads_for(const mgatk_batch *b) {
+// mask slot of one read and the number of slots a CTA holds, from the declared extent (l_seq <= extent)
+int mask_stride_for(int extent) { return 16 * ((extent + 31) / 32); }
+int cap_reads_for(int extent) {
+    const int k = kMaskBytes / mask_stride_for(extent);
+    return k > kStageReads ? kStageReads : k;
+}
+
+// reads per unit: leave room for the reads of the halo and of the chunk the tile border is rounded down to
+int unit_reads_for(int extent) {
     const char *e = getenv("MGATK_UNIT_READS");
     const int v = e ? atoi(e) : 0;
-    if (v > 0) return v < 32 ? 32 : v > kStageReads ? kStageReads : v;
-    int64_t avg = b->n_records > 0 ? (b->blob_bytes / b->n_records + 15) / 16 * 16 : 96;
-    avg += 16 * (avg * 2 / 3 / 32 + 1);                  // query masks: 16 bytes per 32 bases, l_seq ~ 2/3 of the blob
-    int64_t k = (int64_t)(0.75 * kStageBlobBytes) / (avg > 16 ? avg : 16);
-    return (int)(k < 64 ? 64 : k > 384 ? 384 : k);
+    const int cap = cap_reads_for(extent);
+    if (v > 0) return v < 32 ? 32 : v;
+    const int k = (int)(0.8 * cap);
+    return k < 32 ? 32 : k;
 }
 
 int validate(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, const mgatk_outputs *o) {
@@ -184,7 +188,7 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     Layout L;
     if (!make_layout(b->n_records, p->n_cells, L)) return fail(h, MGATK_ERR_RANGE, "n_records / n_cells outside limits");
     if ((int64_t)L.total > ws_bytes || !ws_v) return fail(h, MGATK_ERR_WORKSPACE, "workspace too small");
-    L.unit_reads = unit_reads_for(b);
+    L.unit_reads = unit_reads_for(p->max_read_extent);
     char *ws = (char *)ws_v;
     CU(cudaSetDevice(h->device));
     if (!h->events_ready) {
@@ -255,7 +259,9 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     a.raw = (p->flags & MGATK_FLAG_RAW_PILEUP) ? 1 : 0;
     a.apply_bias = !a.raw && !(p->max_strand_bias >= 1.0);   // max(f,r)/total never exceeds 1.0
     a.extent = p->max_read_extent;
-    rc = launch_pileup(h, s, a, L.unit_reads);
+    a.mask_stride = mask_stride_for(p->max_read_extent);
+    a.cap_reads = cap_reads_for(p->max_read_extent);
+    rc = launch_pileup(h, s, a, a.cap_reads < 32 ? 32 : a.cap_reads);
     if (rc) return rc;
     mark(h, s, "pileup");
 

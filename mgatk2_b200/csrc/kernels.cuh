@@ -31,9 +31,8 @@ constexpr u32 ERR_UNSORTED = 1, ERR_EXTENT = 2, ERR_OVERFLOW_CAP = 4;
 
 // ReadRec.flags bits written by k_dedup, read by k_pileup
 constexpr int GF_PROCESS = 1, GF_STRAND = 2, GF_KEEP = 4, GF_CELL_SHIFT = 8;   // cell index in bits 8..31
-// set by k_pileup on its shared-memory copy: one aligned block covering all of SEQ; ReadRec.off then holds the
-// shared address of the read's query masks
-constexpr int GF_SIMPLE = 8;
+// set by k_pileup on its shared-memory copy: the read has query masks in its slot; one aligned block covers all of SEQ
+constexpr int GF_MASKS = 8, GF_SIMPLE = 16;
 // KeyRec.mq layout: mapq | strand<<8 | paired<<9
 constexpr int GMQ_STRAND = 0x100, GMQ_PAIRED = 0x200;
 
@@ -482,21 +481,24 @@ __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk
 
 // ---------------------------------------------------------------------------------------------
 // Stages 3-6 as a bit-plane gather. One CTA per unit (cell, position tile):
-//   stage   the records and cigar|seq|qual blobs of the unit's reads go to shared memory once (cp.async,
-//           L2 -> shared, no L1 pollution);
-//   phase A one thread per read turns SEQ/QUAL into four bit masks in query coordinates (bitplane.cuh:
-//           base == A/C/G/T, base quality, distance-from-end window; pileup.py:67-86), word-parallel, and
-//           verifies the declared extent;
+//   phase A every warp takes 32 reads of the unit at a time, one per lane: record from global memory, the
+//           cigar|seq|qual blob through a small per-warp staging buffer (cp.async, L2 -> shared, no L1
+//           pollution), then SEQ/QUAL turned into four bit masks in query coordinates (bitplane.cuh:
+//           base == A/C/G/T, base quality, distance-from-end window; pileup.py:67-86), word-parallel; only the
+//           masks (16 bytes per 32 bases) and the record stay in shared memory. The declared extent is verified
+//           and the per-chunk "first candidate" table is filled in the same pass; warps run independently.
 //   phase B the warps take chunks of 32 positions. The candidate reads of a chunk are those starting in
-//           (chunk - extent, chunk + 32); 32 candidates at a time, one per lane: the lane walks its CIGAR
-//           (pileup.py:52-95) and cuts the 32-bit window of every aligned block out of its query masks, a
-//           32x32 bit transpose across the warp turns "lane = read" into "lane = position", and two
-//           popcounts per base (forward / reverse reads) add up the eight base x strand counters in
-//           registers; the Tn5 sites (pileup.py:43-50) travel as a fifth mask. Nothing is shared between
-//           warps, so there are no atomics on counters; when the chunk's reads are exhausted the counts are
-//           final and the strand-bias filter, coverage, Tn5 gating (pileup.py:128-154) and the depth
-//           statistics are applied in registers and the 11 planes are written once.
-// Reads that did not fit the staging area take a per-base path from global memory (same results).
+//           (chunk - extent, chunk + 32); 32 candidates at a time, one per lane: a read with one aligned block
+//           over all of SEQ cuts the 32-bit window at query offset chunk - start out of its masks, any other
+//           read walks its CIGAR (pileup.py:52-95) and ORs the windows of its blocks; a 32x32 bit transpose
+//           across the warp turns "lane = read" into "lane = position", and two popcounts per base (forward /
+//           reverse reads) add up the eight base x strand counters in registers; the Tn5 sites
+//           (pileup.py:43-50) travel as a fifth mask. Nothing is shared between warps, so there are no atomics
+//           on counters; when the chunk's reads are exhausted the counts are final and the strand-bias filter,
+//           coverage, Tn5 gating (pileup.py:128-154) and the depth statistics are applied in registers and the
+//           11 planes are written once.
+// Reads that do not fit (blob larger than the warp buffer, more reads than mask slots) take a per-base path
+// from global memory (same results).
 // ---------------------------------------------------------------------------------------------
 struct PileupArgs {
     const ReadRec *recs;
@@ -505,6 +507,8 @@ struct PileupArgs {
     uint16_t *planes; mgatk_cell_qc *qc; mgatk_stats *stats;
     mgatk_overflow *ovf; int64_t ovf_cap;
     int P, ppad, min_baseq, dist, apply_bias, extent, raw;
+    int mask_stride;                 // bytes of one read's mask slot: 16 * ceil(extent / 32)
+    int cap_reads;                   // mask slots per CTA (<= kStageReads)
     double max_bias;
 };
 
@@ -525,20 +529,20 @@ struct SharedMem {                   // word access to shared memory by 32-bit s
     }
 };
 
-constexpr int kStageReads = 512;     // reads of a unit whose record is staged in shared memory
-constexpr int kStageMaxBytes = 1024; // blob + query masks of one read; larger reads take the per-base path
-constexpr int kStageSlack = 64;      // phase A may load this far past the last staged byte
-constexpr u32 kUnstaged = 0xffffffffu;
-constexpr int kSplitChunks = 4;      // "deep" units: at most this many chunks; their reads are staged in batches
+constexpr int kStageReads = 512;     // records of a batch kept in shared memory
+constexpr int kMaskBytes = 16 * 1024;// query masks of a batch (32-byte slots at 2x50 bp: 512 reads)
+constexpr int kWarpBuf = 2560;       // per-warp blob staging buffer: 32 blobs of a 50 bp read
+constexpr int kWarpBufSlack = 64;    // phase A may load this far past the last staged byte
+constexpr int kSplitChunks = 4;      // "deep" units: at most this many chunks; their reads come in batches
 constexpr int kChunkSeg = 576;       // chunks per pass over a unit (the 518 chunks of chrM in one)
 constexpr int kAccWords = 10 * 32;   // deep units: counts of one chunk, [8 base x strand + 2 Tn5][32]
 
-// dynamic shared memory of k_pileup: staged records, their blob offsets, the blob + mask bytes
-__host__ __device__ inline size_t pileup_smem_bytes(int blob_bytes) {
-    return (size_t)kStageReads * (sizeof(ReadRec) + 4) + blob_bytes + kStageSlack;
+// dynamic shared memory of k_pileup: records, query masks, per-warp staging buffers
+__host__ __device__ inline size_t pileup_smem_bytes() {
+    return (size_t)kStageReads * sizeof(ReadRec) + kMaskBytes + (size_t)kWarpsPerCta * (kWarpBuf + kWarpBufSlack);
 }
 
-// Per-base form of one aligned block for a read whose blob is not staged: masks of chunk bits [pa, pa + span)
+// Per-base form of one aligned block for a read without query masks: chunk bits [pa, pa + span)
 // for query bases q0.. (already clipped to the distance-from-end window).
 __device__ __noinline__ void block_masks_global(const uint8_t *seq, int L, int pa, int span, int q0, int min_baseq, u32 (&m)[4]) {
     const int8_t *qual = reinterpret_cast<const int8_t *>(seq) + ((L + 1) >> 1);
@@ -561,22 +565,96 @@ __device__ __forceinline__ u32 warp_transpose(u32 x, int lane) {
     return x;
 }
 
-// Counts of chunk `ch` of the unit from the reads [rb, rb + nb) of the unit (a batch whose first `ns`
-// records are staged), part `part` of `nparts`: lane = position on return. `first` is the first read of the
-// batch that can reach the chunk.
-__device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un, const ReadRec *s_rec, const u32 *s_so,
-                                            int first, u32 blob_addr, int rb, int nb, int ns, int ch, int part,
+// reference span check of one read against the declared extent (cigar words from global memory)
+__device__ __forceinline__ bool span_exceeds(const u32 *cig, int ncig, int L, int extent) {
+    if (L > extent) return true;
+    int span = 0;
+    for (int ci = 0; ci < ncig; ci++) {
+        const u32 w = __ldg(cig + ci);
+        const int op = w & 15;
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += min((int)(w >> 4), kOpCap);
+        if (span > extent) return true;
+    }
+    return false;
+}
+
+// Phase A for the reads [j0, j0 + 32) of a batch of nb reads (g_rec[0..nb)), one per lane: record, blob through
+// the warp's staging buffer, query masks into slot j, first-candidate table entries. ns = reads with a slot.
+__device__ __forceinline__ void stage_reads(const PileupArgs &a, const ReadRec *g_rec, int nb, int ns, int j0, int lane,
+                                            ReadRec *s_rec, u32 mask_addr, u32 wbuf_addr, int *s_first, int seg0, int nseg,
+                                            int q_lo, QualGe qg, bool &extent_err) {
+    const SharedMem smem;
+    const int j = j0 + lane;
+    ReadRec rr; rr.pos = 0; rr.off = 0; rr.len = 0; rr.flags = 0;
+    if (j < ns) rr = g_rec[j];
+    const int L = rr.len & 0xffff, ncig = rr.len >> 16;
+    const int nq = (L + 31) >> 5;
+    const u32 blob16 = (u32)((4 * ncig + ((L + 1) >> 1) + L + 15) & ~15);
+    const u32 *cig = reinterpret_cast<const u32 *>(a.blob + 16 * (size_t)rr.off);
+    const bool live = j < ns && (rr.flags & GF_PROCESS);
+    bool todo = live && blob16 <= (u32)kWarpBuf && 16 * nq <= a.mask_stride;     // gets query masks
+    if (live && !todo && span_exceeds(cig, ncig, L, a.extent)) extent_err = true;
+    u32 flags = rr.flags;
+    while (__any_sync(kFull, todo)) {                        // as many reads per pass as the buffer holds (all 32 at 50 bp)
+        const u32 sz = todo ? blob16 : 0u;
+        u32 incl = sz;
+        for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+        const bool now = todo && incl <= (u32)kWarpBuf;
+        const u32 sb = wbuf_addr + incl - sz;
+        if (now) for (u32 o = 0; o < blob16; o += 16) cp_async16(sb + o, reinterpret_cast<const uint8_t *>(cig) + o);
+        cp_async_wait_all();
+        __syncwarp();
+        if (now) {
+            if (L > a.extent) extent_err = true;
+            int span = 0;
+            u32 w0 = 0;
+            for (int ci = 0; ci < ncig; ci++) {
+                const u32 w = smem.ld32(sb + 4 * ci);
+                if (ci == 0) w0 = w;
+                const int op = w & 15;
+                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += min((int)(w >> 4), kOpCap);
+                if (span > a.extent) { extent_err = true; break; }
+            }
+            int q_hi = a.dist > 0 ? L - a.dist : L;
+            if (qg.none) q_hi = q_lo;
+            build_query_masks(smem, sb + 4 * ncig, mask_addr + (u32)j * (u32)a.mask_stride, L, q_lo, q_hi, qg);
+            flags |= GF_MASKS;
+            const int op0 = w0 & 15;                         // one aligned block over all of SEQ: phase B needs no CIGAR walk
+            if (ncig == 1 && (op0 == 0 || op0 == 7 || op0 == 8) && (int)(w0 >> 4) >= L) flags |= GF_SIMPLE;
+            todo = false;
+        }
+        __syncwarp();                                        // the buffer is reused by the next pass
+    }
+    if (j < ns) { rr.flags = flags; s_rec[j] = rr; }
+    // s_first[ch] = first read with pos + extent - 1 >= first position of chunk ch of the segment (reads are sorted by start)
+    int pj = 0;
+    if (j < nb) pj = max(j < ns ? rr.pos : g_rec[j].pos, -a.extent - 1);
+    int pp = __shfl_up_sync(kFull, pj, 1);
+    if (j < nb) {
+        if (lane == 0 && j > 0) pp = max(g_rec[j - 1].pos, -a.extent - 1);
+        int prev = -1;
+        if (j > 0) { const int v = pp + a.extent - 1 - seg0; prev = v < 0 ? -1 : min(v >> 5, nseg - 1); }
+        const int vj = pj + a.extent - 1 - seg0;
+        const int cur = vj < 0 ? -1 : min(vj >> 5, nseg - 1);
+        for (int ch = prev + 1; ch <= cur; ch++) s_first[ch] = j;
+        if (j == nb - 1) for (int ch = cur + 1; ch < nseg; ch++) s_first[ch] = nb;
+    }
+}
+
+// Counts of chunk `ch` of the unit from a batch of nb reads (g_rec[0..nb), the first `ns` with a record in
+// shared memory), part `part` of `nparts`: lane = position on return. `first` is the first read of the batch
+// that can reach the chunk; `first_batch` is set for the batch that holds the unit's leftmost reads.
+__device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un, const ReadRec *g_rec, const ReadRec *s_rec,
+                                            u32 mask_addr, int first, bool first_batch, int nb, int ns, int ch, int part,
                                             int nparts, int lane, int q_lo, u32 (&cnt)[10], bool &extent_err) {
     const SharedMem smem;
-    const ReadRec *g_rec = a.recs + un.rbeg + rb;
     const int c0 = un.t0 + 32 * ch, c1 = c0 + 32;
     const int skip_le = c0 - a.extent;               // reads starting at or before this cannot reach the chunk
     first = min(max(first, 0), nb);                  // (stale table entries if the batch was not sorted: flagged elsewhere)
     for (int r = first + 32 * part; r < nb; r += 32 * nparts) {
         const int j = r + lane;
         ReadRec rr; rr.pos = 0x7fffffff; rr.off = 0; rr.len = 0; rr.flags = 0;
-        u32 so = kUnstaged;
-        if (j < ns) { rr = s_rec[j]; so = s_so[j]; }
+        if (j < ns) rr = s_rec[j];
         else if (j < nb) rr = g_rec[j];
         const int pos = rr.pos;
         const u32 m_after = __ballot_sync(kFull, pos >= c1);
@@ -586,6 +664,7 @@ __device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un,
             const int L = rr.len & 0xffff;
             const int nq = (L + 31) >> 5;
             const bool simple = (rr.flags & GF_SIMPLE) != 0;
+            const u32 mask_s = mask_addr + (u32)j * (u32)a.mask_stride;
             u32 m[4] = {0u, 0u, 0u, 0u};
             u32 m5 = 0u;
             if (cand) {
@@ -594,30 +673,20 @@ __device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un,
                 if (t5 >= c0 && t5 < c1 && t5 < a.P) m5 = 1u << (t5 - c0);
                 // one aligned block over all of SEQ: reference position p <-> query base p - pos; the masks are
                 // already empty outside the distance-from-end window and beyond SEQ
-                if (simple) query_window(smem, rr.off, nq, c0 - pos, m);
+                if (simple) query_window(smem, mask_s, nq, c0 - pos, m);
             }
-            if (__any_sync(kFull, cand && !simple)) {        // soft clips, indels, reads outside the staging area
+            if (__any_sync(kFull, cand && !simple)) {        // soft clips, indels, reads without query masks
                 if (cand && !simple) {
                     const int ncig = rr.len >> 16;
-                    const bool staged = so != kUnstaged;
-                    const u32 sb = blob_addr + (staged ? so : 0u);                   // shared address of the staged blob
+                    const bool masks = (rr.flags & GF_MASKS) != 0;
                     const u32 *cig = reinterpret_cast<const u32 *>(a.blob + 16 * (size_t)rr.off);
-                    if (j >= ns && (pos >= c0 || (ch == 0 && rb == 0))) {   // no staged record: verify the declared extent here
-                        if (L > a.extent) extent_err = true;
-                        int span = 0;
-                        for (int ci = 0; ci < ncig; ci++) {
-                            const u32 w = __ldg(cig + ci);
-                            const int op = w & 15;
-                            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += min((int)(w >> 4), kOpCap);
-                            if (span > a.extent) { extent_err = true; break; }
-                        }
-                    }
+                    // no record in shared memory: the declared extent is verified here, once per unit
+                    if (j >= ns && (pos >= c0 || (ch == 0 && first_batch)) && span_exceeds(cig, ncig, L, a.extent)) extent_err = true;
                     // aligned blocks overlapping this chunk (pileup.py:55-95)
                     const int q_hi = a.dist > 0 ? L - a.dist : L;
-                    const u32 mask_s = sb + (u32)((4 * ncig + ((L + 1) >> 1) + L + 15) & ~15);
                     int ref = pos, qp = 0;
                     for (int ci = 0; ci < ncig; ci++) {
-                        const u32 w = staged ? smem.ld32(sb + 4 * ci) : __ldg(cig + ci);
+                        const u32 w = __ldg(cig + ci);
                         const int op = w & 15;
                         const int n = min((int)(w >> 4), kOpCap);
                         if (op == 0 || op == 7 || op == 8) {             // pileup.py:56
@@ -626,7 +695,7 @@ __device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un,
                             ref += n; qp = min(qp + n, kOpCap);          // pileup.py:90-91
                             if (vb > va && r0 + va < c1 && r0 + vb > c0) {
                                 const int pa = r0 + va - c0, span = vb - va, q0 = q00 + va;
-                                if (staged) {
+                                if (masks) {
                                     u32 wv[4];
                                     query_window(smem, mask_s, nq, q0 - pa, wv);
                                     const u32 rm = bit_range(pa, pa + span);
@@ -705,21 +774,20 @@ __device__ __forceinline__ void finish_chunk(const PileupArgs &a, int cell, int 
 }
 
 __global__ void __launch_bounds__(kThreads, 4)
-k_pileup(PileupArgs a, int blob_cap, int batch_reads) {
+k_pileup(PileupArgs a, int batch_reads) {
     __shared__ int s_unit;
     __shared__ u32 s_acc[kSplitChunks * kAccWords];          // deep units: counts of every chunk, summed over warps and batches
-    __shared__ u32 s_wsum[2 * kWarpsPerCta];
     __shared__ int s_first[kChunkSeg];                       // per chunk of the segment: first read of the batch that can reach it
     extern __shared__ __align__(16) uint8_t dyn[];
     ReadRec *s_rec = reinterpret_cast<ReadRec *>(dyn);                                  // [kStageReads]
-    u32 *s_so = reinterpret_cast<u32 *>(dyn + kStageReads * sizeof(ReadRec));           // [kStageReads] offset in s_blob or kUnstaged
-    uint8_t *s_blob = dyn + kStageReads * (sizeof(ReadRec) + 4);                        // [blob_cap + slack]
+    uint8_t *s_mask = dyn + kStageReads * sizeof(ReadRec);                              // [kMaskBytes]
+    uint8_t *s_wbuf = s_mask + kMaskBytes;                                              // [warps][kWarpBuf + slack]
     for (int e = threadIdx.x; e < kSplitChunks * kAccWords; e += blockDim.x) s_acc[e] = 0;
-    const u32 blob_addr = (u32)__cvta_generic_to_shared(s_blob);
     const int lane = lane_id(), wid = threadIdx.x >> 5;
-    const SharedMem smem;
+    const u32 mask_addr = (u32)__cvta_generic_to_shared(s_mask);
+    const u32 wbuf_addr = (u32)__cvta_generic_to_shared(s_wbuf) + (u32)wid * (kWarpBuf + kWarpBufSlack);
     const int n_units = *a.n_units;
-    QualGe qg = make_qual_ge(a.min_baseq);
+    const QualGe qg = make_qual_ge(a.min_baseq);
     const int q_lo = a.dist > 0 ? a.dist : 0;                // pileup.py:67-72
     int next_unit = 0;
     if (threadIdx.x == 0) next_unit = atomicAdd(a.work_counter, 1);
@@ -734,8 +802,8 @@ k_pileup(PileupArgs a, int blob_cap, int batch_reads) {
         const int n_chunks = (un.t1 - un.t0) >> 5;
         if (n_chunks <= 0) continue;                         // empty tile (its reads belong to the tile before)
         const int n_reads = un.rend - un.rbeg;
-        // deep unit (few chunks): the reads go through the staging area in batches and every chunk's candidates
-        // are split over `nparts` warps; partial counts meet in s_acc and are finished after the last batch
+        // deep unit (few chunks): the reads come in batches and every chunk's candidates are split over `nparts`
+        // warps; partial counts meet in s_acc and are finished after the last batch
         const bool deep = n_chunks <= kSplitChunks;
         int nparts = 1, part_shift = 0;
         if (deep) while (nparts * 2 * n_chunks <= kWarpsPerCta) { nparts *= 2; part_shift++; }
@@ -744,107 +812,22 @@ k_pileup(PileupArgs a, int blob_cap, int batch_reads) {
 
         for (int rb = 0; rb == 0 || rb < n_reads; ) {
             const int nb = deep ? min(batch_reads, n_reads - rb) : n_reads;   // reads of this batch
-            const int ns = min(nb, kStageReads);                              // reads with a staged record
+            const int ns = min(nb, a.cap_reads);                              // reads with a record + mask slot in shared memory
             const ReadRec *g_rec = a.recs + un.rbeg + rb;
-            if (rb > 0) __syncthreads();                     // the previous batch is consumed
-            // ---- stage: every thread owns up to two reads (j = tid, tid + 256): record to shared memory, blob
-            //      offset from a block-wide exclusive scan of the sizes (blob + query masks), blob with 16-byte cp.async ----
-            ReadRec rr2[2];
-            u32 sz2[2], incl2[2], bsz2[2];
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const int j = threadIdx.x + k * kThreads;
-                sz2[k] = 0; bsz2[k] = 0;
-                rr2[k].flags = 0; rr2[k].len = 0; rr2[k].off = 0; rr2[k].pos = 0;
-                if (j < ns) {
-                    rr2[k] = g_rec[j];
-                    s_rec[j] = rr2[k];
-                    const int L = rr2[k].len & 0xffff;
-                    const int nbytes = ((4 * (int)(rr2[k].len >> 16) + ((L + 1) >> 1) + L + 15) & ~15);
-                    const int total = nbytes + 16 * ((L + 31) >> 5);
-                    if ((rr2[k].flags & GF_PROCESS) && total <= kStageMaxBytes) { sz2[k] = (u32)total; bsz2[k] = (u32)nbytes; }
-                }
-                u32 incl = sz2[k];
-                for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
-                incl2[k] = incl;
-                if (lane == 31) s_wsum[k * kWarpsPerCta + wid] = incl;
-            }
-            __syncthreads();
-            u32 start2[2];
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const int j = threadIdx.x + k * kThreads;
-                u32 before = 0;                              // bytes of all reads in earlier warps / the earlier half
-                for (int w = 0; w < k * kWarpsPerCta + wid; w++) before += s_wsum[w];
-                const u32 start = before + incl2[k] - sz2[k];
-                const bool st = sz2[k] && start + sz2[k] <= (u32)blob_cap;
-                start2[k] = st ? start : (u32)kUnstaged;
-                if (j < ns) s_so[j] = start2[k];
-                if (st) {
-                    const uint8_t *src = a.blob + 16 * (size_t)rr2[k].off;
-                    for (u32 o = 0; o < bsz2[k]; o += 16) cp_async16(blob_addr + start + o, src + o);
-                }
-            }
-            cp_async_wait_all();
-            __syncthreads();
-
-            // ---- phase A: query masks of the staged reads; declared extent of every read with a staged record ----
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                if (!(rr2[k].flags & GF_PROCESS)) continue;  // also covers j >= ns
-                const int L = rr2[k].len & 0xffff, ncig = rr2[k].len >> 16;
-                const bool staged = start2[k] != kUnstaged;
-                const u32 sb = blob_addr + (staged ? start2[k] : 0u);
-                const u32 *cig = reinterpret_cast<const u32 *>(a.blob + 16 * (size_t)rr2[k].off);
-                if (L > a.extent) extent_err = true;
-                int span = 0;
-                for (int ci = 0; ci < ncig; ci++) {
-                    const u32 w = staged ? smem.ld32(sb + 4 * ci) : __ldg(cig + ci);
-                    const int op = w & 15;
-                    if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += min((int)(w >> 4), kOpCap);
-                    if (span > a.extent) { extent_err = true; break; }
-                }
-                if (staged) {
-                    int q_hi = a.dist > 0 ? L - a.dist : L;
-                    if (qg.none) q_hi = q_lo;
-                    build_query_masks(smem, sb + 4 * ncig, sb + bsz2[k], L, q_lo, q_hi, qg);
-                    if (ncig == 1) {                         // one aligned block over all of SEQ: phase B needs no CIGAR walk
-                        const u32 w = smem.ld32(sb);
-                        const int op = w & 15;
-                        if ((op == 0 || op == 7 || op == 8) && (int)(w >> 4) >= L) {
-                            const int j = threadIdx.x + k * kThreads;
-                            s_rec[j].off = sb + bsz2[k];
-                            s_rec[j].flags = rr2[k].flags | GF_SIMPLE;
-                        }
-                    }
-                }
-            }
-
-            // ---- phase B: chunks of 32 positions (x parts) dealt to the warps round-robin, kChunkSeg chunks per pass ----
-            for (int cs = 0; cs < n_chunks; cs += kChunkSeg) {
+            for (int cs = 0; cs < n_chunks; cs += kChunkSeg) {                // kChunkSeg chunks per pass (one pass for chrM)
                 const int nseg = min(kChunkSeg, n_chunks - cs);
-                if (cs > 0) __syncthreads();                 // the previous pass no longer reads s_first
-                // s_first[ch] = first read j with pos_j + extent - 1 >= first position of chunk cs + ch (reads are sorted by start)
-                const int seg0 = un.t0 + 32 * cs;
+                if (rb > 0 || cs > 0) __syncthreads();       // the previous batch / pass is consumed
+                // ---- phase A (the first pass also builds the masks) ----
                 if (nb == 0) for (int ch = threadIdx.x; ch < nseg; ch += kThreads) s_first[ch] = 0;
-                for (int j = threadIdx.x; j < nb; j += kThreads) {
-                    int prev = -1;
-                    if (j > 0) {
-                        const int pp = max(j - 1 < ns ? s_rec[j - 1].pos : g_rec[j - 1].pos, -a.extent - 1);
-                        const int v = pp + a.extent - 1 - seg0;
-                        prev = v < 0 ? -1 : min(v >> 5, nseg - 1);
-                    }
-                    const int pj = max(j < ns ? s_rec[j].pos : g_rec[j].pos, -a.extent - 1);
-                    const int vj = pj + a.extent - 1 - seg0;
-                    const int cur = vj < 0 ? -1 : min(vj >> 5, nseg - 1);
-                    for (int ch = prev + 1; ch <= cur; ch++) s_first[ch] = j;
-                    if (j == nb - 1) for (int ch = cur + 1; ch < nseg; ch++) s_first[ch] = nb;
-                }
+                for (int j0 = 32 * wid; j0 < nb; j0 += kThreads)
+                    stage_reads(a, g_rec, nb, cs == 0 ? ns : 0, j0, lane, s_rec, mask_addr, wbuf_addr, s_first, un.t0 + 32 * cs, nseg,
+                                q_lo, qg, extent_err);
                 __syncthreads();
+                // ---- phase B: chunks of 32 positions (x parts) dealt to the warps round-robin ----
                 for (int item = wid; item < nseg * nparts; item += kWarpsPerCta) {
                     const int chl = item >> part_shift, part = item & (nparts - 1);
                     u32 cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // 8 base x strand counters, Tn5 fwd / rev; lane = position
-                    count_chunk(a, un, s_rec, s_so, s_first[chl], blob_addr, rb, nb, ns, cs + chl, part, nparts, lane, q_lo, cnt, extent_err);
+                    count_chunk(a, un, g_rec, s_rec, mask_addr, s_first[chl], rb == 0, nb, ns, cs + chl, part, nparts, lane, q_lo, cnt, extent_err);
                     if (deep) {
 #pragma unroll
                         for (int k = 0; k < 10; k++) if (cnt[k]) atomicAdd(&s_acc[chl * kAccWords + k * 32 + lane], cnt[k]);
