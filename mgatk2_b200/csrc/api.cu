@@ -132,16 +132,23 @@ int partition_pass(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout
     return MGATK_OK;
 }
 
-int launch_pileup(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, int batch_reads) {
+constexpr int kChrMPpad = (int)MGATK_POS_PAD(16569);    // the plane pitch of chrM is compiled in
+
+template <int kPpad>
+int launch_pileup_t(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, int batch_reads) {
     const size_t smem = pileup_smem_bytes();
-    CU(cudaFuncSetAttribute(k_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_pileup<kPpad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup, kThreads, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup<kPpad>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    k_pileup<<<h->sm_count * per_sm, kThreads, smem, s>>>(a, batch_reads);    // persistent CTAs pulling units
+    k_pileup<kPpad><<<h->sm_count * per_sm, kThreads, smem, s>>>(a, batch_reads);    // persistent CTAs pulling units
     h->launches += 1;
     CU(cudaGetLastError());
     return MGATK_OK;
+}
+
+int launch_pileup(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, int batch_reads) {
+    return a.ppad == kChrMPpad ? launch_pileup_t<kChrMPpad>(h, s, a, batch_reads) : launch_pileup_t<0>(h, s, a, batch_reads);
 }
 
 // mask slot of one read and the number of slots a CTA holds, from the declared extent (l_seq <= extent)

@@ -69,7 +69,7 @@ MG_HD u32 qual_ge4(u32 q, QualGe g) {
 }
 
 // bits 7, 15, 23, 31 -> bits 28..31 (in byte order)
-MG_HD u32 pack_byte_flags_top(u32 ge) { return ((ge >> 7) * 0x10204080u) & 0xf0000000u; }
+MG_HD u32 pack_byte_flags_top(u32 ge) { return (((ge) >> 7) * 0x10204080u) & 0xf0000000u; }
 
 // pass flags of eight consecutive quality bytes (two words) as the top byte: bit 24+i = byte i passes
 MG_HD u32 qual_ok8_top(u32 q0, u32 q1, QualGe g) {
@@ -83,13 +83,13 @@ struct Eq8 { u32 a, c, g, t; };
 
 MG_HD u32 pack_nibble_flags_top(u32 e) {                // flags at bits 4n (n = 0..7) -> bits 24..31
     u32 y = e & 0x11111111u;
-    y = (y | (y >> 3)) & 0x03030303u;                   // byte k: bits 0,1 = nibbles 2k, 2k+1
+    y = (y | ((y) >> 3)) & 0x03030303u;                  // byte k: bits 0,1 = nibbles 2k, 2k+1
     return (y * 0x01041040u) & 0xff000000u;
 }
 
 MG_HD Eq8 seq_eq8_top(u32 s) {
-    const u32 t0 = ((s & 0x0f0f0f0fu) << 4) | ((s >> 4) & 0x0f0f0f0fu);   // nibble n now holds base n
-    const u32 t1 = t0 >> 1, t2 = t0 >> 2, t3 = t0 >> 3;
+    const u32 t0 = ((s & 0x0f0f0f0fu) << 4) | (((s) >> 4) & 0x0f0f0f0fu);   // nibble n now holds base n
+    const u32 t1 = ((t0) >> 1), t2 = ((t0) >> 2), t3 = ((t0) >> 3);
     Eq8 r;
     r.a = pack_nibble_flags_top(t0 & ~t1 & ~t2 & ~t3);   // 0001
     r.c = pack_nibble_flags_top(~t0 & t1 & ~t2 & ~t3);   // 0010
@@ -140,8 +140,10 @@ MG_HD void build_query_masks(const M &mem, u32 seq_addr /*4-aligned*/, u32 out /
             const u32 ok = qual_ok8_top(funnel_r(carry, w1, qsh), funnel_r(w1, w2, qsh), qg);
             carry = w2;
             const Eq8 e = seq_eq8_top(s);
-            const int sh = 24 - 8 * g;
-            mA |= (e.a & ok) >> sh; mC |= (e.c & ok) >> sh; mG |= (e.g & ok) >> sh; mT |= (e.t & ok) >> sh;
+            if (g == 0) { mA |= ((e.a & ok) >> 24); mC |= ((e.c & ok) >> 24); mG |= ((e.g & ok) >> 24); mT |= ((e.t & ok) >> 24); }
+            else if (g == 1) { mA |= ((e.a & ok) >> 16); mC |= ((e.c & ok) >> 16); mG |= ((e.g & ok) >> 16); mT |= ((e.t & ok) >> 16); }
+            else if (g == 2) { mA |= ((e.a & ok) >> 8); mC |= ((e.c & ok) >> 8); mG |= ((e.g & ok) >> 8); mT |= ((e.t & ok) >> 8); }
+            else { mA |= e.a & ok; mC |= e.c & ok; mG |= e.g & ok; mT |= e.t & ok; }
         }
         qa += 32u;
         const u32 wm = bit_range(q_lo - 32 * w, q_hi - 32 * w);   // pileup.py:67-78 (also cuts bases >= L)

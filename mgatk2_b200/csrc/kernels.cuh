@@ -22,7 +22,10 @@ namespace mgatk {
 
 typedef unsigned long long u64;
 
-constexpr int kWarpsPerCta = 8;
+#ifndef MGATK_PILEUP_WARPS
+#define MGATK_PILEUP_WARPS 8
+#endif
+constexpr int kWarpsPerCta = MGATK_PILEUP_WARPS;       // k_pileup: warps per CTA; 32 warps per SM in all
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kScanGroup = 16;        // chunks per scan group
 constexpr u32 kFull = 0xffffffffu;
@@ -277,7 +280,7 @@ constexpr int kDedupRounds = 4;                              // records per thre
 constexpr int kDedupTile = kDedupThreads * kDedupRounds;
 constexpr u64 kScanAggregate = 1ull << 62, kScanPrefix = 2ull << 62, kScanValue = (1ull << 62) - 1;
 
-__global__ void __launch_bounds__(kDedupThreads)
+__global__ void __launch_bounds__(kDedupThreads, 3)
 k_dedup(const GroupRec *__restrict__ g, const int64_t *__restrict__ m_ptr, ReadRec *__restrict__ recs, int dedup_mode, int min_mapq,
         mgatk_cell_qc *__restrict__ qc, mgatk_stats *__restrict__ stats, u32 *__restrict__ ticket,
         u64 *__restrict__ scan_state, int64_t *__restrict__ n_proc_out) {
@@ -300,21 +303,28 @@ k_dedup(const GroupRec *__restrict__ g, const int64_t *__restrict__ m_ptr, ReadR
         int cell = -1;
         bool keep = false, paired = false, process = false;
         rr[k].pos = 0; rr[k].off = 0; rr[k].len = 0; rr[k].flags = 0;
+        uint4 me = make_uint4(0xffffffffu, 0u, 0u, 0u);                      // cell, pos, |tlen|, mq
+        uint2 lc = make_uint2(0u, 0u);                                       // off, len
+        if (i < m) { me = reinterpret_cast<const uint4 *>(g + i)[0]; lc = reinterpret_cast<const uint2 *>(g + i)[2]; }
+        // the record before this one is the neighbouring lane's (lane 0 fetches it)
+        uint4 prev;
+        prev.x = __shfl_up_sync(kFull, me.x, 1); prev.y = __shfl_up_sync(kFull, me.y, 1);
+        prev.z = __shfl_up_sync(kFull, me.z, 1); prev.w = __shfl_up_sync(kFull, me.w, 1);
+        if (lane == 0 && i > 0 && i < m) prev = reinterpret_cast<const uint4 *>(g + i - 1)[0];
         if (i < m) {
-            const uint4 me = reinterpret_cast<const uint4 *>(g + i)[0];      // cell, pos, |tlen|, mq
-            const uint2 lc = reinterpret_cast<const uint2 *>(g + i)[2];      // off, len
             cell = (int)me.x;
             const u32 strand = me.w & GMQ_STRAND;
             paired = me.w & GMQ_PAIRED;
             bool len_dup = false, pos_dup = false;
             if (dedup_mode != MGATK_DEDUP_NONE) {
-                for (int64_t j = i - 1; j >= 0; j--) {
-                    const uint4 o = reinterpret_cast<const uint4 *>(g + j)[0];
+                uint4 o = prev;
+                for (int64_t j = i - 1; j >= 0; ) {
                     if (o.y != me.y || o.x != me.x) break;
                     if ((o.w & GMQ_STRAND) == strand) {
                         pos_dup = true;
                         if (o.z == me.z) { len_dup = true; break; }
                     }
+                    if (--j >= 0) o = reinterpret_cast<const uint4 *>(g + j)[0];
                 }
             }
             keep = dedup_mode == MGATK_DEDUP_FRAGMENT_LENGTH ? !len_dup : dedup_mode == MGATK_DEDUP_POSITION_ONLY ? !pos_dup : true;
@@ -348,27 +358,42 @@ k_dedup(const GroupRec *__restrict__ g, const int64_t *__restrict__ m_ptr, ReadR
     }
     __syncthreads();
     // stable compaction of the reads that are piled up: position inside the tile, then the tile's prefix
-    u32 before[kDedupRounds], total = 0;
-#pragma unroll
-    for (int k = 0; k < kDedupRounds; k++) {
-        before[k] = total;
-#pragma unroll
-        for (int w = 0; w < kDedupThreads / 32; w++) { const u32 v = s_warp[k][w]; if (w < wid) before[k] += v; total += v; }
-    }
-    if (wid == 0) {                                          // decoupled look-back, 32 predecessors at a time
+    if (wid == 0) {
+        // exclusive scan of the kDedupRounds x 16 warp counts (round-major = record order), two per lane
+        constexpr int kCounts = kDedupRounds * (kDedupThreads / 32);
+        static_assert(kCounts == 64, "two counts per lane");
+        u32 *flat = &s_warp[0][0];
+        const u32 c0 = flat[2 * lane], c1 = flat[2 * lane + 1];
+        u32 incl = c0 + c1;
+        for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+        const u32 total = __shfl_sync(kFull, incl, 31);
+        flat[2 * lane] = incl - c0 - c1; flat[2 * lane + 1] = incl - c1;
+        // decoupled look-back, 128 predecessors at a time
         u64 prefix = 0;
         if (lane == 0) atomicExch((unsigned long long *)&scan_state[blk], (blk == 0 ? kScanPrefix : kScanAggregate) | (u64)total);
-        for (int64_t top = (int64_t)blk - 1; top >= 0; ) {
-            const int64_t b = top - lane;
-            u64 v = kScanPrefix;                             // below block 0: an empty prefix
-            if (b >= 0) do { v = *(volatile u64 *)&scan_state[b]; } while ((v & ~kScanValue) == 0);
-            const u32 has_prefix = __ballot_sync(kFull, (v & kScanPrefix) != 0);
-            const int stop = __ffs(has_prefix) - 1;          // nearest predecessor with a full prefix (or -1)
-            u64 add = (stop < 0 || lane <= stop) ? (v & kScanValue) : 0;
+        for (int64_t top = (int64_t)blk - 1; top >= 0; top -= 128) {
+            u64 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {                    // lane-major: lane l looks at top - 4l - k
+                const int64_t b = top - 4 * lane - k;
+                v[k] = kScanPrefix;                          // below block 0: an empty prefix
+                if (b >= 0) v[k] = *(volatile u64 *)&scan_state[b];
+            }
+            bool stop_here = false;                          // this lane holds the nearest full prefix
+            u64 add = 0;
+            bool seen = false;                               // a full prefix was seen at a nearer block of this lane
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int64_t b = top - 4 * lane - k;
+                while (b >= 0 && (v[k] & ~kScanValue) == 0) v[k] = *(volatile u64 *)&scan_state[b];
+                if (!seen) { add += v[k] & kScanValue; if (v[k] & kScanPrefix) { seen = true; stop_here = true; } }
+            }
+            const u32 has_prefix = __ballot_sync(kFull, stop_here);
+            const int stop = __ffs(has_prefix) - 1;          // nearest lane with a full prefix (or -1)
+            if (stop >= 0 && lane > stop) add = 0;
             for (int o = 16; o; o >>= 1) add += __shfl_xor_sync(kFull, add, o);
             prefix += add;
             if (stop >= 0) break;
-            top -= 32;
         }
         if (lane == 0) {
             if (blk != 0) atomicExch((unsigned long long *)&scan_state[blk], kScanPrefix | (prefix + total));
@@ -384,7 +409,7 @@ k_dedup(const GroupRec *__restrict__ g, const int64_t *__restrict__ m_ptr, ReadR
     const u64 prefix = s_prefix;
 #pragma unroll
     for (int k = 0; k < kDedupRounds; k++)
-        if ((pm[k] >> lane) & 1u) recs[prefix + before[k] + __popc(pm[k] & ((1u << lane) - 1u))] = rr[k];
+        if ((pm[k] >> lane) & 1u) recs[prefix + s_warp[k][wid] + __popc(pm[k] & ((1u << lane) - 1u))] = rr[k];
 }
 
 // first compacted index of every cell: lower_bound on the cell field (records are grouped by cell)
@@ -529,8 +554,8 @@ struct SharedMem {                   // word access to shared memory by 32-bit s
     }
 };
 
-constexpr int kStageReads = 512;     // records of a batch kept in shared memory
-constexpr int kMaskBytes = 16 * 1024;// query masks of a batch (32-byte slots at 2x50 bp: 512 reads)
+constexpr int kStageReads = 64 * kWarpsPerCta;       // records of a batch kept in shared memory
+constexpr int kMaskBytes = 32 * kStageReads;         // query masks of a batch (32-byte slots at 2x50 bp)
 constexpr int kWarpBuf = 2560;       // per-warp blob staging buffer: 32 blobs of a 50 bp read
 constexpr int kWarpBufSlack = 64;    // phase A may load this far past the last staged byte
 constexpr int kSplitChunks = 4;      // "deep" units: at most this many chunks; their reads come in batches
@@ -730,8 +755,10 @@ __device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un,
 
 // The counts of a chunk are final: strand-bias filter, coverage, Tn5 gating (pileup.py:128-154), depth
 // statistics, saturation (writers.py:205-218) and the one write of the 11 planes.
+template <int kPpad>
 __device__ __forceinline__ void finish_chunk(const PileupArgs &a, int cell, int c0, int lane, u32 (&cnt)[10],
                                              u64 &sum, u32 &covered, u32 &maxd) {
+    const int ppad = kPpad ? kPpad : a.ppad;             // compile-time plane pitch: the 11 stores share one address
     const int p = c0 + lane;
     if (p >= a.P) {                                  // pileup.py:58 end_refpos = min(.., mito_length): padding stays zero
 #pragma unroll
@@ -768,12 +795,13 @@ __device__ __forceinline__ void finish_chunk(const PileupArgs &a, int cell, int 
             }
         }
     }
-    uint16_t *out = a.planes + (size_t)cell * MGATK_N_PLANES * a.ppad + p;
+    uint16_t *out = a.planes + (size_t)cell * MGATK_N_PLANES * ppad + p;
 #pragma unroll
-    for (int pl = 0; pl < MGATK_N_PLANES; pl++) out[(size_t)pl * a.ppad] = (uint16_t)vals[pl];
+    for (int pl = 0; pl < MGATK_N_PLANES; pl++) out[(size_t)pl * ppad] = (uint16_t)vals[pl];
 }
 
-__global__ void __launch_bounds__(kThreads, 4)
+template <int kPpad>
+__global__ void __launch_bounds__(kThreads, 32 / kWarpsPerCta)
 k_pileup(PileupArgs a, int batch_reads) {
     __shared__ int s_unit;
     __shared__ u32 s_acc[kSplitChunks * kAccWords];          // deep units: counts of every chunk, summed over warps and batches
@@ -832,7 +860,7 @@ k_pileup(PileupArgs a, int batch_reads) {
 #pragma unroll
                         for (int k = 0; k < 10; k++) if (cnt[k]) atomicAdd(&s_acc[chl * kAccWords + k * 32 + lane], cnt[k]);
                     } else {
-                        finish_chunk(a, un.cell, un.t0 + 32 * (cs + chl), lane, cnt, sum, covered, maxd);
+                        finish_chunk<kPpad>(a, un.cell, un.t0 + 32 * (cs + chl), lane, cnt, sum, covered, maxd);
                     }
                 }
             }
@@ -844,7 +872,7 @@ k_pileup(PileupArgs a, int batch_reads) {
                 u32 cnt[10];
 #pragma unroll
                 for (int k = 0; k < 10; k++) { cnt[k] = s_acc[wid * kAccWords + k * 32 + lane]; s_acc[wid * kAccWords + k * 32 + lane] = 0; }
-                finish_chunk(a, un.cell, un.t0 + 32 * wid, lane, cnt, sum, covered, maxd);
+                finish_chunk<kPpad>(a, un.cell, un.t0 + 32 * wid, lane, cnt, sum, covered, maxd);
             }
         }
         // per-cell depth statistics (processors.py:36-39, writers.py:187-193)
