@@ -68,12 +68,12 @@ MG_HD u32 qual_ge4(u32 q, QualGe g) {
     return ((u & a) | ((u | a) & g.sel)) & 0x80808080u;
 }
 
-// bits 7, 15, 23, 31 -> bits 28..31 (in byte order)
-MG_HD u32 pack_byte_flags_top(u32 ge) { return (((ge) >> 7) * 0x10204080u) & 0xf0000000u; }
-
-// pass flags of eight consecutive quality bytes (two words) as the top byte: bit 24+i = byte i passes
+// pass flags of eight consecutive quality bytes (two words) as the top byte: bit 24+i = byte i passes.
+// The flags of the first word move to bits 3, 11, 19, 27, next to those of the second word at 7, 15, 23, 31; one
+// multiplication then lines all eight up in the top byte (every partial product lands on its own bit).
 MG_HD u32 qual_ok8_top(u32 q0, u32 q1, QualGe g) {
-    return (pack_byte_flags_top(qual_ge4(q0, g)) >> 4) | pack_byte_flags_top(qual_ge4(q1, g));
+    const u32 f = (qual_ge4(q0, g) >> 4) | qual_ge4(q1, g);
+    return (f * 0x00204081u) & 0xff000000u;
 }
 
 // ---- bases: one little-endian word of BAM 4-bit SEQ = eight bases, high nibble first in every byte ----
@@ -81,31 +81,49 @@ MG_HD u32 qual_ok8_top(u32 q0, u32 q1, QualGe g) {
 // (bit 24+i = base i). Any other code (=, N, IUPAC) matches nothing (pileup.py:83-86).
 struct Eq8 { u32 a, c, g, t; };
 
-MG_HD u32 pack_nibble_flags_top(u32 e) {                // flags at bits 4n (n = 0..7) -> bits 24..31
-    u32 y = e & 0x11111111u;
-    y = (y | ((y) >> 3)) & 0x03030303u;                  // byte k: bits 0,1 = nibbles 2k, 2k+1
-    return (y * 0x01041040u) & 0xff000000u;
+MG_HD u32 pack_nibble_flags_raw(u32 e) {                // flags at bits 4n (n = 0..7, nothing else set) -> bits 24..31; lower bits are scrap
+    const u32 y = (e | (e >> 3)) & 0x03030303u;         // byte k: bits 0,1 = nibbles 2k, 2k+1
+    return y * 0x01041040u;
+}
+
+MG_HD Eq8 seq_eq8_raw(u32 s) {                          // top byte = flags, lower bits scrap (AND with a top-byte mask)
+    const u32 t0 = ((s & 0x0f0f0f0fu) << 4) | ((s >> 4) & 0x0f0f0f0fu);   // nibble n now holds base n
+    const u32 t1 = t0 >> 1, t2 = t0 >> 2, t3 = t0 >> 3;
+    const u32 k = 0x11111111u;
+    Eq8 r;
+    r.a = pack_nibble_flags_raw((t0 & ~t1 & ~t2) & (~t3 & k));   // 0001
+    r.c = pack_nibble_flags_raw((~t0 & t1 & ~t2) & (~t3 & k));   // 0010
+    r.g = pack_nibble_flags_raw((~t0 & ~t1 & t2) & (~t3 & k));   // 0100
+    r.t = pack_nibble_flags_raw((~t0 & ~t1 & ~t2) & (t3 & k));   // 1000
+    return r;
 }
 
 MG_HD Eq8 seq_eq8_top(u32 s) {
-    const u32 t0 = ((s & 0x0f0f0f0fu) << 4) | (((s) >> 4) & 0x0f0f0f0fu);   // nibble n now holds base n
-    const u32 t1 = ((t0) >> 1), t2 = ((t0) >> 2), t3 = ((t0) >> 3);
-    Eq8 r;
-    r.a = pack_nibble_flags_top(t0 & ~t1 & ~t2 & ~t3);   // 0001
-    r.c = pack_nibble_flags_top(~t0 & t1 & ~t2 & ~t3);   // 0010
-    r.g = pack_nibble_flags_top(~t0 & ~t1 & t2 & ~t3);   // 0100
-    r.t = pack_nibble_flags_top(~t0 & ~t1 & ~t2 & t3);   // 1000
+    Eq8 r = seq_eq8_raw(s);
+    r.a &= 0xff000000u; r.c &= 0xff000000u; r.g &= 0xff000000u; r.t &= 0xff000000u;
     return r;
+}
+
+// byte G of m <- top byte of v
+template <int G>
+MG_HD u32 insert_top_byte(u32 m, u32 v) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(m, v, G == 0 ? 0x3217 : G == 1 ? 0x3270 : G == 2 ? 0x3710 : 0x7210);
+#else
+    return (m & ~(0xffu << (8 * G))) | ((v >> 24) << (8 * G));
+#endif
 }
 
 // ---- 32x32 bit transpose across a warp: one butterfly stage ----
 // Lane r holds row r; after the five stages (j = 16, 8, 4, 2, 1) lane p holds column p (bit r = row r's bit p).
-// `mine` is the word of this lane, `other` the word of lane ^ j.
-MG_HD u32 transpose_stage(u32 mine, u32 other, int lane, int j) {
+// `mine` is the word of this lane, `other` the word of lane ^ j. keep / amt are the lane's constants of the stage.
+MG_HD u32 transpose_keep(int lane, int j) {
     const u32 m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
-    const bool upper = (lane & j) != 0;
-    const u32 keep = upper ? ~m : m;
-    const u32 moved = rotl32(other, upper ? 32 - j : j);   // wrapped-around bits fall outside ~keep
+    return (lane & j) ? ~m : m;
+}
+MG_HD u32 transpose_amt(int lane, int j) { return (lane & j) ? 32 - j : j; }
+MG_HD u32 transpose_stage(u32 mine, u32 other, u32 keep, u32 amt) {
+    const u32 moved = rotl32(other, amt);                  // wrapped-around bits fall outside ~keep
     return (mine & keep) | (moved & ~keep);
 }
 
@@ -139,11 +157,11 @@ MG_HD void build_query_masks(const M &mem, u32 seq_addr /*4-aligned*/, u32 out /
             const u32 w1 = mem.ld32(qa + 8u * g + 4u), w2 = mem.ld32(qa + 8u * g + 8u);
             const u32 ok = qual_ok8_top(funnel_r(carry, w1, qsh), funnel_r(w1, w2, qsh), qg);
             carry = w2;
-            const Eq8 e = seq_eq8_top(s);
-            if (g == 0) { mA |= ((e.a & ok) >> 24); mC |= ((e.c & ok) >> 24); mG |= ((e.g & ok) >> 24); mT |= ((e.t & ok) >> 24); }
-            else if (g == 1) { mA |= ((e.a & ok) >> 16); mC |= ((e.c & ok) >> 16); mG |= ((e.g & ok) >> 16); mT |= ((e.t & ok) >> 16); }
-            else if (g == 2) { mA |= ((e.a & ok) >> 8); mC |= ((e.c & ok) >> 8); mG |= ((e.g & ok) >> 8); mT |= ((e.t & ok) >> 8); }
-            else { mA |= e.a & ok; mC |= e.c & ok; mG |= e.g & ok; mT |= e.t & ok; }
+            const Eq8 e = seq_eq8_raw(s);
+            if (g == 0) { mA = insert_top_byte<0>(mA, e.a & ok); mC = insert_top_byte<0>(mC, e.c & ok); mG = insert_top_byte<0>(mG, e.g & ok); mT = insert_top_byte<0>(mT, e.t & ok); }
+            else if (g == 1) { mA = insert_top_byte<1>(mA, e.a & ok); mC = insert_top_byte<1>(mC, e.c & ok); mG = insert_top_byte<1>(mG, e.g & ok); mT = insert_top_byte<1>(mT, e.t & ok); }
+            else if (g == 2) { mA = insert_top_byte<2>(mA, e.a & ok); mC = insert_top_byte<2>(mC, e.c & ok); mG = insert_top_byte<2>(mG, e.g & ok); mT = insert_top_byte<2>(mT, e.t & ok); }
+            else { mA = insert_top_byte<3>(mA, e.a & ok); mC = insert_top_byte<3>(mC, e.c & ok); mG = insert_top_byte<3>(mG, e.g & ok); mT = insert_top_byte<3>(mT, e.t & ok); }
         }
         qa += 32u;
         const u32 wm = bit_range(q_lo - 32 * w, q_hi - 32 * w);   // pileup.py:67-78 (also cuts bases >= L)

@@ -584,9 +584,20 @@ __device__ __noinline__ void block_masks_global(const uint8_t *seq, int L, int p
     }
 }
 
-__device__ __forceinline__ u32 warp_transpose(u32 x, int lane) {
+struct TransposeConst { u32 keep[5], amt[5]; };          // per-lane constants of the five butterfly stages
+__device__ __forceinline__ TransposeConst make_transpose_const(int lane) {
+    TransposeConst tc;
 #pragma unroll
-    for (int j = 16; j >= 1; j >>= 1) x = transpose_stage(x, __shfl_xor_sync(kFull, x, j), lane, j);
+    for (int s = 0; s < 5; s++) {
+        tc.keep[s] = transpose_keep(lane, 16 >> s); tc.amt[s] = transpose_amt(lane, 16 >> s);
+        // opaque to the compiler: it would otherwise recompute both with two SELs per stage on the saturated ALU pipe
+        asm volatile("" : "+r"(tc.keep[s]), "+r"(tc.amt[s]));
+    }
+    return tc;
+}
+__device__ __forceinline__ u32 warp_transpose(u32 x, const TransposeConst &tc) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) x = transpose_stage(x, __shfl_xor_sync(kFull, x, 16 >> s), tc.keep[s], tc.amt[s]);
     return x;
 }
 
@@ -671,7 +682,7 @@ __device__ __forceinline__ void stage_reads(const PileupArgs &a, const ReadRec *
 // that can reach the chunk; `first_batch` is set for the batch that holds the unit's leftmost reads.
 __device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un, const ReadRec *g_rec, const ReadRec *s_rec,
                                             u32 mask_addr, int first, bool first_batch, int nb, int ns, int ch, int part,
-                                            int nparts, int lane, int q_lo, u32 (&cnt)[10], bool &extent_err) {
+                                            int nparts, int lane, int q_lo, const TransposeConst &tc, u32 (&cnt)[10], bool &extent_err) {
     const SharedMem smem;
     const int c0 = un.t0 + 32 * ch, c1 = c0 + 32;
     const int skip_le = c0 - a.extent;               // reads starting at or before this cannot reach the chunk
@@ -739,12 +750,12 @@ __device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un,
             const u32 rev = __ballot_sync(kFull, cand && strand);
 #pragma unroll
             for (int x = 0; x < 4; x++) {
-                const u32 t = warp_transpose(m[x], lane);
+                const u32 t = warp_transpose(m[x], tc);
                 cnt[2 * x] += __popc(t & ~rev);
                 cnt[2 * x + 1] += __popc(t & rev);
             }
             if (__any_sync(kFull, m5 != 0u)) {
-                const u32 t = warp_transpose(m5, lane);
+                const u32 t = warp_transpose(m5, tc);
                 cnt[8] += __popc(t & ~rev);
                 cnt[9] += __popc(t & rev);
             }
@@ -817,6 +828,7 @@ k_pileup(PileupArgs a, int batch_reads) {
     const int n_units = *a.n_units;
     const QualGe qg = make_qual_ge(a.min_baseq);
     const int q_lo = a.dist > 0 ? a.dist : 0;                // pileup.py:67-72
+    const TransposeConst tc = make_transpose_const(lane);
     int next_unit = 0;
     if (threadIdx.x == 0) next_unit = atomicAdd(a.work_counter, 1);
     for (;;) {
@@ -855,7 +867,7 @@ k_pileup(PileupArgs a, int batch_reads) {
                 for (int item = wid; item < nseg * nparts; item += kWarpsPerCta) {
                     const int chl = item >> part_shift, part = item & (nparts - 1);
                     u32 cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // 8 base x strand counters, Tn5 fwd / rev; lane = position
-                    count_chunk(a, un, g_rec, s_rec, mask_addr, s_first[chl], rb == 0, nb, ns, cs + chl, part, nparts, lane, q_lo, cnt, extent_err);
+                    count_chunk(a, un, g_rec, s_rec, mask_addr, s_first[chl], rb == 0, nb, ns, cs + chl, part, nparts, lane, q_lo, tc, cnt, extent_err);
                     if (deep) {
 #pragma unroll
                         for (int k = 0; k < 10; k++) if (cnt[k]) atomicAdd(&s_acc[chl * kAccWords + k * 32 + lane], cnt[k]);
@@ -875,16 +887,22 @@ k_pileup(PileupArgs a, int batch_reads) {
                 finish_chunk<kPpad>(a, un.cell, un.t0 + 32 * wid, lane, cnt, sum, covered, maxd);
             }
         }
-        // per-cell depth statistics (processors.py:36-39, writers.py:187-193)
-        for (int o = 16; o; o >>= 1) {
-            sum += __shfl_xor_sync(kFull, sum, o);
-            covered += __shfl_xor_sync(kFull, covered, o);
-            maxd = max(maxd, __shfl_xor_sync(kFull, maxd, o));
-        }
-        if (lane == 0 && covered) {
-            atomicAdd((u64 *)&a.qc[un.cell].sum_depth, sum);
-            atomicAdd(&a.qc[un.cell].covered, covered);
-            atomicMax(&a.qc[un.cell].max_depth, maxd);
+        // per-cell depth statistics (processors.py:36-39, writers.py:187-193): hardware warp reductions
+        if (__any_sync(kFull, covered != 0)) {
+            u64 tot;
+            if (__any_sync(kFull, (sum >> 32) != 0)) {       // cannot happen below 2^32 counted bases per lane and unit
+                tot = sum;
+                for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(kFull, tot, o);
+            } else {
+                const u32 lo = (u32)sum;
+                tot = (u64)__reduce_add_sync(kFull, lo & 0xffffu) + ((u64)__reduce_add_sync(kFull, lo >> 16) << 16);
+            }
+            const u32 cv = __reduce_add_sync(kFull, covered), mx = __reduce_max_sync(kFull, maxd);
+            if (lane == 0) {
+                atomicAdd((u64 *)&a.qc[un.cell].sum_depth, tot);
+                atomicAdd(&a.qc[un.cell].covered, cv);
+                atomicMax(&a.qc[un.cell].max_depth, mx);
+            }
         }
         if (__any_sync(kFull, extent_err) && lane == 0) atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_EXTENT);
     }

@@ -60,7 +60,7 @@ int main() {
         u32 x[32], y[32], org[32];
         for (int l = 0; l < 32; l++) org[l] = x[l] = rnd() & ((it % 3) ? 0xffffffffu : rnd());
         for (int j = 16; j >= 1; j >>= 1) {
-            for (int l = 0; l < 32; l++) y[l] = transpose_stage(x[l], x[l ^ j], l, j);
+            for (int l = 0; l < 32; l++) y[l] = transpose_stage(x[l], x[l ^ j], transpose_keep(l, j), transpose_amt(l, j));
             memcpy(x, y, sizeof(x));
         }
         for (int p = 0; p < 32; p++) for (int r = 0; r < 32; r++)
