@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--cells", type=int, default=2000)
     ap.add_argument("--records", type=int, default=20_000_000)
     ap.add_argument("--profile", default="atac50")
+    ap.add_argument("--params", default="run", choices=["run", "tenx", "stress"],
+                    help="filter set: run defaults (the bench line), tenx (configs[3]) or stress (configs[4]); "
+                         "anything but `run` is a side measurement, not the bench line")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true", help="check per-cell QC rows against the oracle at full size")
@@ -46,8 +49,9 @@ def parse():
 
 def config_dict(a, n_gpus):
     return {"workload": f"synthetic 10x-ATAC chrM, BASELINE configs[{CONFIG_INDEX}]: {a.cells} cells x {a.records} "
-                        f"records per GPU, profile {a.profile}, default run filters (q20 mapq30 d5 bias1.0, "
-                        f"alignment_and_fragment_length dedup)",
+                        f"records per GPU, profile {a.profile}, " + {"run": "default run filters (q20 mapq30 d5 bias1.0, "
+                        "alignment_and_fragment_length dedup)", "tenx": "tenx filters (q0 mapq0 d5 alignment_start dedup)",
+                        "stress": "stress filters (q20 mapq30 d10 bias0.8)"}[a.params],
             "cells_per_gpu": a.cells, "records_per_gpu": a.records, "profile": a.profile,
             "sharding": f"by barcode, {n_gpus} shard(s), no data-path collective",
             "l2": "inputs per step (>2 GB) exceed the 126 MB L2; no explicit flush"}
@@ -61,8 +65,13 @@ def algorithmic_bytes(batch, n_cells, P=16569):
     return per_rec + n_cells * P * 22 + n_cells * 32
 
 
-def default_params(n_cells, extent):
+def default_params(n_cells, extent, which="run"):
+    """ParamsC(min_baseq, min_mapq, min_distance_from_end, dedup_mode, max_strand_bias, min_reads_per_cell, P, ...)."""
     from mgatk2_b200._lib import ParamsC
+    if which == "tenx":       # cli/options.py:172-236; min_distance_from_end stays 5 through the CLI (SURVEY Q1)
+        return ParamsC(0, 0, 5, 1, 1.0, 0, 16569, n_cells, extent, 0)
+    if which == "stress":     # BASELINE configs[4]: max-strand-bias 0.8, min-distance-from-end 10
+        return ParamsC(20, 30, 10, 0, 0.8, 1, 16569, n_cells, extent, 0)
     return ParamsC(20, 30, 5, 0, 1.0, 1, 16569, n_cells, extent, 0)
 
 
@@ -183,7 +192,7 @@ def run_b200(a):
     batch = synth_batch(a.cells, a.records, a.profile, seed=BASE_SEED + CONFIG_INDEX + 1000 * rank)
     t_gen = time.perf_counter() - t_gen
     extent = batch.max_read_extent()
-    params = default_params(a.cells, extent)
+    params = default_params(a.cells, extent, a.params)
     eng = PileupEngine(local)
 
     # pinned host staging (e2e) and device-resident copy (value)
@@ -251,7 +260,9 @@ def run_b200(a):
 
     if a.verify:
         from oracle.oracle import make_params, run_oracle
-        ora = run_oracle(batch, make_params(a.cells, max_read_extent=extent), n_threads=os.cpu_count() or 1, dense=False)
+        ora = run_oracle(batch, make_params(a.cells, params.min_baseq, params.min_mapq, params.min_distance_from_end,
+                                            params.dedup_mode, params.max_strand_bias, params.min_reads_per_cell,
+                                            max_read_extent=extent), n_threads=os.cpu_count() or 1, dense=False)
         for f in ("n_reads", "n_paired", "sum_depth", "covered", "max_depth", "median_lo", "median_hi"):
             np.testing.assert_array_equal(res.cell_qc[f], ora.cell_qc[f])
         np.testing.assert_array_equal(res.base_totals, ora.base_totals)

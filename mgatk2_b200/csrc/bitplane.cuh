@@ -140,33 +140,36 @@ MG_HD u32 transpose_stage(u32 mine, u32 other, u32 keep, u32 amt) {
 // ---------------------------------------------------------------------------------------------
 namespace mgatk {
 
+// masks of query bases 32w .. 32w+31 of one read -> four words at out + 16w
+template <class M>
+MG_HD void build_query_mask_group(const M &mem, u32 seq_addr /*4-aligned*/, u32 out /*16-aligned*/, int L, int w, int q_lo, int q_hi, QualGe qg) {
+    const u32 qual_addr = seq_addr + (u32)((L + 1) >> 1) + 32u * (u32)w;
+    const u32 qsh = (qual_addr & 3u) * 8u;
+    const u32 qa = qual_addr & ~3u;
+    u32 mA = 0, mC = 0, mG = 0, mT = 0;
+    u32 carry = mem.ld32(qa);
+    const int rem = L - 32 * w;                              // bases left in this group of 32
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        if (8 * g >= rem) break;
+        const u32 s = mem.ld32(seq_addr + 16u * w + 4u * g);
+        const u32 w1 = mem.ld32(qa + 8u * g + 4u), w2 = mem.ld32(qa + 8u * g + 8u);
+        const u32 ok = qual_ok8_top(funnel_r(carry, w1, qsh), funnel_r(w1, w2, qsh), qg);
+        carry = w2;
+        const Eq8 e = seq_eq8_raw(s);
+        if (g == 0) { mA = insert_top_byte<0>(mA, e.a & ok); mC = insert_top_byte<0>(mC, e.c & ok); mG = insert_top_byte<0>(mG, e.g & ok); mT = insert_top_byte<0>(mT, e.t & ok); }
+        else if (g == 1) { mA = insert_top_byte<1>(mA, e.a & ok); mC = insert_top_byte<1>(mC, e.c & ok); mG = insert_top_byte<1>(mG, e.g & ok); mT = insert_top_byte<1>(mT, e.t & ok); }
+        else if (g == 2) { mA = insert_top_byte<2>(mA, e.a & ok); mC = insert_top_byte<2>(mC, e.c & ok); mG = insert_top_byte<2>(mG, e.g & ok); mT = insert_top_byte<2>(mT, e.t & ok); }
+        else { mA = insert_top_byte<3>(mA, e.a & ok); mC = insert_top_byte<3>(mC, e.c & ok); mG = insert_top_byte<3>(mG, e.g & ok); mT = insert_top_byte<3>(mT, e.t & ok); }
+    }
+    const u32 wm = bit_range(q_lo - 32 * w, q_hi - 32 * w);   // pileup.py:67-78 (also cuts bases >= L)
+    mem.st128(out + 16u * w, mA & wm, mC & wm, mG & wm, mT & wm);
+}
+
 template <class M>
 MG_HD void build_query_masks(const M &mem, u32 seq_addr /*4-aligned*/, u32 out /*16-aligned*/, int L, int q_lo, int q_hi, QualGe qg) {
-    const u32 qual_addr = seq_addr + (u32)((L + 1) >> 1);
-    const u32 qsh = (qual_addr & 3u) * 8u;
-    u32 qa = qual_addr & ~3u;
     const int nq = (L + 31) >> 5;
-    for (int w = 0; w < nq; w++) {
-        u32 mA = 0, mC = 0, mG = 0, mT = 0;
-        u32 carry = mem.ld32(qa);
-        const int rem = L - 32 * w;                          // bases left in this group of 32
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-            if (8 * g >= rem) break;
-            const u32 s = mem.ld32(seq_addr + 16u * w + 4u * g);
-            const u32 w1 = mem.ld32(qa + 8u * g + 4u), w2 = mem.ld32(qa + 8u * g + 8u);
-            const u32 ok = qual_ok8_top(funnel_r(carry, w1, qsh), funnel_r(w1, w2, qsh), qg);
-            carry = w2;
-            const Eq8 e = seq_eq8_raw(s);
-            if (g == 0) { mA = insert_top_byte<0>(mA, e.a & ok); mC = insert_top_byte<0>(mC, e.c & ok); mG = insert_top_byte<0>(mG, e.g & ok); mT = insert_top_byte<0>(mT, e.t & ok); }
-            else if (g == 1) { mA = insert_top_byte<1>(mA, e.a & ok); mC = insert_top_byte<1>(mC, e.c & ok); mG = insert_top_byte<1>(mG, e.g & ok); mT = insert_top_byte<1>(mT, e.t & ok); }
-            else if (g == 2) { mA = insert_top_byte<2>(mA, e.a & ok); mC = insert_top_byte<2>(mC, e.c & ok); mG = insert_top_byte<2>(mG, e.g & ok); mT = insert_top_byte<2>(mT, e.t & ok); }
-            else { mA = insert_top_byte<3>(mA, e.a & ok); mC = insert_top_byte<3>(mC, e.c & ok); mG = insert_top_byte<3>(mG, e.g & ok); mT = insert_top_byte<3>(mT, e.t & ok); }
-        }
-        qa += 32u;
-        const u32 wm = bit_range(q_lo - 32 * w, q_hi - 32 * w);   // pileup.py:67-78 (also cuts bases >= L)
-        mem.st128(out + 16u * w, mA & wm, mC & wm, mG & wm, mT & wm);
-    }
+    for (int w = 0; w < nq; w++) build_query_mask_group(mem, seq_addr, out, L, w, q_lo, q_hi, qg);
 }
 
 // 32-bit windows of the four query masks starting at query bit qb (may be negative or beyond the read)

@@ -558,6 +558,7 @@ constexpr int kStageReads = 64 * kWarpsPerCta;       // records of a batch kept 
 constexpr int kMaskBytes = 32 * kStageReads;         // query masks of a batch (32-byte slots at 2x50 bp)
 constexpr int kWarpBuf = 2560;       // per-warp blob staging buffer: 32 blobs of a 50 bp read
 constexpr int kWarpBufSlack = 64;    // phase A may load this far past the last staged byte
+constexpr int kMaxItems = 256;       // 32 reads x 8 groups of 32 bases per staging pass
 constexpr int kSplitChunks = 4;      // "deep" units: at most this many chunks; their reads come in batches
 constexpr int kChunkSeg = 576;       // chunks per pass over a unit (the 518 chunks of chrM in one)
 constexpr int kAccWords = 10 * 32;   // deep units: counts of one chunk, [8 base x strand + 2 Tn5][32]
@@ -617,7 +618,7 @@ __device__ __forceinline__ bool span_exceeds(const u32 *cig, int ncig, int L, in
 // Phase A for the reads [j0, j0 + 32) of a batch of nb reads (g_rec[0..nb)), one per lane: record, blob through
 // the warp's staging buffer, query masks into slot j, first-candidate table entries. ns = reads with a slot.
 __device__ __forceinline__ void stage_reads(const PileupArgs &a, const ReadRec *g_rec, int nb, int ns, int j0, int lane,
-                                            ReadRec *s_rec, u32 mask_addr, u32 wbuf_addr, int *s_first, int seg0, int nseg,
+                                            ReadRec *s_rec, u32 mask_addr, u32 wbuf_addr, uint8_t *s_items, int *s_first, int seg0, int nseg,
                                             int q_lo, QualGe qg, bool &extent_err) {
     const SharedMem smem;
     const int j = j0 + lane;
@@ -651,14 +652,39 @@ __device__ __forceinline__ void stage_reads(const PileupArgs &a, const ReadRec *
                 if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += min((int)(w >> 4), kOpCap);
                 if (span > a.extent) { extent_err = true; break; }
             }
-            int q_hi = a.dist > 0 ? L - a.dist : L;
-            if (qg.none) q_hi = q_lo;
-            build_query_masks(smem, sb + 4 * ncig, mask_addr + (u32)j * (u32)a.mask_stride, L, q_lo, q_hi, qg);
             flags |= GF_MASKS;
             const int op0 = w0 & 15;                         // one aligned block over all of SEQ: phase B needs no CIGAR walk
             if (ncig == 1 && (op0 == 0 || op0 == 7 || op0 == 8) && (int)(w0 >> 4) >= L) flags |= GF_SIMPLE;
-            todo = false;
         }
+        // the groups of 32 bases of the staged reads are dealt to the lanes (a 150 bp read has five, and only a few such
+        // reads fit the buffer at a time): item t = (owner lane, group)
+        const u32 ng = now ? (u32)nq : 0u;
+        u32 gincl = ng;
+        for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, gincl, o); if (lane >= o) gincl += v; }
+        const int n_items = (int)__shfl_sync(kFull, gincl, 31);
+        // (when every read of the warp fits one pass - 32 reads of 50 bp - one read per lane is already dense)
+        if (__any_sync(kFull, todo && !now) && !__any_sync(kFull, now && nq > 8)) {   // n_items <= kMaxItems, three bits hold the group
+            for (u32 g = 0; g < ng; g++) s_items[gincl - ng + g] = (uint8_t)((lane << 3) | (int)g);
+            __syncwarp();
+            const u32 seq_a = sb + 4 * ncig;
+            for (int t0 = 0; t0 < n_items; t0 += 32) {
+                const int t = t0 + lane;
+                const int item = t < n_items ? s_items[t] : 0;
+                const int owner = item >> 3, w = item & 7;
+                const u32 o_seq = __shfl_sync(kFull, seq_a, owner);
+                const int o_L = __shfl_sync(kFull, L, owner);
+                if (t < n_items) {
+                    int q_hi = a.dist > 0 ? o_L - a.dist : o_L;
+                    if (qg.none) q_hi = q_lo;
+                    build_query_mask_group(smem, o_seq, mask_addr + (u32)(j0 + owner) * (u32)a.mask_stride, o_L, w, q_lo, q_hi, qg);
+                }
+            }
+        } else if (now) {                                    // one read per lane
+            int q_hi = a.dist > 0 ? L - a.dist : L;
+            if (qg.none) q_hi = q_lo;
+            build_query_masks(smem, sb + 4 * ncig, mask_addr + (u32)j * (u32)a.mask_stride, L, q_lo, q_hi, qg);
+        }
+        if (now) todo = false;
         __syncwarp();                                        // the buffer is reused by the next pass
     }
     if (j < ns) { rr.flags = flags; s_rec[j] = rr; }
@@ -817,6 +843,7 @@ k_pileup(PileupArgs a, int batch_reads) {
     __shared__ int s_unit;
     __shared__ u32 s_acc[kSplitChunks * kAccWords];          // deep units: counts of every chunk, summed over warps and batches
     __shared__ int s_first[kChunkSeg];                       // per chunk of the segment: first read of the batch that can reach it
+    __shared__ uint8_t s_items[kWarpsPerCta][kMaxItems];     // phase A: (lane << 3 | group) work items of a warp's staging pass
     extern __shared__ __align__(16) uint8_t dyn[];
     ReadRec *s_rec = reinterpret_cast<ReadRec *>(dyn);                                  // [kStageReads]
     uint8_t *s_mask = dyn + kStageReads * sizeof(ReadRec);                              // [kMaskBytes]
@@ -860,7 +887,7 @@ k_pileup(PileupArgs a, int batch_reads) {
                 // ---- phase A (the first pass also builds the masks) ----
                 if (nb == 0) for (int ch = threadIdx.x; ch < nseg; ch += kThreads) s_first[ch] = 0;
                 for (int j0 = 32 * wid; j0 < nb; j0 += kThreads)
-                    stage_reads(a, g_rec, nb, cs == 0 ? ns : 0, j0, lane, s_rec, mask_addr, wbuf_addr, s_first, un.t0 + 32 * cs, nseg,
+                    stage_reads(a, g_rec, nb, cs == 0 ? ns : 0, j0, lane, s_rec, mask_addr, wbuf_addr, s_items[wid], s_first, un.t0 + 32 * cs, nseg,
                                 q_lo, qg, extent_err);
                 __syncthreads();
                 // ---- phase B: chunks of 32 positions (x parts) dealt to the warps round-robin ----
