@@ -275,12 +275,18 @@ k_scatter(Src src, int64_t chunk, int nchunks, int shift, int bins, const u32 *_
 // one pass, block-wise exclusive scan chained over blocks by decoupled look-back (blocks take
 // their index from a ticket, so a block only ever waits for blocks that are already running).
 // ---------------------------------------------------------------------------------------------
-constexpr int kDedupThreads = 512;
-constexpr int kDedupRounds = 4;                              // records per thread
+#ifndef MGATK_DEDUP_THREADS
+#define MGATK_DEDUP_THREADS 256
+#endif
+#ifndef MGATK_DEDUP_ROUNDS
+#define MGATK_DEDUP_ROUNDS 8
+#endif
+constexpr int kDedupThreads = MGATK_DEDUP_THREADS;
+constexpr int kDedupRounds = MGATK_DEDUP_ROUNDS;             // records per thread
 constexpr int kDedupTile = kDedupThreads * kDedupRounds;
 constexpr u64 kScanAggregate = 1ull << 62, kScanPrefix = 2ull << 62, kScanValue = (1ull << 62) - 1;
 
-__global__ void __launch_bounds__(kDedupThreads, 3)
+__global__ void __launch_bounds__(kDedupThreads, 1536 / kDedupThreads)
 k_dedup(const GroupRec *__restrict__ g, const int64_t *__restrict__ m_ptr, ReadRec *__restrict__ recs, int dedup_mode, int min_mapq,
         mgatk_cell_qc *__restrict__ qc, mgatk_stats *__restrict__ stats, u32 *__restrict__ ticket,
         u64 *__restrict__ scan_state, int64_t *__restrict__ n_proc_out) {
@@ -359,15 +365,19 @@ k_dedup(const GroupRec *__restrict__ g, const int64_t *__restrict__ m_ptr, ReadR
     __syncthreads();
     // stable compaction of the reads that are piled up: position inside the tile, then the tile's prefix
     if (wid == 0) {
-        // exclusive scan of the kDedupRounds x 16 warp counts (round-major = record order), two per lane
-        constexpr int kCounts = kDedupRounds * (kDedupThreads / 32);
-        static_assert(kCounts == 64, "two counts per lane");
+        // exclusive scan of the kDedupRounds x (warps) warp counts (round-major = record order), kPer per lane
+        constexpr int kCounts = kDedupRounds * (kDedupThreads / 32), kPer = kCounts / 32;
+        static_assert(kCounts % 32 == 0, "whole counts per lane");
         u32 *flat = &s_warp[0][0];
-        const u32 c0 = flat[2 * lane], c1 = flat[2 * lane + 1];
-        u32 incl = c0 + c1;
+        u32 c[kPer], incl = 0;
+#pragma unroll
+        for (int q = 0; q < kPer; q++) { c[q] = flat[kPer * lane + q]; incl += c[q]; }
+        const u32 mine = incl;
         for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
         const u32 total = __shfl_sync(kFull, incl, 31);
-        flat[2 * lane] = incl - c0 - c1; flat[2 * lane + 1] = incl - c1;
+        u32 run = incl - mine;
+#pragma unroll
+        for (int q = 0; q < kPer; q++) { flat[kPer * lane + q] = run; run += c[q]; }
         // decoupled look-back, 128 predecessors at a time
         u64 prefix = 0;
         if (lane == 0) atomicExch((unsigned long long *)&scan_state[blk], (blk == 0 ? kScanPrefix : kScanAggregate) | (u64)total);
