@@ -14,7 +14,7 @@ using namespace mgatk;
 
 namespace {
 
-constexpr int kMaxChunks = 148 * 4;                  // partition CTAs: one wave at 4 CTAs/SM (bounds the open write heads)
+constexpr int kMaxChunks = 148 * 4 * (256 / kPartThreads);   // partition CTAs: one wave (bounds the open write heads)
 constexpr int kMaxDigitBits = 11;                    // 2048 bins * 20 B = 40 KB of shared memory per scatter CTA
 constexpr int kMaxStages = 16;
 
@@ -120,13 +120,13 @@ int partition_pass(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout
     const int bins = 1 << L.bits[pass];
     u32 *mat = (u32 *)(ws + L.mat), *part = (u32 *)(ws + L.part);
     const int grid = L.nchunks;
-    const size_t smem_h = (size_t)bins * 4, smem = (size_t)bins * 20;
-    k_hist<Src><<<grid, kHistThreads, smem_h, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, sorted_pos, error_bits);
+    const size_t smem_h = (size_t)bins * 4, smem = scatter_smem_bytes(bins);
+    k_hist<Src><<<grid, kHistThreads, smem_h, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat);
     dim3 sg((bins + 255) / 256, L.ngroups);
     k_scan_group_sums<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part);
     k_scan_bases<<<1, 1024, 0, s>>>(part, L.ngroups, bins, m_out);
     k_scan_apply<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part);
-    k_scatter<Src><<<grid, kPartThreads, smem, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, dst);
+    k_scatter<Src><<<grid, kPartThreads, smem, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, dst, error_bits);
     h->launches += 5;
     CU(cudaGetLastError());
     return MGATK_OK;

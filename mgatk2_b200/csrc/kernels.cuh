@@ -65,15 +65,22 @@ struct SrcUser {          // pass 0: reads the caller's SoA batch and applies th
         const int c = b.bc_idx[i];
         return ((b.flag[i] & 0x904) || c < 0 || c >= n_cells) ? -1 : c;
     }
-    struct Raw { int32_t pos, tlen, bc; u32 off; uint16_t flag, lseq, ncig; uint8_t mapq; bool valid; };
+    struct Raw { int32_t pos, tlen, bc, prev; u32 off; uint16_t flag, lseq, ncig; uint8_t mapq; bool valid; };
     __device__ __forceinline__ Raw load_raw(int64_t i, bool valid) const {     // loads only; combined one step later
         Raw r; r.valid = valid;
-        r.pos = 0; r.tlen = 0; r.bc = -1; r.off = 0; r.flag = 0x4; r.lseq = 0; r.ncig = 0; r.mapq = 0;
+        r.pos = 0; r.tlen = 0; r.bc = -1; r.off = 0; r.flag = 0x4; r.lseq = 0; r.ncig = 0; r.mapq = 0; r.prev = 0x80000000;
         if (valid) {
+            if ((threadIdx.x & 31) == 0 && i > 0) r.prev = b.pos[i - 1];     // sortedness check across the warp border
             r.pos = b.pos[i]; r.tlen = b.tlen[i]; r.bc = b.bc_idx[i]; r.off = b.blob_off[i];
             r.flag = b.flag[i]; r.lseq = b.l_seq[i]; r.ncig = b.n_cigar[i]; r.mapq = b.mapq[i];
         }
         return r;
+    }
+    // records must come sorted by reference_start (coordinate-sorted BAM): compare with the record before
+    __device__ __forceinline__ bool out_of_order(const Raw &w) const {
+        int32_t before = __shfl_up_sync(0xffffffffu, w.valid ? w.pos : 0x7fffffff, 1);
+        if ((threadIdx.x & 31) == 0) before = w.prev;
+        return w.valid && w.pos < before;
     }
     __device__ __forceinline__ GroupRec finish(const Raw &w) const {
         GroupRec r;
@@ -103,6 +110,7 @@ struct SrcGrouped {       // pass 1 of a two-digit partition: already filtered, 
         if (valid) { r.lo = reinterpret_cast<const uint4 *>(a + i)[0]; r.hi = reinterpret_cast<const uint4 *>(a + i)[1]; }
         return r;
     }
+    __device__ __forceinline__ bool out_of_order(const Raw &) const { return false; }
     __device__ __forceinline__ GroupRec finish(const Raw &w) const {
         GroupRec r;
         r.cell = w.valid ? (int32_t)w.lo.x : -1; r.pos = (int32_t)w.lo.y; r.tlen = w.lo.z; r.mq = w.lo.w;
@@ -111,15 +119,17 @@ struct SrcGrouped {       // pass 1 of a two-digit partition: already filtered, 
     }
 };
 
-constexpr int kPartThreads = 256;  // records per CTA step
+#ifndef MGATK_PART_THREADS
+#define MGATK_PART_THREADS 256
+#endif
+constexpr int kPartThreads = MGATK_PART_THREADS;  // records per CTA step of the scatter
 constexpr int kHistAhead = 4;      // steps loaded before counting (k_hist)
 
 // Per-CTA digit histogram of a contiguous chunk of records (order does not matter for counting).
 constexpr int kHistThreads = 1024;
 template <class Src>
 __global__ void __launch_bounds__(kHistThreads)
-k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict__ mat,
-       const int32_t *__restrict__ sorted_check_pos, u64 *__restrict__ error_bits) {
+k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict__ mat) {
     extern __shared__ u32 smem[];
     u32 *h = smem;
     for (int b = threadIdx.x; b < bins; b += kHistThreads) h[b] = 0;
@@ -127,7 +137,6 @@ k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict
     const int64_t n = src.count();
     int64_t beg = (int64_t)blockIdx.x * chunk, end = beg + chunk;
     if (end > n) end = n;
-    bool unsorted = false;
     for (int64_t i0 = beg + threadIdx.x; i0 < end; i0 += kHistThreads * kHistAhead) {
         int d[kHistAhead];
 #pragma unroll
@@ -137,13 +146,11 @@ k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict
             if (i < end) {
                 const int c = src.cell(i);
                 if (c >= 0) d[k] = (c >> shift) & (bins - 1);
-                if (sorted_check_pos && i > 0 && sorted_check_pos[i] < sorted_check_pos[i - 1]) unsorted = true;
             }
         }
 #pragma unroll
         for (int k = 0; k < kHistAhead; k++) if (d[k] >= 0) atomicAdd(&h[d[k]], 1u);
     }
-    if (unsorted) atomicOr(error_bits, (u64)ERR_UNSORTED);
     __syncthreads();
     u32 *row = mat + (size_t)blockIdx.x * bins;
     for (int b = threadIdx.x; b < bins; b += kHistThreads) row[b] = h[b];
@@ -216,53 +223,74 @@ __global__ void k_scan_apply(u32 *__restrict__ mat, int nchunks, int bins, const
 // one shared-memory atomic per (warp, digit) and two barriers per step (the packed counters are double
 // buffered). Every record leaves as one full 32-byte sector.
 constexpr int kPartWarps = kPartThreads / 32;
-static_assert(kPartWarps == 8, "the packed per-digit counter holds one byte per warp");
+static_assert(kPartWarps == 8 || kPartWarps == 4, "the packed per-digit counter holds one byte per warp");
+
+// packed per-digit counter of a step: one byte per warp
+template <int kWarps> struct Packed;
+template <> struct Packed<4> {
+    u32 x;
+    __device__ __forceinline__ void clear() { x = 0u; }
+    __device__ __forceinline__ static void add(Packed *p, int wid, u32 n) { atomicAdd(&p->x, n << (8 * wid)); }
+    __device__ __forceinline__ u32 before(int wid) const { return __dp4a(x & (wid == 0 ? 0u : (0xffffffffu >> (32 - 8 * wid))), 0x01010101u, 0u); }
+    __device__ __forceinline__ bool first(int wid) const { return (x & (wid == 0 ? 0u : (0xffffffffu >> (32 - 8 * wid)))) == 0u; }
+    __device__ __forceinline__ u32 total() const { return __dp4a(x, 0x01010101u, 0u); }
+};
+template <> struct Packed<8> {
+    u32 x, y;                                              // x: warps 0-3, y: warps 4-7
+    __device__ __forceinline__ void clear() { x = 0u; y = 0u; }
+    __device__ __forceinline__ static void add(Packed *p, int wid, u32 n) { atomicAdd(wid < 4 ? &p->x : &p->y, n << (8 * (wid & 3))); }
+    __device__ __forceinline__ u32 mx(int wid) const { return wid >= 4 ? 0xffffffffu : wid == 0 ? 0u : (0xffffffffu >> (32 - 8 * wid)); }
+    __device__ __forceinline__ u32 my(int wid) const { return wid <= 4 ? 0u : (0xffffffffu >> (32 - 8 * (wid - 4))); }
+    __device__ __forceinline__ u32 before(int wid) const { return __dp4a(x & mx(wid), 0x01010101u, __dp4a(y & my(wid), 0x01010101u, 0u)); }
+    __device__ __forceinline__ bool first(int wid) const { return ((x & mx(wid)) | (y & my(wid))) == 0u; }
+    __device__ __forceinline__ u32 total() const { return __dp4a(x, 0x01010101u, __dp4a(y, 0x01010101u, 0u)); }
+};
+typedef Packed<kPartWarps> Pack;
+__host__ __device__ inline size_t scatter_smem_bytes(int bins) { return (size_t)bins * (2 * sizeof(Pack) + 4); }
 
 template <class Src>
 __global__ void __launch_bounds__(kPartThreads)
-k_scatter(Src src, int64_t chunk, int nchunks, int shift, int bins, const u32 *__restrict__ mat, GroupRec *__restrict__ dst) {
+k_scatter(Src src, int64_t chunk, int nchunks, int shift, int bins, const u32 *__restrict__ mat, GroupRec *__restrict__ dst,
+          u64 *__restrict__ error_bits) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint2 *packed = reinterpret_cast<uint2 *>(smem_raw);               // [2][bins] per-warp byte counters of the step (x: warps 0-3, y: warps 4-7)
-    u32 *off = reinterpret_cast<u32 *>(smem_raw + (size_t)2 * bins * 8);   // [bins] running destination offsets
+    Pack *packed = reinterpret_cast<Pack *>(smem_raw);                 // [2][bins] per-warp byte counters of the step
+    u32 *off = reinterpret_cast<u32 *>(smem_raw + (size_t)2 * bins * sizeof(Pack));   // [bins] running destination offsets
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const u32 *row = mat + (size_t)blockIdx.x * bins;
-    for (int b = t; b < bins; b += kPartThreads) { off[b] = row[b]; packed[b] = make_uint2(0u, 0u); packed[bins + b] = make_uint2(0u, 0u); }
+    for (int b = t; b < bins; b += kPartThreads) { off[b] = row[b]; packed[b].clear(); packed[bins + b].clear(); }
     const int64_t n = src.count();
     int64_t beg = (int64_t)blockIdx.x * chunk, end = beg + chunk;
     if (end > n) end = n;
     const u32 lt = (1u << lane) - 1;
-    const u32 below_x = wid >= 4 ? 0xffffffffu : wid == 0 ? 0u : (0xffffffffu >> (32 - 8 * wid));        // bytes of the earlier warps
-    const u32 below_y = wid <= 4 ? 0u : (0xffffffffu >> (32 - 8 * (wid - 4)));
     typename Src::Raw r1 = src.load_raw(beg + t, beg + t < end);                        // two steps of loads in flight
     typename Src::Raw r2 = src.load_raw(beg + kPartThreads + t, beg + kPartThreads + t < end);
     __syncthreads();
     int buf = 0;
+    bool unsorted = false;
     for (int64_t i0 = beg; i0 < end; i0 += kPartThreads, buf ^= 1) {
+        unsorted |= src.out_of_order(r1);
         const GroupRec cur = src.finish(r1);
         r1 = r2;
         r2 = src.load_raw(i0 + 2 * kPartThreads + t, i0 + 2 * kPartThreads + t < end);
         const int c = cur.cell;
         const int d = c >= 0 ? (c >> shift) & (bins - 1) : -1;
-        uint2 *pk = packed + (size_t)buf * bins;
+        Pack *pk = packed + (size_t)buf * bins;
         const u32 peers = __match_any_sync(kFull, d);
         const bool leader = d >= 0 && lane == __ffs(peers) - 1;
-        if (leader) atomicAdd(wid < 4 ? &pk[d].x : &pk[d].y, (u32)__popc(peers) << (8 * (wid & 3)));
+        if (leader) Pack::add(&pk[d], wid, (u32)__popc(peers));
         __syncthreads();
-        uint2 v = make_uint2(0u, 0u); u32 base = 0;
+        Pack v; v.clear(); u32 base = 0;
         if (d >= 0) { v = pk[d]; base = off[d]; }
         __syncthreads();
         if (d >= 0) {
-            const u32 lx = v.x & below_x, ly = v.y & below_y;
-            if (leader && (lx | ly) == 0) {                  // first warp that holds the digit
-                off[d] = base + __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, 0u));
-                pk[d] = make_uint2(0u, 0u);
-            }
-            const size_t dd = (size_t)base + __dp4a(lx, 0x01010101u, __dp4a(ly, 0x01010101u, 0u)) + __popc(peers & lt);
+            if (leader && v.first(wid)) { off[d] = base + v.total(); pk[d].clear(); }   // first warp that holds the digit
+            const size_t dd = (size_t)base + v.before(wid) + __popc(peers & lt);
             // one 256-bit store per record: a scattered store costs the LSU one pass per lane whatever its width
             asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + dd), "r"((u32)cur.cell), "r"((u32)cur.pos),
                          "r"(cur.tlen), "r"(cur.mq), "r"(cur.off), "r"(cur.len), "r"(0u), "r"(0u) : "memory");
         }
     }
+    if (unsorted) atomicOr(error_bits, (u64)ERR_UNSORTED);
 }
 
 // ---------------------------------------------------------------------------------------------
