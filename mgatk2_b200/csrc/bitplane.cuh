@@ -147,15 +147,14 @@ MG_HD void build_query_mask_group(const M &mem, u32 seq_addr /*4-aligned*/, u32 
     const u32 qsh = (qual_addr & 3u) * 8u;
     const u32 qa = qual_addr & ~3u;
     u32 mA = 0, mC = 0, mG = 0, mT = 0;
-    u32 carry = mem.ld32(qa);
-    const int rem = L - 32 * w;                              // bases left in this group of 32
+    const int lo = q_lo - 32 * w, hi = (q_hi < L ? q_hi : L) - 32 * w;   // window inside this group of 32 bases
 #pragma unroll
     for (int g = 0; g < 4; g++) {
-        if (8 * g >= rem) break;
+        if (8 * g >= hi) break;                              // eight bases at a time; those outside the window are skipped
+        if (8 * g + 8 <= lo) continue;
         const u32 s = mem.ld32(seq_addr + 16u * w + 4u * g);
-        const u32 w1 = mem.ld32(qa + 8u * g + 4u), w2 = mem.ld32(qa + 8u * g + 8u);
-        const u32 ok = qual_ok8_top(funnel_r(carry, w1, qsh), funnel_r(w1, w2, qsh), qg);
-        carry = w2;
+        const u32 w0 = mem.ld32(qa + 8u * g), w1 = mem.ld32(qa + 8u * g + 4u), w2 = mem.ld32(qa + 8u * g + 8u);
+        const u32 ok = qual_ok8_top(funnel_r(w0, w1, qsh), funnel_r(w1, w2, qsh), qg);
         const Eq8 e = seq_eq8_raw(s);
         if (g == 0) { mA = insert_top_byte<0>(mA, e.a & ok); mC = insert_top_byte<0>(mC, e.c & ok); mG = insert_top_byte<0>(mG, e.g & ok); mT = insert_top_byte<0>(mT, e.t & ok); }
         else if (g == 1) { mA = insert_top_byte<1>(mA, e.a & ok); mC = insert_top_byte<1>(mC, e.c & ok); mG = insert_top_byte<1>(mG, e.g & ok); mT = insert_top_byte<1>(mT, e.t & ok); }
