@@ -221,6 +221,7 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
 
     // ---- stage 1 + partition by cell ----
     SrcUser su; su.b = *b; su.n_cells = C;
+    su.vec4 = (((uintptr_t)b->bc_idx & 15) == 0 && ((uintptr_t)b->flag & 7) == 0) ? 1 : 0;
     GroupRec *g0 = grouped_at(ws, L, 0);
     rc = partition_pass(h, s, su, L, 0, ws, b->pos, error_bits, m_ptr, g0);
     if (rc) return rc;
@@ -242,14 +243,13 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     CU(cudaMemsetAsync(ws + L.scan_state, 0, (size_t)L.dedup_blocks * 8, s));
     k_dedup<<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(g, m_ptr, recs, p->dedup_mode, p->min_mapq, o->cell_qc, o->stats,
                                                               ticket, (u64 *)(ws + L.scan_state), n_proc);
-    k_cell_start<<<(C + 1 + 255) / 256, 256, 0, s>>>(recs, n_proc, C, cell_start);
-    h->launches += 2;
+    h->launches += 1;
     mark(h, s, "dedup");
 
     // ---- units ----
     int32_t *unit_start = (int32_t *)(ws + L.unit_start);
     Unit *units = (Unit *)(ws + L.units);
-    k_plan_scan<<<1, 1024, 0, s>>>(cell_start, o->cell_qc, C, p->min_reads_per_cell, L.unit_reads, ppad, unit_start, n_units);
+    k_plan_scan<<<1, 1024, 0, s>>>(o->cell_qc, C, p->min_reads_per_cell, L.unit_reads, ppad, cell_start, unit_start, n_units);
     k_plan_units<<<(unsigned)((L.max_units + 255) / 256), 256, 0, s>>>(cell_start, o->cell_qc, recs, unit_start, C,
                                                                       p->min_reads_per_cell, L.unit_reads, ppad,
                                                                       p->max_read_extent, units);

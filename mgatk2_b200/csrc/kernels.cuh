@@ -59,6 +59,15 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 struct SrcUser {          // pass 0: reads the caller's SoA batch and applies the stage-1 filter
     mgatk_batch b;
     int32_t n_cells;
+    int vec4;             // bc_idx is 16-byte and flag 8-byte aligned: k_hist loads four records at a time
+    __device__ __forceinline__ void cell4(int64_t i, int (&c)[4]) const {      // i % 4 == 0, i + 3 < count()
+        const int4 bc = *reinterpret_cast<const int4 *>(b.bc_idx + i);
+        const uint2 fl = *reinterpret_cast<const uint2 *>(b.flag + i);
+        const int cc[4] = {bc.x, bc.y, bc.z, bc.w};
+        const u32 ff[4] = {fl.x & 0xffffu, fl.x >> 16, fl.y & 0xffffu, fl.y >> 16};
+#pragma unroll
+        for (int k = 0; k < 4; k++) c[k] = ((ff[k] & 0x904u) || cc[k] < 0 || cc[k] >= n_cells) ? -1 : cc[k];
+    }
     __device__ __forceinline__ int64_t count() const { return b.n_records; }
     __device__ __forceinline__ int cell(int64_t i) const {
         // readers.py:96-97 unmapped/secondary/supplementary; :104-111 tag absent or not whitelisted
@@ -101,6 +110,8 @@ struct SrcUser {          // pass 0: reads the caller's SoA batch and applies th
 struct SrcGrouped {       // pass 1 of a two-digit partition: already filtered, count on the device
     const GroupRec *a;
     const int64_t *m;
+    static constexpr int vec4 = 0;
+    __device__ __forceinline__ void cell4(int64_t, int (&)[4]) const {}
     __device__ __forceinline__ int64_t count() const { return *m; }
     __device__ __forceinline__ int cell(int64_t i) const { return a[i].cell; }
     struct Raw { uint4 lo, hi; bool valid; };
@@ -137,6 +148,27 @@ k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict
     const int64_t n = src.count();
     int64_t beg = (int64_t)blockIdx.x * chunk, end = beg + chunk;
     if (end > n) end = n;
+    if (src.vec4) {                                          // four records per thread and load, two loads in flight
+        const int64_t end4 = beg + ((end - beg) & ~(int64_t)3);
+        for (int64_t i0 = beg + 4 * (int64_t)threadIdx.x; i0 < end4; i0 += 8 * kHistThreads) {
+            int c[2][4];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int64_t i = i0 + 4 * (int64_t)kHistThreads * k;
+#pragma unroll
+                for (int q = 0; q < 4; q++) c[k][q] = -1;
+                if (i < end4) src.cell4(i, c[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (c[k][q] >= 0) atomicAdd(&h[(c[k][q] >> shift) & (bins - 1)], 1u);
+        }
+        for (int64_t i = end4 + threadIdx.x; i < end; i += kHistThreads) {
+            const int c = src.cell(i);
+            if (c >= 0) atomicAdd(&h[(c >> shift) & (bins - 1)], 1u);
+        }
+    } else
     for (int64_t i0 = beg + threadIdx.x; i0 < end; i0 += kHistThreads * kHistAhead) {
         int d[kHistAhead];
 #pragma unroll
@@ -312,6 +344,7 @@ k_scatter(Src src, int64_t chunk, int nchunks, int shift, int bins, const u32 *_
 constexpr int kDedupThreads = MGATK_DEDUP_THREADS;
 constexpr int kDedupRounds = MGATK_DEDUP_ROUNDS;             // records per thread
 constexpr int kDedupTile = kDedupThreads * kDedupRounds;
+constexpr int kDedupCells = 64;                             // consecutive cells of a tile counted in shared memory
 constexpr u64 kScanAggregate = 1ull << 62, kScanPrefix = 2ull << 62, kScanValue = (1ull << 62) - 1;
 
 __global__ void __launch_bounds__(kDedupThreads, 1536 / kDedupThreads)
@@ -322,11 +355,15 @@ k_dedup(const GroupRec *__restrict__ g, const int64_t *__restrict__ m_ptr, ReadR
     __shared__ u32 s_warp[kDedupRounds][kDedupThreads / 32];
     __shared__ u32 s_blk;
     __shared__ u64 s_prefix;
+    __shared__ u32 s_cell[kDedupCells][3];                   // per-cell counts of the tile's first cells: one global atomic per (tile, cell)
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    for (int e = threadIdx.x; e < kDedupCells * 3; e += kDedupThreads) (&s_cell[0][0])[e] = 0;
     if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1u);
     __syncthreads();
     const u32 blk = s_blk;
     const int64_t m = *m_ptr;
+    // the records are grouped by cell: a tile holds a short run of consecutive cells, counted in shared memory
+    const int cell0 = (int64_t)blk * kDedupTile < m ? g[(int64_t)blk * kDedupTile].cell : 0;
     const int lane = lane_id(), wid = threadIdx.x >> 5;
     ReadRec rr[kDedupRounds];
     u32 pm[kDedupRounds];
@@ -372,12 +409,20 @@ k_dedup(const GroupRec *__restrict__ g, const int64_t *__restrict__ m_ptr, ReadR
         // per-cell survivors: lanes of a warp mostly share one cell
         const u32 peers = __match_any_sync(kFull, cell);
         const u32 kept = __ballot_sync(kFull, keep), paird = __ballot_sync(kFull, keep && paired);
-        if (cell >= 0 && lane == __ffs(peers) - 1) {
-            const u32 nk = __popc(kept & peers), np = __popc(paird & peers);
-            if (nk) atomicAdd(&qc[cell].n_reads, nk);
-            if (np) atomicAdd(&qc[cell].n_paired, np);
-        }
         pm[k] = __ballot_sync(kFull, process);
+        if (cell >= 0 && lane == __ffs(peers) - 1) {
+            const u32 nk = __popc(kept & peers), np = __popc(paird & peers), npr = __popc(pm[k] & peers);
+            const u32 rel = (u32)(cell - cell0);
+            if (rel < (u32)kDedupCells) {
+                if (nk) atomicAdd(&s_cell[rel][0], nk);
+                if (np) atomicAdd(&s_cell[rel][1], np);
+                if (npr) atomicAdd(&s_cell[rel][2], npr);
+            } else {
+                if (nk) atomicAdd(&qc[cell].n_reads, nk);
+                if (np) atomicAdd(&qc[cell].n_paired, np);
+                if (npr) atomicAdd(&qc[cell].median_lo, npr);
+            }
+        }
         if (lane == 0) s_warp[k][wid] = __popc(pm[k]);
     }
     for (int o = 16; o; o >>= 1) {
@@ -391,6 +436,13 @@ k_dedup(const GroupRec *__restrict__ g, const int64_t *__restrict__ m_ptr, ReadR
         if (n_empty) atomicAdd(&s_cnt[3], n_empty);
     }
     __syncthreads();
+    // per-cell survivors (processors.py:33-34) and reads to pile up per cell (the cell borders of the compacted records;
+    // parked in median_lo, which shares a sector with the two counters and is only written by k_median at the very end)
+    for (int e = threadIdx.x; e < kDedupCells; e += kDedupThreads) {
+        if (s_cell[e][0]) atomicAdd(&qc[cell0 + e].n_reads, s_cell[e][0]);
+        if (s_cell[e][1]) atomicAdd(&qc[cell0 + e].n_paired, s_cell[e][1]);
+        if (s_cell[e][2]) atomicAdd(&qc[cell0 + e].median_lo, s_cell[e][2]);
+    }
     // stable compaction of the reads that are piled up: position inside the tile, then the tile's prefix
     if (wid == 0) {
         // exclusive scan of the kDedupRounds x (warps) warp counts (round-major = record order), kPer per lane
@@ -450,16 +502,6 @@ k_dedup(const GroupRec *__restrict__ g, const int64_t *__restrict__ m_ptr, ReadR
         if ((pm[k] >> lane) & 1u) recs[prefix + s_warp[k][wid] + __popc(pm[k] & ((1u << lane) - 1u))] = rr[k];
 }
 
-// first compacted index of every cell: lower_bound on the cell field (records are grouped by cell)
-__global__ void k_cell_start(const ReadRec *__restrict__ recs, const int64_t *__restrict__ n_ptr, int n_cells,
-                             int32_t *__restrict__ cell_start) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > n_cells) return;
-    int lo = 0, hi = (int)*n_ptr;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if ((int)(recs[mid].flags >> GF_CELL_SHIFT) < c) lo = mid + 1; else hi = mid; }
-    cell_start[c] = lo;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Work planning: a unit is (cell, position tile). Tile borders sit at every `unit_reads`-th read of
 // the cell (rounded down to a chunk of 32 positions), so units carry about the same number of reads
@@ -476,38 +518,43 @@ __device__ __forceinline__ bool cell_dead(const mgatk_cell_qc &q, int min_reads)
     return q.n_reads == 0 || (int64_t)q.n_reads < (int64_t)min_reads;
 }
 
+// one pass over the cells: first compacted record of every cell (exclusive scan of the per-cell counts of k_dedup)
+// and first unit of every cell (exclusive scan of the tile counts), both in one 64-bit scan
 __global__ void __launch_bounds__(1024)
-k_plan_scan(const int32_t *__restrict__ cell_start, const mgatk_cell_qc *__restrict__ qc, int n_cells, int min_reads,
-            int unit_reads, int ppad, int32_t *__restrict__ unit_start, int32_t *__restrict__ n_units) {
-    __shared__ int warp_sums[32];
-    __shared__ int carry_s;
+k_plan_scan(const mgatk_cell_qc *__restrict__ qc, int n_cells, int min_reads,
+            int unit_reads, int ppad, int32_t *__restrict__ cell_start, int32_t *__restrict__ unit_start, int32_t *__restrict__ n_units) {
+    __shared__ u64 warp_sums[32];
+    __shared__ u64 carry_s;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     if (t == 0) carry_s = 0;
     __syncthreads();
     for (int c0 = 0; c0 < n_cells; c0 += 1024) {
         const int c = c0 + t;
-        int nt = 0;
+        u64 mine = 0;                                        // records << 32 | tiles
         if (c < n_cells) {
-            const int cnt = cell_dead(qc[c], min_reads) ? 0 : cell_start[c + 1] - cell_start[c];
-            nt = tiles_for(cnt, unit_reads, ppad);
+            const u32 np = qc[c].median_lo;                  // parked there by k_dedup
+            const int cnt = cell_dead(qc[c], min_reads) ? 0 : (int)np;
+            mine = ((u64)np << 32) | (u32)tiles_for(cnt, unit_reads, ppad);
         }
-        int inc = nt;
-        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
+        u64 inc = mine;
+        for (int o = 1; o < 32; o <<= 1) { const u64 v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
         if (lane == 31) warp_sums[wid] = inc;
         __syncthreads();
         if (wid == 0) {
-            int v = warp_sums[lane], s = v;
-            for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(kFull, s, o); if (lane >= o) s += x; }
-            warp_sums[lane] = s - v;
+            const u64 v = warp_sums[lane];
+            u64 sc = v;
+            for (int o = 1; o < 32; o <<= 1) { const u64 x = __shfl_up_sync(kFull, sc, o); if (lane >= o) sc += x; }
+            warp_sums[lane] = sc - v;
         }
         __syncthreads();
-        const int carry = carry_s;
-        if (c < n_cells) unit_start[c] = carry + warp_sums[wid] + inc - nt;
+        const u64 carry = carry_s;
+        const u64 excl = carry + warp_sums[wid] + inc - mine;
+        if (c < n_cells) { cell_start[c] = (int32_t)(excl >> 32); unit_start[c] = (int32_t)(u32)excl; }
         __syncthreads();
         if (t == 1023) carry_s = carry + warp_sums[31] + inc;
         __syncthreads();
     }
-    if (t == 0) { unit_start[n_cells] = carry_s; *n_units = carry_s; }
+    if (t == 0) { cell_start[n_cells] = (int32_t)(carry_s >> 32); unit_start[n_cells] = (int32_t)(u32)carry_s; *n_units = (int32_t)(u32)carry_s; }
 }
 
 __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk_cell_qc *__restrict__ qc,
