@@ -157,3 +157,56 @@ def test_long_extent_ring_sizes(engine):
         sub = [r for r in recs if sum(l for o, l in r["cigar"]) <= cap]
         res, ora = run_both(engine, ReadBatch.from_records(sub), 4)
         assert_result_equals_oracle(res, ora)
+
+
+def _random_read(rng, pos, L, bc, kind):
+    """One record with a CIGAR of the requested kind whose query length matches SEQ."""
+    seq = "".join(rng.choice(list("ACGTN="), p=[0.24, 0.24, 0.24, 0.24, 0.03, 0.01], size=L))
+    qual = rng.choice([40, 30, 20, 19, 5, 200], p=[0.5, 0.2, 0.1, 0.1, 0.05, 0.05], size=L).tolist()
+    if kind == "simple" or L < 12:
+        cig = [(0, L)]
+    elif kind == "clip":
+        a, b = int(rng.integers(1, 5)), int(rng.integers(0, 5))
+        cig = [(4, a), (0, L - a - b)] + ([(4, b)] if b else [])
+    elif kind == "indel":
+        a = int(rng.integers(3, L - 6))
+        i, d = int(rng.integers(1, 3)), int(rng.integers(1, 9))
+        cig = [(0, a), (1, i), (0, 2), (2, d), (0, L - a - i - 2)]
+    else:                                # many small blocks: S M (N M)* H
+        cig, left = [(4, 2)], L - 2
+        while left > 6:
+            cig += [(0, 3), (3, int(rng.integers(1, 4)))]
+            left -= 3
+        cig += [(0, left), (5, 7)]
+    return dict(pos=pos, flag=int(rng.choice([0, 16, 99, 147])), mapq=int(rng.choice([60, 29])), seq=seq, qual=qual,
+                cigar=cig, tlen=int(rng.integers(-400, 400)), bc_idx=bc)
+
+
+def test_staging_paths(engine):
+    """The corners of the pileup kernel's staging: a hot spot inside a wide tile (more reads than mask slots), mixed
+    read lengths that need several staging passes per warp, reads with more than eight 32-base groups, reads whose
+    blob exceeds the warp buffer (per-base path), long CIGARs, and the base-quality extremes of the int8 compare."""
+    rng = np.random.default_rng(11)
+    recs = []
+    for _ in range(2500):                # cell 0: hot spot of 50 bp reads in 150 positions + sparse background
+        recs.append(_random_read(rng, int(rng.integers(8000, 8150)), 50, 0, rng.choice(["simple", "clip", "indel"])))
+    for _ in range(400):
+        recs.append(_random_read(rng, int(rng.integers(0, 16569)), 50, 0, "simple"))
+    for _ in range(1500):                # cell 1: 50 / 150 / 300 bp mixed
+        L = int(rng.choice([50, 150, 300]))
+        recs.append(_random_read(rng, int(rng.integers(0, 16400)), L, 1, rng.choice(["simple", "clip", "indel", "blocks"])))
+    for _ in range(40):                  # cell 2: blobs beyond the warp buffer
+        recs.append(_random_read(rng, int(rng.integers(0, 14000)), 2100, 2, rng.choice(["simple", "indel"])))
+    for _ in range(300):
+        recs.append(_random_read(rng, int(rng.integers(0, 16569)), 36, 2, "simple"))
+    recs.sort(key=lambda r: r["pos"])
+    short = [r for r in recs if len(r["seq"]) < 1000]    # extent of a few hundred: mask slots for ~100 reads per CTA
+    for kw in (dict(), dict(min_baseq=-100, min_distance_from_end=0), dict(min_baseq=127, dedup_mode=2),
+               dict(min_baseq=200), dict(max_strand_bias=0.75, min_distance_from_end=12, dedup_mode=1)):
+        res, ora = run_both(engine, ReadBatch.from_records(short), 3, device_path=bool(kw.get("dedup_mode", 0)), **kw)
+        assert_result_equals_oracle(res, ora)
+    plain = [r for r in short if len(r["seq"]) == 50 and len(r["cigar"]) <= 3]   # extent 50: 512 slots, hot spot overflows
+    res, ora = run_both(engine, ReadBatch.from_records(plain), 3)
+    assert_result_equals_oracle(res, ora)
+    res, ora = run_both(engine, ReadBatch.from_records(recs), 3)                 # with the 2100 bp reads: per-base path
+    assert_result_equals_oracle(res, ora)
