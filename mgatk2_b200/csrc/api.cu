@@ -268,7 +268,17 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     a.extent = p->max_read_extent;
     a.mask_stride = mask_stride_for(p->max_read_extent);
     a.cap_reads = cap_reads_for(p->max_read_extent);
+#ifdef MGATK_TIMING
+    a.dbg = (unsigned long long *)(ws + L.scalars + 64);
+    cudaMemsetAsync(a.dbg, 0, 64, s);
+#endif
     rc = launch_pileup(h, s, a, a.cap_reads < 32 ? 32 : a.cap_reads);
+#ifdef MGATK_TIMING                                       // profiling build: share of warp-cycles per phase of k_pileup
+    { unsigned long long hd[6]; cudaStreamSynchronize(s); cudaMemcpy(hd, a.dbg, 48, cudaMemcpyDeviceToHost);
+      double tot = 0; for (int k = 0; k < 6; k++) tot += (double)hd[k];
+      fprintf(stderr, "[timing] wait-for-slowest-warp(unit end) %.1f%% phaseA %.1f%% wait(phase A end) %.1f%% phaseB %.1f%% unit-setup %.1f%% epilogue %.1f%% (warp-cycles %.3g)\n",
+              100 * hd[0] / tot, 100 * hd[1] / tot, 100 * hd[2] / tot, 100 * hd[3] / tot, 100 * hd[4] / tot, 100 * hd[5] / tot, tot); }
+#endif
     if (rc) return rc;
     mark(h, s, "pileup");
 

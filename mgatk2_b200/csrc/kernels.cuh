@@ -617,6 +617,9 @@ struct PileupArgs {
     uint16_t *planes; mgatk_cell_qc *qc; mgatk_stats *stats;
     mgatk_overflow *ovf; int64_t ovf_cap;
     int P, ppad, min_baseq, dist, apply_bias, extent, raw;
+#ifdef MGATK_TIMING
+    unsigned long long *dbg;          // -DMGATK_TIMING: warp-cycles per phase (profiling build only, see profiles/README.md)
+#endif
     int mask_stride;                 // bytes of one read's mask slot: 16 * ceil(extent / 32)
     int cap_reads;                   // mask slots per CTA (<= kStageReads)
     double max_bias;
@@ -941,14 +944,24 @@ k_pileup(PileupArgs a, int batch_reads) {
     const QualGe qg = make_qual_ge(a.min_baseq);
     const int q_lo = a.dist > 0 ? a.dist : 0;                // pileup.py:67-72
     const TransposeConst tc = make_transpose_const(lane);
+#ifdef MGATK_TIMING
+    // BAR.SYNC only blocks at the first instruction that needs the barrier: the wait of a barrier shows up in the tick
+    // AFTER the next dependent instruction, hence the tick behind the shared-memory read of the unit index
+    long long tt[6] = {0, 0, 0, 0, 0, 0}; long long tc0 = clock64(), tc1;
+#define TICK(k) { tc1 = clock64(); tt[k] += tc1 - tc0; tc0 = tc1; }
+#else
+#define TICK(k)
+#endif
     int next_unit = 0;
     if (threadIdx.x == 0) next_unit = atomicAdd(a.work_counter, 1);
     for (;;) {
+        TICK(5)
         __syncthreads();                                     // previous unit fully consumed (also covers the s_acc init)
         if (threadIdx.x == 0) s_unit = next_unit;
         __syncthreads();
         const int u = s_unit;
         if (u >= n_units) break;
+        TICK(0)
         if (threadIdx.x == 0) next_unit = atomicAdd(a.work_counter, 1);   // in flight while this unit is processed
         const Unit un = a.units[u];
         const int n_chunks = (un.t1 - un.t0) >> 5;
@@ -970,11 +983,17 @@ k_pileup(PileupArgs a, int batch_reads) {
                 const int nseg = min(kChunkSeg, n_chunks - cs);
                 if (rb > 0 || cs > 0) __syncthreads();       // the previous batch / pass is consumed
                 // ---- phase A (the first pass also builds the masks) ----
+                TICK(4)
                 if (nb == 0) for (int ch = threadIdx.x; ch < nseg; ch += kThreads) s_first[ch] = 0;
                 for (int j0 = 32 * wid; j0 < nb; j0 += kThreads)
                     stage_reads(a, g_rec, nb, cs == 0 ? ns : 0, j0, lane, s_rec, mask_addr, wbuf_addr, s_items[wid], s_first, un.t0 + 32 * cs, nseg,
                                 q_lo, qg, extent_err);
+                TICK(1)
                 __syncthreads();
+#ifdef MGATK_TIMING
+                if (s_first[0] < 0) break;                   // (never: makes the barrier's wait land in the next tick)
+#endif
+                TICK(2)
                 // ---- phase B: chunks of 32 positions (x parts) dealt to the warps round-robin ----
                 for (int item = wid; item < nseg * nparts; item += kWarpsPerCta) {
                     const int chl = item >> part_shift, part = item & (nparts - 1);
@@ -987,6 +1006,7 @@ k_pileup(PileupArgs a, int batch_reads) {
                         finish_chunk<kPpad>(a, un.cell, un.t0 + 32 * (cs + chl), lane, cnt, sum, covered, maxd);
                     }
                 }
+                TICK(3)
             }
             rb += nb > 0 ? nb : 1;
         }
@@ -1018,6 +1038,9 @@ k_pileup(PileupArgs a, int batch_reads) {
         }
         if (__any_sync(kFull, extent_err) && lane == 0) atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_EXTENT);
     }
+#ifdef MGATK_TIMING
+    if (lane == 0) for (int k = 0; k < 6; k++) atomicAdd(&a.dbg[k], (unsigned long long)tt[k]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
