@@ -212,7 +212,10 @@ k_scan_bases(u32 *__restrict__ part, int ngroups, int bins, int64_t *__restrict_
     for (int b0 = 0; b0 < bins; b0 += 1024) {
         const int b = b0 + t;
         u32 tot = 0;
-        if (b < bins) for (int g = 0; g < ngroups; g++) tot += part[(size_t)g * bins + b];
+        if (b < bins) {
+#pragma unroll 8
+            for (int g = 0; g < ngroups; g++) tot += part[(size_t)g * bins + b];       // independent loads, eight in flight
+        }
         u32 inc = tot;                                   // inclusive block scan of bin totals
         for (int o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
         if (lane == 31) warp_sums[wid] = inc;
@@ -225,8 +228,12 @@ k_scan_bases(u32 *__restrict__ part, int ngroups, int bins, int64_t *__restrict_
         __syncthreads();
         const u32 carry = carry_s;
         u32 run = carry + warp_sums[wid] + inc - tot;    // exclusive base of bin b
-        if (b < bins) for (int g = 0; g < ngroups; g++) {
-            u32 v = part[(size_t)g * bins + b]; part[(size_t)g * bins + b] = run; run += v;
+        if (b < bins) for (int g0 = 0; g0 < ngroups; g0 += 8) {
+            u32 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = g0 + k < ngroups ? part[(size_t)(g0 + k) * bins + b] : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (g0 + k < ngroups) { part[(size_t)(g0 + k) * bins + b] = run; run += v[k]; }
         }
         __syncthreads();
         if (t == 1023) carry_s = carry + warp_sums[31] + inc;
