@@ -28,6 +28,12 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
+def build_bamio(force: bool = False) -> str:
+    """Host-only BAM ingest library (g++, zlib): csrc/bamio.cpp -> libmgatk2_bamio.so."""
+    from .bamio import build_bamio as _b
+    return _b(force)
+
+
 def build_extension(force: bool = False, verbose: bool = False) -> str:
     if force or is_stale():
         cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB, *SOURCES]

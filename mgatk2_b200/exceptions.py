@@ -22,6 +22,18 @@ class BAMReadError(ProcessingError):
         self.bam_path = bam_path
 
 
+class BAMFormatError(BAMReadError):
+    """The file is not a readable BAM (src/core/exceptions.py: raised when pysam cannot open it)."""
+
+
+class NoChrMReadsError(BAMReadError):
+    def __init__(self, bam_path: str, available_chromosomes: list):
+        self.available_chromosomes = available_chromosomes
+        chrs = ", ".join(available_chromosomes[:10])
+        super().__init__(bam_path, "No mitochondrial chromosome (chrM, MT, or M) found.\n"
+                                   f"Available: {chrs}{'...' if len(available_chromosomes) > 10 else ''}")
+
+
 class NoBarcodeTagsError(BAMReadError):
     def __init__(self, bam_path: str, barcode_tag: str, total_reads_checked: int):
         super().__init__(bam_path, f"No reads with barcode tag '{barcode_tag}' found "

@@ -73,16 +73,31 @@ class BAMReader:
         self.barcode_list = list(barcode_list) if barcode_list is not None else sorted(barcodes)
         self.device = device
         self._batch = batch
-        if batch is None and not self.bam_path.exists():
-            raise BAMReadError(str(bam_path), "File does not exist")
+        if batch is None:
+            if not self.bam_path.exists():
+                raise BAMReadError(str(bam_path), "File does not exist")
+            self._validate_bam_file()
+
+    def _validate_bam_file(self):
+        """readers.py:35-61: the file opens as a BAM, a mitochondrial contig is in the header (config.mito_chr is
+        updated to the name found), and one of the first 1001 chrM records carries the barcode tag."""
+        from .bamio import BamFile, pick_mito_contig
+        from .exceptions import NoBarcodeTagsError, NoChrMReadsError
+        with BamFile(str(self.bam_path)) as bam:
+            mito = pick_mito_contig(bam.references)
+            if mito is None:
+                raise NoChrMReadsError(str(self.bam_path), bam.references)
+            if self.config.mito_chr != mito:
+                logger.info("Using mitochondrial chromosome: %s", mito)
+                self.config.mito_chr = mito
+            head, _, _ = bam.fetch(mito, self.config.barcode_tag, threads=1, max_records=1001)
+        if head.n_records > 1000 and not (head.bc_idx != -1).any():
+            raise NoBarcodeTagsError(str(self.bam_path), self.config.barcode_tag, 1000)
 
     def _load_batch(self) -> ReadBatch:
         if self._batch is not None:
             return self._batch
-        try:
-            from .bamio import read_bam_chrM
-        except ImportError as e:      # pysam is absent from this image; the native BGZF/BAM decoder is SURVEY §8 f-1
-            raise BAMReadError(str(self.bam_path), "no BAM decoder available: pass batch=ReadBatch(...)") from e
+        from .bamio import read_bam_chrM          # native BGZF/BAM decoder (csrc/bamio.cpp), SURVEY §8 f-1
         batch, mito_chr = read_bam_chrM(str(self.bam_path), self.config, whitelist_index(self.barcode_list))
         if mito_chr != self.config.mito_chr:            # readers.py:43-48
             logger.info("Using mitochondrial chromosome: %s", mito_chr)

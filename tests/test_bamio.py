@@ -1,0 +1,104 @@
+"""Native BAM ingest (mgatk2_b200/csrc/bamio.cpp + bamio.py) against the BAM writer: every field of the
+structure-of-arrays batch survives a BGZF BAM round trip, with pysam's fetch(contig) semantics (records of other
+contigs skipped, unmapped mates placed on chrM kept, unplaced reads at the end ignored), with and without a .bai,
+for sorted and unsorted headers, plus the validation errors of readers.py:35-61."""
+import numpy as np
+import pytest
+
+from mgatk2_b200.bamio import BamFile, read_bam_chrM, write_bam
+from mgatk2_b200.batch import ReadBatch
+from mgatk2_b200.config import PipelineConfig
+from mgatk2_b200.exceptions import BAMFormatError, BAMReadError, NoBarcodeTagsError, NoChrMReadsError
+from mgatk2_b200.synth import synth_batch
+
+FIELDS = ("pos", "tlen", "flag", "mapq", "l_seq", "n_cigar")
+
+
+def assert_same_records(a: ReadBatch, b: ReadBatch):
+    assert a.n_records == b.n_records
+    for f in FIELDS:
+        np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f)
+    def rec(x, i):
+        r = x.record(i)
+        r.pop("bc_idx")                      # the generator marks "no tag" / "not whitelisted" apart, a BAM reader cannot
+        return r
+    for i in list(range(0, a.n_records, max(1, a.n_records // 997))) + [a.n_records - 1]:   # blobs byte for byte (sampled + end)
+        assert rec(a, i) == rec(b, i), i
+    la = a.l_seq.astype(np.int64) + (a.l_seq.astype(np.int64) + 1) // 2 + 4 * a.n_cigar.astype(np.int64)
+    assert int(((la + 15) // 16 * 16).sum()) == len(b.blob)
+
+
+@pytest.mark.parametrize("profile,index,sorted_header", [("atac50", True, True), ("stress150", False, True), ("atac70", True, False)])
+def test_round_trip(tmp_path, profile, index, sorted_header):
+    n_cells = 50
+    batch = synth_batch(n_cells, 30_000, profile, seed=3)
+    barcodes = [f"BC{i:05d}-1" for i in range(n_cells)]
+    extra = [("chr1", 100), ("chr1", 5000), ("chrX", 7), (None, -1), (None, -1)]
+    path = str(tmp_path / "t.bam")
+    write_bam(path, batch, barcodes, extra=extra, write_index=index, sorted_header=sorted_header, block_bytes=20000)
+    cfg = PipelineConfig()
+    got, mito = read_bam_chrM(path, cfg, {b: i for i, b in enumerate(barcodes)}, threads=4)
+    assert mito == "chrM"
+    assert_same_records(batch, got)
+    np.testing.assert_array_equal(got.bc_idx, np.maximum(batch.bc_idx, -1))
+    with BamFile(path) as bam:
+        assert bam.references == ["chr1", "chrM", "chrX"] and bam.coordinate_sorted == sorted_header
+        few, names, _ = bam.fetch("chrM", "CB", threads=1, max_records=10)
+        assert few.n_records == 10 and all(isinstance(x, str) for x in names)
+        other, _, _ = bam.fetch("chr1")
+        assert other.n_records == 2 and other.pos.tolist() == [100, 5000]
+
+
+def test_mito_names_bulk_and_missing_tags(tmp_path):
+    batch = synth_batch(4, 3000, "atac50", seed=5)
+    barcodes = ["A-1", "B-1", "C-1", "D-1"]
+    cfg = PipelineConfig()
+    p = str(tmp_path / "mt.bam")
+    write_bam(p, batch, barcodes, ref_names=("1", "MT"), ref_lens=(1000, 16569), mito="MT")
+    got, mito = read_bam_chrM(p, cfg, {b: i for i, b in enumerate(barcodes)})
+    assert mito == "MT" and got.n_records == batch.n_records
+    bulk, _ = read_bam_chrM(p, cfg, {"bulk": 0})                       # readers.py:72,100-102
+    assert (bulk.bc_idx == 0).all()
+    # another tag name
+    cfg2 = PipelineConfig(barcode_tag="XC")
+    p2 = str(tmp_path / "xc.bam")
+    write_bam(p2, batch, barcodes, tag="XC")
+    got2, _ = read_bam_chrM(p2, cfg2, {b: i for i, b in enumerate(barcodes)})
+    np.testing.assert_array_equal(got2.bc_idx, np.maximum(batch.bc_idx, -1))
+    # no barcode tag in the first 1001 records -> refused; fewer records than that -> accepted (readers.py:54-59)
+    p3 = str(tmp_path / "notag.bam")
+    write_bam(p3, batch, barcodes, cb_strings=[None] * batch.n_records)
+    with pytest.raises(NoBarcodeTagsError):
+        read_bam_chrM(p3, cfg, {b: i for i, b in enumerate(barcodes)})
+    small = batch.take(np.arange(500))
+    p4 = str(tmp_path / "notag_small.bam")
+    write_bam(p4, small, barcodes, cb_strings=[None] * 500)
+    got4, _ = read_bam_chrM(p4, cfg, {b: i for i, b in enumerate(barcodes)})
+    assert (got4.bc_idx == -1).all()
+
+
+def test_errors(tmp_path):
+    cfg = PipelineConfig()
+    batch = synth_batch(2, 200, "atac50", seed=1)
+    p = str(tmp_path / "nochrm.bam")
+    write_bam(p, batch, ["A-1", "B-1"], ref_names=("chr1", "chr2"), ref_lens=(1000, 16569), mito="chr2")
+    with pytest.raises(NoChrMReadsError):
+        read_bam_chrM(p, cfg, {"A-1": 0})
+    junk = tmp_path / "junk.bam"
+    junk.write_bytes(b"this is not a bam file, not even close........")
+    with pytest.raises(BAMFormatError):
+        read_bam_chrM(str(junk), cfg, {"A-1": 0})
+    # truncated file: an error, never a silently short batch
+    good = str(tmp_path / "good.bam")
+    write_bam(good, synth_batch(2, 5000, "atac50", seed=2), ["A-1", "B-1"], write_index=False, block_bytes=8000)
+    data = open(good, "rb").read()
+    cut = tmp_path / "cut.bam"
+    cut.write_bytes(data[: len(data) // 2])
+    with pytest.raises(BAMReadError):
+        read_bam_chrM(str(cut), cfg, {"A-1": 0, "B-1": 1})
+    # QUAL absent (0xFF) on a record that passes the filters (readers.py:158)
+    b = ReadBatch.from_records([dict(pos=10, flag=0, mapq=60, seq="ACGT" * 5, qual=[255] * 20, cigar=[(0, 20)], bc_idx=0)])
+    q = str(tmp_path / "noqual.bam")
+    write_bam(q, b, ["A-1"])
+    with pytest.raises(BAMReadError):
+        read_bam_chrM(q, cfg, {"A-1": 0})

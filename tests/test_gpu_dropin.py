@@ -99,3 +99,23 @@ def test_pileup_generator_two_step(golden_dir):
     flt = gen.filter_strand_bias(raw)
     assert sorted(flt) == list(range(300, 310))
     assert flt[300]["tn5_cuts_fwd"] == 4 and flt[309]["tn5_cuts_rev"] == 1 and flt[300]["depth"] == 5
+
+
+def test_bam_file_through_the_seam(golden_dir, tmp_path):
+    """BAMReader on a real BGZF BAM (native ingest, csrc/bamio.cpp) gives what the in-memory batch gives, and the
+    reference's constructor-time validation (readers.py:35-61) is in place."""
+    from mgatk2_b200 import BAMReader
+    from mgatk2_b200.bamio import write_bam
+    from mgatk2_b200.exceptions import BAMReadError
+    d, batch, barcodes, params = load_golden(f"{golden_dir}/synth_run_default.npz")
+    path = str(tmp_path / "possorted_bam.bam")
+    write_bam(path, batch, barcodes, extra=[("chr1", 5), ("chrX", 9), (None, -1)])
+    cfg = make_config(params)
+    reads_a, stats_a = BAMReader(path, cfg, set(barcodes), barcode_list=barcodes).collect_reads_by_barcode()
+    reads_b, stats_b = BAMReader("in-memory.bam", make_config(params), set(barcodes), barcode_list=barcodes,
+                                 batch=batch).collect_reads_by_barcode()
+    assert stats_a == stats_b and list(reads_a) == list(reads_b)
+    np.testing.assert_array_equal(reads_a.result.planes, reads_b.result.planes)
+    np.testing.assert_array_equal(reads_a.result.cell_qc, reads_b.result.cell_qc)
+    with pytest.raises(BAMReadError):
+        BAMReader(str(tmp_path / "missing.bam"), cfg, set(barcodes))
