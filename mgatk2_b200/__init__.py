@@ -12,7 +12,7 @@ from .exceptions import (BAMReadError, InvalidInputError, MgatkError, NoBarcodeT
 __all__ = ["ReadBatch", "PipelineConfig", "QualityThresholds", "DeduplicationConfig", "PerformanceConfig",
            "MgatkError", "InvalidInputError", "ProcessingError", "BAMReadError", "NoBarcodeTagsError",
            "PileupKernelError", "BAMReader", "CellProcessor", "process_barcode_worker", "PileupGenerator",
-           "PileupEngine"]
+           "PileupEngine", "MtDNAPipeline", "run_pipeline", "load_singlecell_csv", "extract_barcodes_from_bam"]
 
 
 def __getattr__(name):        # heavy pieces (ctypes library, torch) load on first use
@@ -25,6 +25,12 @@ def __getattr__(name):        # heavy pieces (ctypes library, torch) load on fir
     if name == "PileupGenerator":
         from .pileup import PileupGenerator
         return PileupGenerator
+    if name in ("MtDNAPipeline", "run_pipeline"):
+        from . import pipeline
+        return getattr(pipeline, name)
+    if name in ("load_singlecell_csv", "extract_barcodes_from_bam"):
+        from . import barcodes
+        return getattr(barcodes, name)
     if name == "PileupEngine":
         from .engine import PileupEngine
         return PileupEngine

@@ -119,3 +119,25 @@ def test_bam_file_through_the_seam(golden_dir, tmp_path):
     np.testing.assert_array_equal(reads_a.result.cell_qc, reads_b.result.cell_qc)
     with pytest.raises(BAMReadError):
         BAMReader(str(tmp_path / "missing.bam"), cfg, set(barcodes))
+
+
+def test_pipeline_from_bam_to_text_outputs(golden_dir, tmp_path):
+    """MtDNAPipeline.run() on a BGZF BAM: the files the reference's IncrementalTextWriter wrote for the same records
+    come out byte for byte (pipeline.py:76-181)."""
+    from mgatk2_b200 import MtDNAPipeline, run_pipeline
+    from mgatk2_b200.bamio import write_bam
+    d, batch, barcodes, params = load_golden(f"{golden_dir}/synth_run_default.npz")
+    bam = str(tmp_path / "possorted_bam.bam")
+    write_bam(bam, batch, barcodes, write_index=False)
+    out = tmp_path / "run"
+    res = MtDNAPipeline(bam, barcodes, out, make_config(params)).run()
+    assert res["cells_passed_qc"] == int(d["exp_alive"].sum()) and res["cells_processed"] >= res["cells_passed_qc"]
+    for base in ("A", "C", "G", "T", "coverage"):
+        assert gzip.open(out / "output" / f"output.{base}.txt.gz").read() == d[f"txt_{base}"].tobytes(), base
+    assert (out / "output" / "output.depthTable.txt").read_bytes() == d["txt_depthTable"].tobytes()
+    assert (out / "output" / "chrM_refAllele.txt").read_bytes() == d["txt_refAllele"].tobytes()
+    assert (out / "qc" / "cell_stats.csv").read_bytes() == d["txt_cell_stats"].tobytes()
+    assert "cells_passed_qc" in (out / "qc" / "summary.txt").read_text()
+    # whitelist discovered from the BAM itself (pipeline.py:214-224): at least the cells with >= 10 countable reads
+    res2 = run_pipeline(bam, str(tmp_path / "run2"), barcode_file=None, min_barcode_reads=10)
+    assert res2["cells_passed_qc"] > 0
