@@ -19,6 +19,8 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include "../../include/mgatk2_bamio.h"
+
 #include <algorithm>
 #include <string>
 #include <thread>

@@ -27,6 +27,16 @@ def test_exports_match_header(lib):
         assert hasattr(lib, sym), sym
 
 
+def test_bamio_exports_match_header():
+    header = open(os.path.join(ROOT, "include", "mgatk2_bamio.h")).read()
+    declared = set(re.findall(r"\b(mgatk_bam_[a-z_]+)\s*\(", header))
+    from mgatk2_b200 import bamio
+    assert declared == set(bamio.EXPORTS)
+    lib = bamio.load()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
 def test_struct_sizes():
     from mgatk2_b200._lib import OutputsC, ParamsC
     from mgatk2_b200.batch import MgatkBatchC
