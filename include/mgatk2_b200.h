@@ -47,7 +47,8 @@ typedef enum mgatk_status {
     MGATK_ERR_EXTENT = 5,        /* a read exceeds params.max_read_extent           */
     MGATK_ERR_OVERFLOW_CAP = 6,  /* more >65535 entries than overflow_capacity      */
     MGATK_ERR_NO_DEVICE = 7,     /* no usable CUDA device                           */
-    MGATK_ERR_RANGE = 8          /* n_cells / n_records / blob outside limits       */
+    MGATK_ERR_RANGE = 8,         /* n_cells / n_records / blob outside limits       */
+    MGATK_ERR_STREAM_SATURATED = 9 /* a streamed plane entry passed 65535 (use one batch) */
 } mgatk_status;
 
 /* ---- dedup strategies (reference src/cli/utils.py:164-169) ---------------- */
@@ -96,6 +97,17 @@ typedef struct mgatk_params {
  * (pileup.py:100-124) before pileup.py:128-154 is applied. */
 #define MGATK_FLAG_RAW_PILEUP 1
 
+/* Streaming over several batches (BASELINE configs[4]: inputs larger than HBM). The records of a coordinate-sorted
+ * BAM are cut into batches on reference_start borders (all duplicates of a read share its start, so dedup needs no
+ * state across batches, readers.py:118-150); the planes stay resident and every batch ADDS its raw counts:
+ *     mgatk_stream_begin_device(...)                            zero planes / QC / counters
+ *     mgatk_pileup_device(..., flags | MGATK_FLAG_ACCUMULATE)   once per batch, in file order
+ *     mgatk_stream_finish_device(...)                           cell gate, strand-bias filter, coverage, Tn5 gating,
+ *                                                               depth statistics, base totals, medians
+ * The result equals the one-batch result bit for bit as long as no plane entry passes 65535 while accumulating
+ * (MGATK_ERR_STREAM_SATURATED otherwise: such inputs need the one-batch path and its overflow list). */
+#define MGATK_FLAG_ACCUMULATE 2
+
 /* ---- one batch of records, structure-of-arrays, BAM (coordinate) order ---- */
 /* One entry per record returned by fetch(chrM) (readers.py:87-93), i.e. also
  * unmapped-placed / secondary / supplementary records and records without a
@@ -138,7 +150,7 @@ typedef struct mgatk_stats {
     uint64_t dup_position_only;/* stats["duplicate_reads_position_only"]                */
     uint64_t n_empty_seq;      /* dedup survivors with l_seq==0 (reference raises)      */
     uint64_t n_overflow;       /* entries written to the overflow list                  */
-    uint64_t error_bits;       /* bit0 unsorted, bit1 extent, bit2 overflow capacity    */
+    uint64_t error_bits;       /* bit0 unsorted, bit1 extent, bit2 overflow capacity, bit3 stream saturated */
 } mgatk_stats;
 
 /* exact value of one saturated plane entry */
@@ -182,6 +194,10 @@ int mgatk_pileup_device(mgatk_handle *h, const mgatk_params *params,
                         void *workspace_dev, int64_t workspace_bytes, void *stream);
 
 int mgatk_check_stats(const mgatk_stats *stats_host);
+
+/* streaming: see MGATK_FLAG_ACCUMULATE. params->flags of the finish call selects raw / filtered output. */
+int mgatk_stream_begin_device(mgatk_handle *h, const mgatk_params *params, const mgatk_outputs *out_dev, void *stream);
+int mgatk_stream_finish_device(mgatk_handle *h, const mgatk_params *params, const mgatk_outputs *out_dev, void *stream);
 
 /* PileupGenerator.filter_strand_bias (pileup.py:128-154) on raw planes, in place:
  * planes_dev is [n_cells][MGATK_N_PLANES][MGATK_POS_PAD(P)] as written with MGATK_FLAG_RAW_PILEUP

@@ -13,12 +13,13 @@ LIB_PATH = os.path.join(HERE, "libmgatk2_b200.so")
 EXPORTS = (
     "mgatk_abi_version", "mgatk_status_string", "mgatk_create", "mgatk_destroy", "mgatk_last_error",
     "mgatk_workspace_bytes", "mgatk_pileup_device", "mgatk_check_stats", "mgatk_pileup_host",
-    "mgatk_filter_strand_bias_device",
+    "mgatk_filter_strand_bias_device", "mgatk_stream_begin_device", "mgatk_stream_finish_device",
     "mgatk_last_launch_count", "mgatk_last_stage_times",
 )
 
 N_PLANES = 11
 FLAG_RAW_PILEUP = 1
+FLAG_ACCUMULATE = 2
 ABI_VERSION = 1
 
 

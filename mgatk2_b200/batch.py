@@ -121,6 +121,23 @@ class ReadBatch:
         return c
 
     # ------------------------------------------------------------------ subsetting (barcode sharding)
+    def split_on_start_borders(self, n_parts: int) -> list:
+        """Cut a coordinate-sorted batch into about `n_parts` consecutive batches whose borders fall between different
+        reference_start values: all candidates for a duplicate of a read share its start (readers.py:118-150), so dedup
+        never needs state across such batches."""
+        n = self.n_records
+        if n == 0 or n_parts <= 1:
+            return [self]
+        cuts = [0]
+        for k in range(1, n_parts):
+            i = max(cuts[-1], n * k // n_parts)
+            while 0 < i < n and self.pos[i] == self.pos[i - 1]:
+                i += 1
+            if cuts[-1] < i < n:
+                cuts.append(i)
+        cuts.append(n)
+        return [self.take(np.arange(a, b)) for a, b in zip(cuts[:-1], cuts[1:])]
+
     def take(self, index: np.ndarray) -> "ReadBatch":
         """Records `index` (kept in the given order) with a freshly packed blob."""
         index = np.asarray(index, dtype=np.int64)

@@ -97,14 +97,19 @@ int fail(mgatk_handle *h, int code, const std::string &msg) { if (h) h->err = ms
             return fail(h, MGATK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
     } while (0)
 
-__global__ void k_init(mgatk_stats *stats, int64_t n_records, int32_t *work_counter, u32 *ticket) {
-    stats->total_reads = (uint64_t)n_records;            // readers.py:93 counts every fetched record
-    stats->stage1_reads = 0; stats->filtered_reads = 0; stats->dup_with_length = 0;
-    stats->dup_position_only = 0; stats->n_empty_seq = 0; stats->n_overflow = 0; stats->error_bits = 0;
+__global__ void k_init(mgatk_stats *stats, int64_t n_records, int32_t *work_counter, u32 *ticket, int accumulate) {
+    if (accumulate) stats->total_reads += (uint64_t)n_records;    // streamed batch: the counters keep running
+    else {
+        stats->total_reads = (uint64_t)n_records;        // readers.py:93 counts every fetched record
+        stats->stage1_reads = 0; stats->filtered_reads = 0; stats->dup_with_length = 0;
+        stats->dup_position_only = 0; stats->n_empty_seq = 0; stats->n_overflow = 0; stats->error_bits = 0;
+    }
     *work_counter = 0;
     *ticket = 0;
 }
-__global__ void k_publish_m(mgatk_stats *stats, const int64_t *m) { stats->stage1_reads = (uint64_t)*m; }
+__global__ void k_publish_m(mgatk_stats *stats, const int64_t *m, int accumulate) {
+    stats->stage1_reads = (accumulate ? stats->stage1_reads : 0) + (uint64_t)*m;
+}
 
 void mark(mgatk_handle *h, cudaStream_t s, const char *name) {
     if (h->n_stages < kMaxStages) {
@@ -213,11 +218,19 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     int64_t *n_proc = (int64_t *)(ws + L.scalars + 24);
     u64 *error_bits = (u64 *)&o->stats->error_bits;
 
-    k_init<<<1, 1, 0, s>>>(o->stats, b->n_records, work_counter, ticket);
+    const int accumulate = (p->flags & MGATK_FLAG_ACCUMULATE) ? 1 : 0;      // streamed batch: outputs keep accumulating
+    k_init<<<1, 1, 0, s>>>(o->stats, b->n_records, work_counter, ticket, accumulate);
     h->launches++;
-    CU(cudaMemsetAsync(o->base_totals, 0, sizeof(int64_t) * (size_t)P * 4, s));
-    if (C > 0) CU(cudaMemsetAsync(o->cell_qc, 0, sizeof(mgatk_cell_qc) * (size_t)C, s));
+    if (!accumulate) {
+        CU(cudaMemsetAsync(o->base_totals, 0, sizeof(int64_t) * (size_t)P * 4, s));
+        if (C > 0) CU(cudaMemsetAsync(o->cell_qc, 0, sizeof(mgatk_cell_qc) * (size_t)C, s));
+    } else if (C > 0) {
+        k_clear_parked<<<(C + 255) / 256, 256, 0, s>>>(o->cell_qc, C);
+        h->launches++;
+    }
     if (C == 0) { mark(h, s, "init"); return MGATK_OK; }
+    // a cell that is below min_reads_per_cell so far may pass it with a later batch: the gate waits for the finish pass
+    const int min_reads = accumulate ? 0 : p->min_reads_per_cell;
 
     // ---- stage 1 + partition by cell ----
     SrcUser su; su.b = *b; su.n_cells = C;
@@ -233,7 +246,7 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
         if (rc) return rc;
         g = g1;
     }
-    k_publish_m<<<1, 1, 0, s>>>(o->stats, m_ptr);
+    k_publish_m<<<1, 1, 0, s>>>(o->stats, m_ptr, accumulate);
     h->launches += 1;
     mark(h, s, "filter+partition");
 
@@ -249,9 +262,9 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     // ---- units ----
     int32_t *unit_start = (int32_t *)(ws + L.unit_start);
     Unit *units = (Unit *)(ws + L.units);
-    k_plan_scan<<<1, 1024, 0, s>>>(o->cell_qc, C, p->min_reads_per_cell, L.unit_reads, ppad, cell_start, unit_start, n_units);
+    k_plan_scan<<<1, 1024, 0, s>>>(o->cell_qc, C, min_reads, L.unit_reads, ppad, cell_start, unit_start, n_units);
     k_plan_units<<<(unsigned)((L.max_units + 255) / 256), 256, 0, s>>>(cell_start, o->cell_qc, recs, unit_start, C,
-                                                                      p->min_reads_per_cell, L.unit_reads, ppad,
+                                                                      min_reads, L.unit_reads, ppad,
                                                                       p->max_read_extent, units);
     h->launches += 2;
     mark(h, s, "plan");
@@ -265,6 +278,7 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     a.max_bias = p->max_strand_bias;
     a.raw = (p->flags & MGATK_FLAG_RAW_PILEUP) ? 1 : 0;
     a.apply_bias = !a.raw && !(p->max_strand_bias >= 1.0);   // max(f,r)/total never exceeds 1.0
+    a.accumulate = accumulate;
     a.extent = p->max_read_extent;
     a.mask_stride = mask_stride_for(p->max_read_extent);
     a.cap_reads = cap_reads_for(p->max_read_extent);
@@ -281,6 +295,7 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
 #endif
     if (rc) return rc;
     mark(h, s, "pileup");
+    if (accumulate) return MGATK_OK;                     // filters, coverage, statistics: mgatk_stream_finish_device
 
     // ---- reference-allele totals, median depth ----
     dim3 tg((ppad / 2 + 127) / 128, (C + kTotalsCellGroup - 1) / kTotalsCellGroup);
@@ -324,6 +339,7 @@ const char *mgatk_status_string(int status) {
         case MGATK_ERR_OVERFLOW_CAP: return "overflow list capacity exceeded";
         case MGATK_ERR_NO_DEVICE: return "no usable CUDA device";
         case MGATK_ERR_RANGE: return "size outside supported range";
+        case MGATK_ERR_STREAM_SATURATED: return "a streamed plane entry passed 65535 (use one batch)";
         default: return "unknown status";
     }
 }
@@ -383,11 +399,59 @@ int mgatk_filter_strand_bias_device(mgatk_handle *h, uint16_t *planes_dev, int32
     return MGATK_OK;
 }
 
+int mgatk_stream_begin_device(mgatk_handle *h, const mgatk_params *p, const mgatk_outputs *o, void *stream) {
+    if (!h) return MGATK_ERR_BAD_ARG;
+    h->err.clear();
+    if (!p || !o || !o->stats || !o->base_totals || p->n_cells < 0 || p->mito_length <= 0 || (p->n_cells > 0 && (!o->planes || !o->cell_qc)))
+        return fail(h, MGATK_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t C = (size_t)p->n_cells, P = (size_t)p->mito_length, ppad = (size_t)MGATK_POS_PAD(P);
+    if (C) CU(cudaMemsetAsync(o->planes, 0, C * MGATK_N_PLANES * ppad * 2, s));
+    if (C) CU(cudaMemsetAsync(o->cell_qc, 0, C * sizeof(mgatk_cell_qc), s));
+    CU(cudaMemsetAsync(o->stats, 0, sizeof(mgatk_stats), s));
+    CU(cudaMemsetAsync(o->base_totals, 0, P * 4 * sizeof(int64_t), s));
+    return MGATK_OK;
+}
+
+int mgatk_stream_finish_device(mgatk_handle *h, const mgatk_params *p, const mgatk_outputs *o, void *stream) {
+    if (!h) return MGATK_ERR_BAD_ARG;
+    h->err.clear();
+    if (!p || !o || !o->stats || !o->base_totals || p->n_cells < 0 || p->mito_length <= 0 || (p->n_cells > 0 && (!o->planes || !o->cell_qc)))
+        return fail(h, MGATK_ERR_BAD_ARG, "bad argument");
+    if (o->overflow_capacity > 0 && !o->overflow) return fail(h, MGATK_ERR_BAD_ARG, "null overflow list");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int C = p->n_cells, P = p->mito_length, ppad = (int)MGATK_POS_PAD(P);
+    h->launches = 0;
+    if (C == 0) return MGATK_OK;
+    PileupArgs a;
+    memset(&a, 0, sizeof(a));
+    a.planes = o->planes; a.qc = o->cell_qc; a.stats = o->stats; a.ovf = o->overflow; a.ovf_cap = o->overflow_capacity;
+    a.P = P; a.ppad = ppad; a.max_bias = p->max_strand_bias;
+    a.raw = (p->flags & MGATK_FLAG_RAW_PILEUP) ? 1 : 0;
+    a.apply_bias = !a.raw && !(p->max_strand_bias >= 1.0);
+    k_clear_parked<<<(C + 255) / 256, 256, 0, s>>>(o->cell_qc, C);
+    k_stream_finish<<<h->sm_count * 8, 256, 0, s>>>(a, C, p->min_reads_per_cell);
+    dim3 tg((ppad / 2 + 127) / 128, (C + kTotalsCellGroup - 1) / kTotalsCellGroup);
+    k_base_totals<<<tg, 128, 0, s>>>(o->planes, C, P, ppad, (u64 *)o->base_totals);
+    h->launches += 3;
+    if (o->overflow_capacity > 0) {
+        k_base_totals_overflow<<<8, 256, 0, s>>>(o->overflow, o->stats, o->overflow_capacity, P, (u64 *)o->base_totals);
+        h->launches++;
+    }
+    k_median<<<C, 256, 0, s>>>(o->planes, P, ppad, o->cell_qc);
+    h->launches++;
+    CU(cudaGetLastError());
+    return MGATK_OK;
+}
+
 int mgatk_check_stats(const mgatk_stats *st) {
     if (!st) return MGATK_ERR_BAD_ARG;
     if (st->error_bits & ERR_UNSORTED) return MGATK_ERR_UNSORTED;
     if (st->error_bits & ERR_EXTENT) return MGATK_ERR_EXTENT;
     if (st->error_bits & ERR_OVERFLOW_CAP) return MGATK_ERR_OVERFLOW_CAP;
+    if (st->error_bits & ERR_SATURATED) return MGATK_ERR_STREAM_SATURATED;
     return MGATK_OK;
 }
 

@@ -30,7 +30,7 @@ constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kScanGroup = 16;        // chunks per scan group
 constexpr u32 kFull = 0xffffffffu;
 
-constexpr u32 ERR_UNSORTED = 1, ERR_EXTENT = 2, ERR_OVERFLOW_CAP = 4;
+constexpr u32 ERR_UNSORTED = 1, ERR_EXTENT = 2, ERR_OVERFLOW_CAP = 4, ERR_SATURATED = 8;
 
 // ReadRec.flags bits written by k_dedup, read by k_pileup
 constexpr int GF_PROCESS = 1, GF_STRAND = 2, GF_KEEP = 4, GF_CELL_SHIFT = 8;   // cell index in bits 8..31
@@ -624,6 +624,7 @@ struct PileupArgs {
     uint16_t *planes; mgatk_cell_qc *qc; mgatk_stats *stats;
     mgatk_overflow *ovf; int64_t ovf_cap;
     int P, ppad, min_baseq, dist, apply_bias, extent, raw;
+    int accumulate;                  // streaming: add the counts of this batch to the planes, nothing else (MGATK_FLAG_ACCUMULATE)
 #ifdef MGATK_TIMING
     unsigned long long *dbg;          // -DMGATK_TIMING: warp-cycles per phase (profiling build only, see profiles/README.md)
 #endif
@@ -896,6 +897,20 @@ __device__ __forceinline__ void finish_chunk(const PileupArgs &a, int cell, int 
 #pragma unroll
         for (int k = 0; k < 10; k++) cnt[k] = 0;
     }
+    if (a.accumulate) {                              // streamed batches: raw counts add up in the planes; filters, coverage
+        uint16_t *acc = a.planes + (size_t)cell * MGATK_N_PLANES * ppad + p;      // and statistics come in k_stream_finish
+        bool sat = false;
+#pragma unroll
+        for (int pl = 0; pl < 10; pl++) {
+            if (cnt[pl]) {
+                u32 v = (u32)acc[(size_t)pl * ppad] + cnt[pl];
+                if (v > 65535u) { v = 65535u; sat = true; }
+                acc[(size_t)pl * ppad] = (uint16_t)v;
+            }
+        }
+        if (sat) atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_SATURATED);
+        return;
+    }
     if (a.apply_bias) {
 #pragma unroll
         for (int b = 0; b < 4; b++) {
@@ -1109,6 +1124,44 @@ k_filter_planes(uint16_t *__restrict__ planes, int n_cells, int P, int ppad, dou
     }
     row[(size_t)MGATK_PLANE_COVERAGE * ppad] = (uint16_t)min(cov, 65535u);
     if (cov == 0) { row[(size_t)MGATK_PLANE_TN5_FWD * ppad] = 0; row[(size_t)MGATK_PLANE_TN5_REV * ppad] = 0; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming (batches cut on reference_start borders, planes resident and accumulating): the per-batch kernels only add
+// raw counts; this pass turns the accumulated planes into the final ones exactly as a one-batch run would have written
+// them: cell gate (processors.py:22), strand-bias filter, coverage, Tn5 gating (pileup.py:128-154), depth statistics.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_stream_finish(PileupArgs a, int n_cells, int min_reads) {
+    const int lane = lane_id();
+    const int warps = (int)((gridDim.x * (size_t)blockDim.x) >> 5), gw = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int chunks = a.ppad >> 5;
+    for (long long w = gw; w < (long long)n_cells * chunks; w += warps) {
+        const int cell = (int)(w / chunks), ch = (int)(w - (long long)cell * chunks);
+        const bool dead = cell_dead(a.qc[cell], min_reads);
+        const uint16_t *in = a.planes + (size_t)cell * MGATK_N_PLANES * a.ppad + 32 * ch + lane;
+        u32 cnt[10];
+#pragma unroll
+        for (int k = 0; k < 10; k++) cnt[k] = dead ? 0u : (u32)in[(size_t)k * a.ppad];
+        u64 sum = 0; u32 covered = 0, maxd = 0;
+        finish_chunk<0>(a, cell, 32 * ch, lane, cnt, sum, covered, maxd);
+        if (__any_sync(kFull, covered != 0)) {
+            u64 tot = sum;
+            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(kFull, tot, o);
+            const u32 cv = __reduce_add_sync(kFull, covered), mx = __reduce_max_sync(kFull, maxd);
+            if (lane == 0) {
+                atomicAdd((u64 *)&a.qc[cell].sum_depth, tot);
+                atomicAdd(&a.qc[cell].covered, cv);
+                atomicMax(&a.qc[cell].max_depth, mx);
+            }
+        }
+    }
+}
+
+// k_dedup parks the per-cell count of reads to pile up in median_lo: cleared before every streamed batch
+__global__ void k_clear_parked(mgatk_cell_qc *__restrict__ qc, int n_cells) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_cells) qc[c].median_lo = 0;
 }
 
 // ---------------------------------------------------------------------------------------------

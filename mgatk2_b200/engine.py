@@ -190,6 +190,41 @@ class PileupEngine:
         if rc:
             self._raise(rc)
 
+    # ------------------------------------------------------------------ streaming (inputs larger than HBM)
+    def _outputs_c(self, dout: "DeviceOutputs") -> OutputsC:
+        return OutputsC(dout.planes.data_ptr(), dout.cell_qc.data_ptr(), dout.stats.data_ptr(), dout.base_totals.data_ptr(),
+                        dout.overflow.data_ptr() if dout.overflow_capacity else None, dout.overflow_capacity)
+
+    def run_stream(self, batches, params: ParamsC, dout: "DeviceOutputs") -> PileupResult:
+        """Batches cut on reference_start borders (`ReadBatch.split_on_start_borders`), in file order: every batch adds its
+        raw counts to the resident planes (MGATK_FLAG_ACCUMULATE), the finish pass applies the cell gate, the strand-bias
+        filter, coverage / Tn5 gating and the depth statistics. Equals the one-batch result while no entry passes 65535."""
+        import torch
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        oc = self._outputs_c(dout)
+        rc = self.lib.mgatk_stream_begin_device(self.handle, ctypes.byref(params), ctypes.byref(oc), stream)
+        if rc:
+            self._raise(rc)
+        acc = ParamsC.from_buffer_copy(params)
+        acc.flags = int(params.flags) | _lib.FLAG_ACCUMULATE
+        launches = 0
+        for batch in batches:
+            acc.max_read_extent = max(int(batch.max_read_extent()), 1)
+            db = self.upload(batch)
+            need = int(self.lib.mgatk_workspace_bytes(int(batch.n_records), int(params.n_cells)))
+            if need > dout.workspace.numel():
+                raise PileupKernelError(3, "workspace smaller than the largest streamed batch needs")
+            self.run_device(db, acc, dout)
+            launches += self.launch_count()
+            torch.cuda.synchronize(self.device)          # the batch's device buffers are released before the next upload
+        rc = self.lib.mgatk_stream_finish_device(self.handle, ctypes.byref(params), ctypes.byref(oc), stream)
+        if rc:
+            self._raise(rc)
+        launches += self.launch_count()
+        res = self.download(dout, params)
+        res.launches = launches
+        return res
+
     def download(self, dout: "DeviceOutputs", params: ParamsC) -> PileupResult:
         """Synchronise and bring a device result back as a PileupResult (checks the device error bits)."""
         import torch

@@ -210,3 +210,36 @@ def test_staging_paths(engine):
     assert_result_equals_oracle(res, ora)
     res, ora = run_both(engine, ReadBatch.from_records(recs), 3)                 # with the 2100 bp reads: per-base path
     assert_result_equals_oracle(res, ora)
+
+
+@pytest.mark.parametrize("profile,kw", [("atac50", dict()), ("stress150", dict(max_strand_bias=0.8, min_distance_from_end=10, min_reads_per_cell=300)),
+                                        ("atac70", dict(dedup_mode=1, flags=1))])
+def test_streamed_batches_equal_one_batch(engine, profile, kw):
+    """BASELINE configs[4] streams its input: batches cut on reference_start borders accumulate into resident planes and
+    the finish pass gives, bit for bit, what one batch gives (cell gate included: a cell below min_reads_per_cell in every
+    single batch can still pass it in total)."""
+    from mgatk2_b200.exceptions import PileupKernelError
+    from oracle.oracle import run_oracle
+    n_cells = 120
+    batch = synth_batch(n_cells, 150_000, profile, seed=77)
+    p = make_params(batch, n_cells, **kw)
+    ora = run_oracle(batch, p, n_threads=8)
+    lp = to_lib_params(p)
+    parts = batch.split_on_start_borders(5)
+    assert len(parts) >= 4 and sum(b.n_records for b in parts) == batch.n_records
+    for a, b in zip(parts[:-1], parts[1:]):
+        assert a.pos[-1] < b.pos[0]
+    dout = engine.alloc_device_outputs(n_cells, lp.mito_length, max(b.n_records for b in parts), overflow_capacity=1 << 16)
+    res = engine.run_stream(parts, lp, dout)
+    assert_result_equals_oracle(res, ora)
+    # one position piled beyond 65535 cannot be streamed exactly: refused, not silently saturated
+    n = 70_000
+    one = ReadBatch.from_records([dict(pos=5000, flag=0, mapq=60, seq="ACGTACGTAC" * 2, cigar=[(0, 20)], tlen=0, bc_idx=0)])
+    deep = ReadBatch(pos=np.full(n, 5000, np.int32), tlen=np.arange(n, dtype=np.int32), flag=np.zeros(n, np.uint16),
+                     mapq=np.full(n, 60, np.uint8), bc_idx=np.zeros(n, np.int32), l_seq=np.full(n, 20, np.uint16),
+                     n_cigar=np.ones(n, np.uint16), blob_off=np.zeros(n, np.uint32), blob=one.blob)
+    lp2 = to_lib_params(make_params(deep, 1))
+    dout2 = engine.alloc_device_outputs(1, lp2.mito_length, n)
+    with pytest.raises(PileupKernelError) as e:
+        engine.run_stream([deep], lp2, dout2)
+    assert e.value.status == 9
