@@ -26,7 +26,7 @@ struct Layout {          // carve-up of the caller's workspace
     int passes, bits[2], shift[2];
     int unit_reads; int64_t max_units;
     size_t grp[2];           // grouped records (two generations for a two-digit partition)
-    size_t recs, mat, part, cell_start, unit_start, units, scan_state, scalars, total;
+    size_t recs, mat, part, cell_start, unit_start, units, units_overflow, scan_state, scalars, total;
     int64_t dedup_blocks;
 };
 
@@ -58,6 +58,7 @@ bool make_layout(int64_t n, int32_t n_cells, Layout &L) {
     L.cell_start = o; o += align_up(((size_t)n_cells + 1) * 4);
     L.unit_start = o; o += align_up(((size_t)n_cells + 1) * 4);
     L.units = o; o += align_up((size_t)L.max_units * sizeof(Unit));
+    L.units_overflow = o; o += align_up((size_t)L.max_units * sizeof(Unit));
     L.dedup_blocks = (n + kDedupTile - 1) / kDedupTile + 1;
     L.scan_state = o; o += align_up((size_t)L.dedup_blocks * 8);
     L.scalars = o; o += 256;
@@ -98,6 +99,7 @@ int fail(mgatk_handle *h, int code, const std::string &msg) { if (h) h->err = ms
     } while (0)
 
 __global__ void k_init(mgatk_stats *stats, int64_t n_records, int32_t *work_counter, u32 *ticket, int accumulate) {
+    work_counter[4] = 0; work_counter[5] = 0;            // overflow list: length, work counter (scalars + 32, + 36)
     if (accumulate) stats->total_reads += (uint64_t)n_records;    // streamed batch: the counters keep running
     else {
         stats->total_reads = (uint64_t)n_records;        // readers.py:93 counts every fetched record
@@ -140,20 +142,24 @@ int partition_pass(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout
 constexpr int kChrMPpad = (int)MGATK_POS_PAD(16569);    // the plane pitch of chrM is compiled in
 
 template <int kPpad>
-int launch_pileup_t(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, int batch_reads) {
+int launch_pileup_t(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, const PileupArgs &a_overflow, int batch_reads) {
     const size_t smem = pileup_smem_bytes();
-    CU(cudaFuncSetAttribute(k_pileup<kPpad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_pileup<kPpad, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_pileup<kPpad, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup<kPpad>, kThreads, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup<kPpad, false>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    k_pileup<kPpad><<<h->sm_count * per_sm, kThreads, smem, s>>>(a, batch_reads);    // persistent CTAs pulling units
-    h->launches += 1;
+    k_pileup<kPpad, false><<<h->sm_count * per_sm, kThreads, smem, s>>>(a, batch_reads);    // persistent CTAs pulling units
+    // tiles with more reads than mask slots (hot spots), walked in sub-tiles; usually an empty list
+    k_pileup<kPpad, true><<<h->sm_count * per_sm, kThreads, smem, s>>>(a_overflow, batch_reads);
+    h->launches += 2;
     CU(cudaGetLastError());
     return MGATK_OK;
 }
 
-int launch_pileup(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, int batch_reads) {
-    return a.ppad == kChrMPpad ? launch_pileup_t<kChrMPpad>(h, s, a, batch_reads) : launch_pileup_t<0>(h, s, a, batch_reads);
+int launch_pileup(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, const PileupArgs &a_overflow, int batch_reads) {
+    return a.ppad == kChrMPpad ? launch_pileup_t<kChrMPpad>(h, s, a, a_overflow, batch_reads)
+                               : launch_pileup_t<0>(h, s, a, a_overflow, batch_reads);
 }
 
 // mask slot of one read and the number of slots a CTA holds, from the declared extent (l_seq <= extent)
@@ -265,7 +271,9 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     k_plan_scan<<<1, 1024, 0, s>>>(o->cell_qc, C, min_reads, L.unit_reads, ppad, cell_start, unit_start, n_units);
     k_plan_units<<<(unsigned)((L.max_units + 255) / 256), 256, 0, s>>>(cell_start, o->cell_qc, recs, unit_start, C,
                                                                       min_reads, L.unit_reads, ppad,
-                                                                      p->max_read_extent, units);
+                                                                      p->max_read_extent, units,
+                                                                      cap_reads_for(p->max_read_extent) < 32 ? 32 : cap_reads_for(p->max_read_extent),
+                                                                      (Unit *)(ws + L.units_overflow), work_counter + 4);
     h->launches += 2;
     mark(h, s, "plan");
 
@@ -286,7 +294,9 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     a.dbg = (unsigned long long *)(ws + L.scalars + 64);
     cudaMemsetAsync(a.dbg, 0, 64, s);
 #endif
-    rc = launch_pileup(h, s, a, a.cap_reads < 32 ? 32 : a.cap_reads);
+    PileupArgs a2 = a;
+    a2.units = (Unit *)(ws + L.units_overflow); a2.n_units = work_counter + 4; a2.work_counter = work_counter + 5;
+    rc = launch_pileup(h, s, a, a2, a.cap_reads < 32 ? 32 : a.cap_reads);
 #ifdef MGATK_TIMING                                       // profiling build: share of warp-cycles per phase of k_pileup
     { unsigned long long hd[6]; cudaStreamSynchronize(s); cudaMemcpy(hd, a.dbg, 48, cudaMemcpyDeviceToHost);
       double tot = 0; for (int k = 0; k < 6; k++) tot += (double)hd[k];

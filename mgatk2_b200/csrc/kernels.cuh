@@ -29,6 +29,7 @@ constexpr int kWarpsPerCta = MGATK_PILEUP_WARPS;       // k_pileup: warps per CT
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kScanGroup = 16;        // chunks per scan group
 constexpr u32 kFull = 0xffffffffu;
+constexpr int kSplitChunks = 4;       // k_pileup "deep" units: at most this many chunks of 32 positions; their reads come in batches
 
 constexpr u32 ERR_UNSORTED = 1, ERR_EXTENT = 2, ERR_OVERFLOW_CAP = 4, ERR_SATURATED = 8;
 
@@ -566,7 +567,8 @@ k_plan_scan(const mgatk_cell_qc *__restrict__ qc, int n_cells, int min_reads,
 
 __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk_cell_qc *__restrict__ qc,
                              const ReadRec *__restrict__ recs, const int32_t *__restrict__ unit_start, int n_cells,
-                             int min_reads, int unit_reads, int ppad, int halo, Unit *__restrict__ units) {
+                             int min_reads, int unit_reads, int ppad, int halo, Unit *__restrict__ units,
+                             int cap_reads, Unit *__restrict__ units_overflow, int32_t *__restrict__ n_overflow_units) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= unit_start[n_cells]) return;
     int lo = 0, hi = n_cells;                              // last cell with unit_start[c] <= u
@@ -592,6 +594,12 @@ __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk
         b = ce;
         while (a < b) { int mid = (a + b) >> 1; if (recs[mid].pos < un.t1) a = mid + 1; else b = mid; }
         un.rend = a;
+    }
+    // tiles with clearly more reads than a CTA has mask slots go to the overflow list (walked in sub-tiles by the kSplit
+    // kernel); a few reads beyond the slots are cheaper on the per-base path than a second pass over the halo
+    if (un.rend - un.rbeg > cap_reads + (cap_reads >> 3) && un.t1 - un.t0 > 32 * kSplitChunks) {
+        units_overflow[atomicAdd(n_overflow_units, 1)] = un;
+        un.t1 = un.t0;                                      // empty here
     }
     units[u] = un;
 }
@@ -655,7 +663,6 @@ constexpr int kMaskBytes = 32 * kStageReads;         // query masks of a batch (
 constexpr int kWarpBuf = 2560;       // per-warp blob staging buffer: 32 blobs of a 50 bp read
 constexpr int kWarpBufSlack = 64;    // phase A may load this far past the last staged byte
 constexpr int kMaxItems = 256;       // 32 reads x 8 groups of 32 bases per staging pass
-constexpr int kSplitChunks = 4;      // "deep" units: at most this many chunks; their reads come in batches
 constexpr int kChunkSeg = 576;       // chunks per pass over a unit (the 518 chunks of chrM in one)
 constexpr int kAccWords = 10 * 32;   // deep units: counts of one chunk, [8 base x strand + 2 Tn5][32]
 
@@ -947,10 +954,25 @@ __device__ __forceinline__ void finish_chunk(const PileupArgs &a, int cell, int 
     for (int pl = 0; pl < MGATK_N_PLANES; pl++) out[(size_t)pl * ppad] = (uint16_t)vals[pl];
 }
 
-template <int kPpad>
+// Number of records among g[0..n) (sorted by start) whose start is below `key`: every thread of the CTA counts a
+// strided share, one shared-memory counter collects the warp sums.
+__device__ __forceinline__ int block_count_below(const ReadRec *g, int n, int key, int *s_count) {
+    if (threadIdx.x == 0) *s_count = 0;
+    __syncthreads();
+    int c = 0;
+    for (int i = threadIdx.x; i < n; i += kThreads) c += g[i].pos < key;
+    c = __reduce_add_sync(kFull, c);
+    if (lane_id() == 0 && c) atomicAdd(s_count, c);
+    __syncthreads();
+    const int total = *s_count;
+    __syncthreads();                                         // everybody has read it before the counter is reused
+    return total;
+}
+
+template <int kPpad, bool kSplit>
 __global__ void __launch_bounds__(kThreads, 32 / kWarpsPerCta)
 k_pileup(PileupArgs a, int batch_reads) {
-    __shared__ int s_unit;
+    __shared__ int s_unit, s_count;
     __shared__ u32 s_acc[kSplitChunks * kAccWords];          // deep units: counts of every chunk, summed over warps and batches
     __shared__ int s_first[kChunkSeg];                       // per chunk of the segment: first read of the batch that can reach it
     __shared__ uint8_t s_items[kWarpsPerCta][kMaxItems];     // phase A: (lane << 3 | group) work items of a warp's staging pass
@@ -985,9 +1007,31 @@ k_pileup(PileupArgs a, int batch_reads) {
         if (u >= n_units) break;
         TICK(0)
         if (threadIdx.x == 0) next_unit = atomicAdd(a.work_counter, 1);   // in flight while this unit is processed
-        const Unit un = a.units[u];
+        const Unit un0 = a.units[u];
+        if (un0.t1 - un0.t0 < 32) continue;                  // empty tile (its reads belong to the tile before)
+        // A tile whose reads do not fit the mask slots (a hot spot inside a wide tile) is walked in sub-tiles, each cut
+        // where the slots are full; a sub-tile that cannot be cut any narrower is a deep unit and takes its reads in batches.
+        // (k_plan_units sends such tiles to a list of their own, processed by the kSplit instance of this kernel, so the
+        // common instance does not carry the registers of the walk)
+        const bool split = kSplit && un0.rend - un0.rbeg > a.cap_reads && un0.t1 - un0.t0 > 32 * kSplitChunks;
+        int sub_t0 = un0.t0, sub_r = un0.rbeg;
+      for (;;) {
+        Unit un = un0;
+        if (split) {
+            if (sub_t0 >= un0.t1) break;
+            if (sub_t0 > un0.t0) {
+                __syncthreads();                             // the previous sub-tile is consumed
+                sub_r += block_count_below(a.recs + sub_r, un0.rend - sub_r, sub_t0 - a.extent + 1, &s_count);
+            }
+            un.t0 = sub_t0; un.rbeg = sub_r;
+            if (un0.rend - sub_r > a.cap_reads) {
+                const int cut = min(max(a.recs[sub_r + a.cap_reads].pos, 0), un0.t1) & ~31;     // first read that finds no slot
+                un.t1 = cut > sub_t0 ? cut : min(sub_t0 + 32 * kSplitChunks, un0.t1);
+                un.rend = sub_r + block_count_below(a.recs + sub_r, un0.rend - sub_r, un.t1, &s_count);
+            }
+            sub_t0 = un.t1;
+        }
         const int n_chunks = (un.t1 - un.t0) >> 5;
-        if (n_chunks <= 0) continue;                         // empty tile (its reads belong to the tile before)
         const int n_reads = un.rend - un.rbeg;
         // deep unit (few chunks): the reads come in batches and every chunk's candidates are split over `nparts`
         // warps; partial counts meet in s_acc and are finished after the last batch
@@ -1020,7 +1064,7 @@ k_pileup(PileupArgs a, int batch_reads) {
                 for (int item = wid; item < nseg * nparts; item += kWarpsPerCta) {
                     const int chl = item >> part_shift, part = item & (nparts - 1);
                     u32 cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // 8 base x strand counters, Tn5 fwd / rev; lane = position
-                    count_chunk(a, un, g_rec, s_rec, mask_addr, s_first[chl], rb == 0, nb, ns, cs + chl, part, nparts, lane, q_lo, tc, cnt, extent_err);
+                    count_chunk(a, un, g_rec, s_rec, mask_addr, s_first[chl], rb == 0 && un.t0 == un0.t0, nb, ns, cs + chl, part, nparts, lane, q_lo, tc, cnt, extent_err);
                     if (deep) {
 #pragma unroll
                         for (int k = 0; k < 10; k++) if (cnt[k]) atomicAdd(&s_acc[chl * kAccWords + k * 32 + lane], cnt[k]);
@@ -1059,6 +1103,8 @@ k_pileup(PileupArgs a, int batch_reads) {
             }
         }
         if (__any_sync(kFull, extent_err) && lane == 0) atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_EXTENT);
+        if (!split) break;
+      }
     }
 #ifdef MGATK_TIMING
     if (lane == 0) for (int k = 0; k < 6; k++) atomicAdd(&a.dbg[k], (unsigned long long)tt[k]);
