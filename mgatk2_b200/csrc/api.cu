@@ -169,6 +169,13 @@ int cap_reads_for(int extent) {
     return k > kStageReads ? kStageReads : k;
 }
 
+// reads beyond the mask slots that a tile may carry before it goes to the overflow list (they take the per-base path)
+int overflow_slack_for(int extent) {
+    const char *e = getenv("MGATK_OVERFLOW_SLACK");
+    if (e) return atoi(e);
+    return cap_reads_for(extent) >> 5;
+}
+
 // reads per unit: leave room for the reads of the halo and of the chunk the tile border is rounded down to
 int unit_reads_for(int extent) {
     const char *e = getenv("MGATK_UNIT_READS");
@@ -273,6 +280,7 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
                                                                       min_reads, L.unit_reads, ppad,
                                                                       p->max_read_extent, units,
                                                                       cap_reads_for(p->max_read_extent) < 32 ? 32 : cap_reads_for(p->max_read_extent),
+                                                                      overflow_slack_for(p->max_read_extent),
                                                                       (Unit *)(ws + L.units_overflow), work_counter + 4);
     h->launches += 2;
     mark(h, s, "plan");
@@ -290,6 +298,11 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     a.extent = p->max_read_extent;
     a.mask_stride = mask_stride_for(p->max_read_extent);
     a.cap_reads = cap_reads_for(p->max_read_extent);
+    {   // reads per staging group: what one pass through the 2.5 KB warp buffer holds at the batch's average blob size
+        const int64_t avg = b->n_records > 0 ? (b->blob_bytes / b->n_records + 15) / 16 * 16 : 80;
+        const int64_t g = kWarpBuf / (avg > 16 ? avg : 16);
+        a.group_reads = (int)(g >= 32 ? 32 : g < 4 ? 4 : g);
+    }
 #ifdef MGATK_TIMING
     a.dbg = (unsigned long long *)(ws + L.scalars + 64);
     cudaMemsetAsync(a.dbg, 0, 64, s);

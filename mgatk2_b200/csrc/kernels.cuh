@@ -568,7 +568,7 @@ k_plan_scan(const mgatk_cell_qc *__restrict__ qc, int n_cells, int min_reads,
 __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk_cell_qc *__restrict__ qc,
                              const ReadRec *__restrict__ recs, const int32_t *__restrict__ unit_start, int n_cells,
                              int min_reads, int unit_reads, int ppad, int halo, Unit *__restrict__ units,
-                             int cap_reads, Unit *__restrict__ units_overflow, int32_t *__restrict__ n_overflow_units) {
+                             int cap_reads, int overflow_slack, Unit *__restrict__ units_overflow, int32_t *__restrict__ n_overflow_units) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= unit_start[n_cells]) return;
     int lo = 0, hi = n_cells;                              // last cell with unit_start[c] <= u
@@ -596,8 +596,8 @@ __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk
         un.rend = a;
     }
     // tiles with clearly more reads than a CTA has mask slots go to the overflow list (walked in sub-tiles by the kSplit
-    // kernel); a few reads beyond the slots are cheaper on the per-base path than a second pass over the halo
-    if (un.rend - un.rbeg > cap_reads + (cap_reads >> 3) && un.t1 - un.t0 > 32 * kSplitChunks) {
+    // kernel); a handful of reads beyond the slots is cheaper on the per-base path than a second pass over the halo
+    if (un.rend - un.rbeg > cap_reads + overflow_slack && un.t1 - un.t0 > 32 * kSplitChunks) {
         units_overflow[atomicAdd(n_overflow_units, 1)] = un;
         un.t1 = un.t0;                                      // empty here
     }
@@ -638,6 +638,7 @@ struct PileupArgs {
 #endif
     int mask_stride;                 // bytes of one read's mask slot: 16 * ceil(extent / 32)
     int cap_reads;                   // mask slots per CTA (<= kStageReads)
+    int group_reads;                 // reads a warp stages at a time: 32, fewer when 32 average blobs exceed the warp buffer
     double max_bias;
 };
 
@@ -722,9 +723,12 @@ __device__ __forceinline__ bool span_exceeds(const u32 *cig, int ncig, int L, in
 // the warp's staging buffer, query masks into slot j, first-candidate table entries. ns = reads with a slot.
 __device__ __forceinline__ void stage_reads(const PileupArgs &a, const ReadRec *g_rec, int nb, int ns, int j0, int lane,
                                             ReadRec *s_rec, u32 mask_addr, u32 wbuf_addr, uint8_t *s_items, int *s_first, int seg0, int nseg,
-                                            int q_lo, QualGe qg, bool &extent_err) {
+                                            int q_lo, QualGe qg, bool &extent_err, int gs) {
     const SharedMem smem;
-    const int j = j0 + lane;
+    // a group holds `gs` <= 32 reads: as many as fit the staging buffer in one pass, so that long reads spread over all
+    // warps of the CTA instead of queueing for the buffer of one
+    const bool mine = lane < gs;
+    const int j = mine ? j0 + lane : 0x3fffffff;
     ReadRec rr; rr.pos = 0; rr.off = 0; rr.len = 0; rr.flags = 0;
     if (j < ns) rr = g_rec[j];
     const int L = rr.len & 0xffff, ncig = rr.len >> 16;
@@ -766,7 +770,7 @@ __device__ __forceinline__ void stage_reads(const PileupArgs &a, const ReadRec *
         for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, gincl, o); if (lane >= o) gincl += v; }
         const int n_items = (int)__shfl_sync(kFull, gincl, 31);
         // (when every read of the warp fits one pass - 32 reads of 50 bp - one read per lane is already dense)
-        if (__any_sync(kFull, todo && !now) && !__any_sync(kFull, now && nq > 8)) {   // n_items <= kMaxItems, three bits hold the group
+        if ((gs < 32 || __any_sync(kFull, todo && !now)) && !__any_sync(kFull, now && nq > 8)) {   // n_items <= kMaxItems, three bits hold the group
             for (u32 g = 0; g < ng; g++) s_items[gincl - ng + g] = (uint8_t)((lane << 3) | (int)g);
             __syncwarp();
             const u32 seq_a = sb + 4 * ncig;
@@ -1051,9 +1055,9 @@ k_pileup(PileupArgs a, int batch_reads) {
                 // ---- phase A (the first pass also builds the masks) ----
                 TICK(4)
                 if (nb == 0) for (int ch = threadIdx.x; ch < nseg; ch += kThreads) s_first[ch] = 0;
-                for (int j0 = 32 * wid; j0 < nb; j0 += kThreads)
+                for (int j0 = a.group_reads * wid; j0 < nb; j0 += a.group_reads * kWarpsPerCta)
                     stage_reads(a, g_rec, nb, cs == 0 ? ns : 0, j0, lane, s_rec, mask_addr, wbuf_addr, s_items[wid], s_first, un.t0 + 32 * cs, nseg,
-                                q_lo, qg, extent_err);
+                                q_lo, qg, extent_err, a.group_reads);
                 TICK(1)
                 __syncthreads();
 #ifdef MGATK_TIMING
