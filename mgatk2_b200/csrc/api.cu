@@ -14,7 +14,7 @@ using namespace mgatk;
 
 namespace {
 
-constexpr int kMaxChunks = 148 * 4 * (256 / kPartThreads);   // partition CTAs: one wave (bounds the open write heads)
+constexpr int kMaxChunks = 148 * MGATK_SCATTER_CTAS * (256 / kPartThreads);   // partition CTAs: one wave (bounds the open write heads)
 constexpr int kMaxDigitBits = 11;                    // 2048 bins * 20 B = 40 KB of shared memory per scatter CTA
 constexpr int kMaxStages = 16;
 

@@ -288,8 +288,11 @@ template <> struct Packed<8> {
 typedef Packed<kPartWarps> Pack;
 __host__ __device__ inline size_t scatter_smem_bytes(int bins) { return (size_t)bins * (2 * sizeof(Pack) + 4); }
 
+#ifndef MGATK_SCATTER_CTAS
+#define MGATK_SCATTER_CTAS 4
+#endif
 template <class Src>
-__global__ void __launch_bounds__(kPartThreads)
+__global__ void __launch_bounds__(kPartThreads, MGATK_SCATTER_CTAS)
 k_scatter(Src src, int64_t chunk, int nchunks, int shift, int bins, const u32 *__restrict__ mat, GroupRec *__restrict__ dst,
           u64 *__restrict__ error_bits) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
