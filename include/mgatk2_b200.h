@@ -210,6 +210,18 @@ int mgatk_filter_strand_bias_device(mgatk_handle *h, uint16_t *planes_dev, int32
 int mgatk_pileup_host(mgatk_handle *h, const mgatk_params *params,
                       const mgatk_batch *batch_host, const mgatk_outputs *out_host);
 
+/* The same call in two halves, for callers with more than one batch (one BAM per sample, or the
+ * reference's `bulk` runs over many libraries): submit enqueues the upload, the kernels and the
+ * download on three streams and returns; wait blocks until out_host of that ticket is complete
+ * (overflow list included) and returns the batch's status. Up to TWO tickets may be in flight:
+ * the upload of batch k+1 then runs while batch k computes and downloads (PCIe is full duplex),
+ * which is what bounds throughput with host buffers. batch_host / out_host must stay valid and
+ * untouched until wait returns; pinned memory is needed for the copies to overlap. Tickets may be
+ * waited for in any order. mgatk_pileup_host == submit + wait. */
+int mgatk_pileup_host_submit(mgatk_handle *h, const mgatk_params *params, const mgatk_batch *batch_host,
+                             const mgatk_outputs *out_host, int64_t *ticket);
+int mgatk_pileup_host_wait(mgatk_handle *h, int64_t ticket);
+
 /* number of kernel launches issued by the last mgatk_pileup_* call on this handle */
 int64_t mgatk_last_launch_count(const mgatk_handle *h);
 

@@ -14,7 +14,7 @@ EXPORTS = (
     "mgatk_abi_version", "mgatk_status_string", "mgatk_create", "mgatk_destroy", "mgatk_last_error",
     "mgatk_workspace_bytes", "mgatk_pileup_device", "mgatk_check_stats", "mgatk_pileup_host",
     "mgatk_filter_strand_bias_device", "mgatk_stream_begin_device", "mgatk_stream_finish_device",
-    "mgatk_last_launch_count", "mgatk_last_stage_times",
+    "mgatk_last_launch_count", "mgatk_last_stage_times", "mgatk_pileup_host_submit", "mgatk_pileup_host_wait",
 )
 
 N_PLANES = 11
@@ -74,6 +74,9 @@ def load():
                                                     ctypes.c_double, ctypes.c_void_p]
     lib.mgatk_pileup_host.argtypes = [ctypes.c_void_p, ctypes.POINTER(ParamsC), ctypes.POINTER(MgatkBatchC),
                                       ctypes.POINTER(OutputsC)]
+    lib.mgatk_pileup_host_submit.argtypes = [ctypes.c_void_p, ctypes.POINTER(ParamsC), ctypes.POINTER(MgatkBatchC),
+                                             ctypes.POINTER(OutputsC), ctypes.POINTER(ctypes.c_int64)]
+    lib.mgatk_pileup_host_wait.argtypes = [ctypes.c_void_p, ctypes.c_int64]
     lib.mgatk_last_launch_count.restype = ctypes.c_int64
     lib.mgatk_last_launch_count.argtypes = [ctypes.c_void_p]
     lib.mgatk_last_stage_times.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_char_p),

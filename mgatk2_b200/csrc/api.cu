@@ -70,6 +70,14 @@ GroupRec *grouped_at(char *ws, const Layout &L, int gen) { return (GroupRec *)(w
 
 struct DevBuf { void *p = nullptr; size_t cap = 0; };
 
+struct HostSlot {
+    DevBuf in[9], planes, qc, stats, totals, ovf;
+    cudaEvent_t in_done = nullptr, compute_done = nullptr, out_done = nullptr;
+    mgatk_outputs host = {};          // the caller's buffers of the batch in flight
+    uint32_t serial = 0;
+    bool busy = false;
+};
+
 }  // namespace
 
 struct mgatk_handle {
@@ -82,9 +90,16 @@ struct mgatk_handle {
     const char *stage_names[kMaxStages] = {};
     int n_stages = 0;
     bool events_ready = false;
-    // device buffers of the host entry point
-    DevBuf in[9], planes, qc, stats, totals, ovf, ws;
-    cudaStream_t stream = nullptr;
+    // host entry points: two slots of device buffers (inputs + outputs) so that the upload of one batch, the kernels
+    // of another and the download of a third overlap (mgatk_pileup_host_submit / _wait); the workspace is shared
+    // because the kernels of all batches run in order on `stream`
+    HostSlot slot[2];
+    DevBuf ws;
+    uint32_t serial = 0;
+    cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    // side stream of the overflow-list kernel (runs next to the main pileup kernel): fork / join events
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -149,9 +164,20 @@ int launch_pileup_t(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, const 
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup<kPpad, false>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
+    // Tiles with more reads than mask slots (hot spots) are walked in sub-tiles by the kSplit instance. The list is
+    // usually short: the kernel goes first on a side stream, most of its CTAs leave at once and the CTAs of the main
+    // kernel take their place, so both run side by side (they write disjoint tiles).
+    if (!h->side) {
+        CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(h->ev_fork, s));
+    CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    k_pileup<kPpad, true><<<h->sm_count * per_sm, kThreads, smem, h->side>>>(a_overflow, batch_reads);
+    CU(cudaEventRecord(h->ev_join, h->side));
     k_pileup<kPpad, false><<<h->sm_count * per_sm, kThreads, smem, s>>>(a, batch_reads);    // persistent CTAs pulling units
-    // tiles with more reads than mask slots (hot spots), walked in sub-tiles; usually an empty list
-    k_pileup<kPpad, true><<<h->sm_count * per_sm, kThreads, smem, s>>>(a_overflow, batch_reads);
+    CU(cudaStreamWaitEvent(s, h->ev_join, 0));
     h->launches += 2;
     CU(cudaGetLastError());
     return MGATK_OK;
@@ -384,11 +410,18 @@ int mgatk_create(mgatk_handle **out, int device) {
 int mgatk_destroy(mgatk_handle *h) {
     if (!h) return MGATK_OK;
     cudaSetDevice(h->device);
-    DevBuf *all[] = {&h->planes, &h->qc, &h->stats, &h->totals, &h->ovf, &h->ws};
-    for (DevBuf *b : all) if (b->p) cudaFree(b->p);
-    for (DevBuf &b : h->in) if (b.p) cudaFree(b.p);
+    cudaDeviceSynchronize();
+    for (HostSlot &sl : h->slot) {
+        DevBuf *all[] = {&sl.planes, &sl.qc, &sl.stats, &sl.totals, &sl.ovf};
+        for (DevBuf *b : all) if (b->p) cudaFree(b->p);
+        for (DevBuf &b : sl.in) if (b.p) cudaFree(b.p);
+        if (sl.in_done) { cudaEventDestroy(sl.in_done); cudaEventDestroy(sl.compute_done); cudaEventDestroy(sl.out_done); }
+    }
+    if (h->ws.p) cudaFree(h->ws.p);
+    if (h->s_h2d) { cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h); }
     if (h->events_ready) for (int i = 0; i <= kMaxStages; i++) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     delete h;
     return MGATK_OK;
 }
@@ -478,51 +511,99 @@ int mgatk_check_stats(const mgatk_stats *st) {
     return MGATK_OK;
 }
 
-int mgatk_pileup_host(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, const mgatk_outputs *o) {
+int mgatk_pileup_host_submit(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, const mgatk_outputs *o,
+                             int64_t *ticket) {
     if (!h) return MGATK_ERR_BAD_ARG;
     h->err.clear();
+    if (!ticket) return fail(h, MGATK_ERR_BAD_ARG, "null ticket");
+    *ticket = -1;
     int rc = validate(h, p, b, o);
     if (rc) return rc;
+    const int k_slot = !h->slot[0].busy ? 0 : !h->slot[1].busy ? 1 : -1;
+    if (k_slot < 0) return fail(h, MGATK_ERR_BAD_ARG, "two batches in flight: wait for the older ticket first");
+    HostSlot &sl = h->slot[k_slot];
     CU(cudaSetDevice(h->device));
     if (!h->stream) CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    cudaStream_t s = h->stream;
+    if (!h->s_h2d) {
+        CU(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    }
+    if (!sl.in_done) {
+        CU(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+    }
     const size_t n = (size_t)b->n_records, C = (size_t)p->n_cells, P = (size_t)p->mito_length;
     const size_t ppad = (size_t)MGATK_POS_PAD(P);
-    const void *src[9] = {b->pos, b->tlen, b->flag, b->mapq, b->bc_idx, b->l_seq, b->n_cigar, b->blob_off, b->blob};
-    const size_t bytes[9] = {4 * n, 4 * n, 2 * n, n, 4 * n, 2 * n, 2 * n, 4 * n, (size_t)b->blob_bytes};
-    for (int k = 0; k < 9; k++) {
-        if ((rc = ensure(h, h->in[k], bytes[k]))) return rc;
-        if (bytes[k]) CU(cudaMemcpyAsync(h->in[k].p, src[k], bytes[k], cudaMemcpyHostToDevice, s));
-    }
     const size_t planes_bytes = C * MGATK_N_PLANES * ppad * 2;
     const int64_t ws_bytes = mgatk_workspace_bytes(b->n_records, p->n_cells);
     if (ws_bytes < 0) return fail(h, MGATK_ERR_RANGE, "n_records / n_cells outside limits");
-    if ((rc = ensure(h, h->planes, planes_bytes)) || (rc = ensure(h, h->qc, C * sizeof(mgatk_cell_qc))) ||
-        (rc = ensure(h, h->stats, sizeof(mgatk_stats))) || (rc = ensure(h, h->totals, P * 4 * 8)) ||
-        (rc = ensure(h, h->ovf, (size_t)o->overflow_capacity * sizeof(mgatk_overflow))) ||
+    const void *src[9] = {b->pos, b->tlen, b->flag, b->mapq, b->bc_idx, b->l_seq, b->n_cigar, b->blob_off, b->blob};
+    const size_t bytes[9] = {4 * n, 4 * n, 2 * n, n, 4 * n, 2 * n, 2 * n, 4 * n, (size_t)b->blob_bytes};
+    // (a growing buffer is freed and reallocated: cudaFree waits for the device, so nothing in flight loses its memory;
+    //  the workspace grows only while no other batch is in flight)
+    if ((size_t)ws_bytes > h->ws.cap && h->slot[k_slot ^ 1].busy) CU(cudaEventSynchronize(h->slot[k_slot ^ 1].compute_done));
+    for (int k = 0; k < 9; k++)
+        if ((rc = ensure(h, sl.in[k], bytes[k]))) return rc;
+    if ((rc = ensure(h, sl.planes, planes_bytes)) || (rc = ensure(h, sl.qc, C * sizeof(mgatk_cell_qc))) ||
+        (rc = ensure(h, sl.stats, sizeof(mgatk_stats))) || (rc = ensure(h, sl.totals, P * 4 * 8)) ||
+        (rc = ensure(h, sl.ovf, (size_t)o->overflow_capacity * sizeof(mgatk_overflow))) ||
         (rc = ensure(h, h->ws, (size_t)ws_bytes)))
         return rc;
+    // upload
+    for (int k = 0; k < 9; k++)
+        if (bytes[k]) CU(cudaMemcpyAsync(sl.in[k].p, src[k], bytes[k], cudaMemcpyHostToDevice, h->s_h2d));
+    CU(cudaEventRecord(sl.in_done, h->s_h2d));
+    // kernels
+    cudaStream_t s = h->stream;
+    CU(cudaStreamWaitEvent(s, sl.in_done, 0));
     mgatk_batch bd = *b;
-    bd.pos = (const int32_t *)h->in[0].p; bd.tlen = (const int32_t *)h->in[1].p; bd.flag = (const uint16_t *)h->in[2].p;
-    bd.mapq = (const uint8_t *)h->in[3].p; bd.bc_idx = (const int32_t *)h->in[4].p; bd.l_seq = (const uint16_t *)h->in[5].p;
-    bd.n_cigar = (const uint16_t *)h->in[6].p; bd.blob_off = (const uint32_t *)h->in[7].p; bd.blob = (const uint8_t *)h->in[8].p;
+    bd.pos = (const int32_t *)sl.in[0].p; bd.tlen = (const int32_t *)sl.in[1].p; bd.flag = (const uint16_t *)sl.in[2].p;
+    bd.mapq = (const uint8_t *)sl.in[3].p; bd.bc_idx = (const int32_t *)sl.in[4].p; bd.l_seq = (const uint16_t *)sl.in[5].p;
+    bd.n_cigar = (const uint16_t *)sl.in[6].p; bd.blob_off = (const uint32_t *)sl.in[7].p; bd.blob = (const uint8_t *)sl.in[8].p;
     mgatk_outputs od = *o;
-    od.planes = (uint16_t *)h->planes.p; od.cell_qc = (mgatk_cell_qc *)h->qc.p; od.stats = (mgatk_stats *)h->stats.p;
-    od.base_totals = (int64_t *)h->totals.p; od.overflow = o->overflow_capacity ? (mgatk_overflow *)h->ovf.p : nullptr;
+    od.planes = (uint16_t *)sl.planes.p; od.cell_qc = (mgatk_cell_qc *)sl.qc.p; od.stats = (mgatk_stats *)sl.stats.p;
+    od.base_totals = (int64_t *)sl.totals.p; od.overflow = o->overflow_capacity ? (mgatk_overflow *)sl.ovf.p : nullptr;
     rc = run_device(h, p, &bd, &od, h->ws.p, ws_bytes, s);
-    if (rc) return rc;
-    if (planes_bytes) CU(cudaMemcpyAsync(o->planes, od.planes, planes_bytes, cudaMemcpyDeviceToHost, s));
-    if (C) CU(cudaMemcpyAsync(o->cell_qc, od.cell_qc, C * sizeof(mgatk_cell_qc), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(o->stats, od.stats, sizeof(mgatk_stats), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(o->base_totals, od.base_totals, P * 4 * 8, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    if (rc) { cudaStreamSynchronize(s); return rc; }
+    CU(cudaEventRecord(sl.compute_done, s));
+    // download
+    CU(cudaStreamWaitEvent(h->s_d2h, sl.compute_done, 0));
+    if (planes_bytes) CU(cudaMemcpyAsync(o->planes, od.planes, planes_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+    if (C) CU(cudaMemcpyAsync(o->cell_qc, od.cell_qc, C * sizeof(mgatk_cell_qc), cudaMemcpyDeviceToHost, h->s_d2h));
+    CU(cudaMemcpyAsync(o->stats, od.stats, sizeof(mgatk_stats), cudaMemcpyDeviceToHost, h->s_d2h));
+    CU(cudaMemcpyAsync(o->base_totals, od.base_totals, P * 4 * 8, cudaMemcpyDeviceToHost, h->s_d2h));
+    CU(cudaEventRecord(sl.out_done, h->s_d2h));
+    sl.host = *o; sl.busy = true; sl.serial = ++h->serial;
+    *ticket = ((int64_t)sl.serial << 1) | k_slot;
+    return MGATK_OK;
+}
+
+int mgatk_pileup_host_wait(mgatk_handle *h, int64_t ticket) {
+    if (!h) return MGATK_ERR_BAD_ARG;
+    h->err.clear();
+    if (ticket < 0) return fail(h, MGATK_ERR_BAD_ARG, "bad ticket");
+    HostSlot &sl = h->slot[ticket & 1];
+    if (!sl.busy || (int64_t)sl.serial != (ticket >> 1)) return fail(h, MGATK_ERR_BAD_ARG, "ticket is not in flight");
+    CU(cudaSetDevice(h->device));
+    sl.busy = false;
+    CU(cudaEventSynchronize(sl.out_done));
+    const mgatk_outputs *o = &sl.host;
     if (o->overflow_capacity && o->stats->n_overflow) {
         size_t k = (size_t)(o->stats->n_overflow < (uint64_t)o->overflow_capacity ? o->stats->n_overflow : (uint64_t)o->overflow_capacity);
-        CU(cudaMemcpy(o->overflow, od.overflow, k * sizeof(mgatk_overflow), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpyAsync(o->overflow, sl.ovf.p, k * sizeof(mgatk_overflow), cudaMemcpyDeviceToHost, h->s_d2h));
+        CU(cudaStreamSynchronize(h->s_d2h));
     }
-    rc = mgatk_check_stats(o->stats);
+    int rc = mgatk_check_stats(o->stats);
     if (rc) return fail(h, rc, mgatk_status_string(rc));
     return MGATK_OK;
+}
+
+int mgatk_pileup_host(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, const mgatk_outputs *o) {
+    int64_t ticket = -1;
+    int rc = mgatk_pileup_host_submit(h, p, b, o, &ticket);
+    if (rc) return rc;
+    return mgatk_pileup_host_wait(h, ticket);
 }
 
 int64_t mgatk_last_launch_count(const mgatk_handle *h) { return h ? h->launches : 0; }

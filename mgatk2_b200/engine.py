@@ -151,6 +151,45 @@ class PileupEngine:
                             out["overflow"][: stats["n_overflow"]], params.mito_length, params.min_reads_per_cell,
                             self.stage_times(), self.launch_count())
 
+    def submit_host(self, batch: ReadBatch, params: ParamsC, out: dict) -> int:
+        """First half of run_host (mgatk_pileup_host_submit): enqueue upload, kernels and download, return a ticket.
+        Two tickets may be in flight; `batch` and `out` must stay untouched until wait_host(ticket)."""
+        oc = OutputsC(out["planes"].ctypes.data, out["cell_qc"].ctypes.data, out["stats"].ctypes.data,
+                      out["base_totals"].ctypes.data, out["overflow"].ctypes.data if len(out["overflow"]) else None,
+                      len(out["overflow"]))
+        bc = batch.as_c()
+        ticket = ctypes.c_int64(-1)
+        rc = self.lib.mgatk_pileup_host_submit(self.handle, ctypes.byref(params), ctypes.byref(bc), ctypes.byref(oc),
+                                               ctypes.byref(ticket))
+        if rc:
+            self._raise(rc)
+        if not hasattr(self, "_in_flight"):
+            self._in_flight = {}
+        self._in_flight[ticket.value] = (batch, out, params.mito_length, params.min_reads_per_cell, self.launch_count())
+        return ticket.value
+
+    def wait_host(self, ticket: int) -> PileupResult:
+        batch, out, mito_length, min_reads, launches = getattr(self, "_in_flight", {}).pop(ticket, (None,) * 5)
+        rc = self.lib.mgatk_pileup_host_wait(self.handle, int(ticket))
+        if rc:
+            self._raise(rc)
+        stats = {k: int(v) for k, v in zip(STATS_FIELDS, out["stats"])}
+        return PileupResult(out["planes"], out["cell_qc"], stats, out["base_totals"], out["overflow"][: stats["n_overflow"]],
+                            mito_length, min_reads, {}, launches)
+
+    def run_host_many(self, batches, params_of, outs):
+        """Pipelined run_host over an iterable of batches: yields (index, PileupResult) in order. `params_of(batch)`
+        gives the parameters of a batch, `outs` is a list of TWO host output sets (alloc_host_outputs) that are reused
+        alternately, so a result must be consumed before the next but one is yielded."""
+        pending = []
+        for i, batch in enumerate(batches):
+            if len(pending) == 2:
+                j, t = pending.pop(0)
+                yield j, self.wait_host(t)
+            pending.append((i, self.submit_host(batch, params_of(batch), outs[i % 2])))
+        for j, t in pending:
+            yield j, self.wait_host(t)
+
     # ------------------------------------------------------------------ device-resident path
     def upload(self, batch: ReadBatch, pinned_src: dict | None = None):
         """Copy a batch into HBM (torch tensors own the memory). Returns a DeviceBatch."""

@@ -243,3 +243,53 @@ def test_streamed_batches_equal_one_batch(engine, profile, kw):
     with pytest.raises(PileupKernelError) as e:
         engine.run_stream([deep], lp2, dout2)
     assert e.value.status == 9
+
+
+def test_submit_wait_two_batches_in_flight(engine):
+    """mgatk_pileup_host_submit / _wait: different batches (sizes, cell counts, parameters) in flight together give what the
+    oracle gives for each; tickets are waited for out of order; a third submit is refused while two are in flight; an
+    unsorted batch reports its status at wait and leaves the other ticket intact."""
+    from mgatk2_b200.exceptions import PileupKernelError
+    from oracle.oracle import run_oracle
+    cases = [(synth_batch(64, 60_000, "atac50", seed=5), 64, dict()),
+             (synth_batch(200, 150_000, "stress150", seed=6), 200, dict(max_strand_bias=0.8, min_reads_per_cell=300)),
+             (synth_batch(16, 9_000, "atac70", seed=7), 16, dict(dedup_mode=0, min_baseq=30)),
+             (synth_batch(300, 40_000, "atac50", seed=8), 300, dict(flags=1))]
+    params = [make_params(b, c, **kw) for b, c, kw in cases]
+    oracles = [run_oracle(b, p, n_threads=8) for (b, _, _), p in zip(cases, params)]
+    lps = [to_lib_params(p) for p in params]
+    outs = [engine.alloc_host_outputs(c, 16569, 1 << 16) for _, c, _ in cases]
+    # pairs in flight, second ticket waited for first
+    for i in (0, 2):
+        t0 = engine.submit_host(cases[i][0], lps[i], outs[i])
+        t1 = engine.submit_host(cases[i + 1][0], lps[i + 1], outs[i + 1])
+        with pytest.raises(PileupKernelError):
+            engine.submit_host(cases[i][0], lps[i], outs[i])
+        r1 = engine.wait_host(t1)
+        r0 = engine.wait_host(t0)
+        assert_result_equals_oracle(r0, oracles[i])
+        assert_result_equals_oracle(r1, oracles[i + 1])
+        with pytest.raises(PileupKernelError):
+            engine.wait_host(t0)                                      # not in flight any more
+    # the generator form: same cell count (the two output sets are reused alternately), parameters per batch
+    same = [synth_batch(64, 20_000 + 7_000 * k, "atac50", seed=20 + k) for k in range(5)]
+    sp = [make_params(b, 64, min_baseq=10 + 5 * k) for k, b in enumerate(same)]
+    by_id = {id(b): to_lib_params(p) for b, p in zip(same, sp)}
+    pair = [engine.alloc_host_outputs(64, 16569, 1 << 16) for _ in range(2)]
+    seen = []
+    for j, res in engine.run_host_many(same, lambda b: by_id[id(b)], pair):
+        assert_result_equals_oracle(res, run_oracle(same[j], sp[j], n_threads=8))
+        seen.append(j)
+    assert seen == [0, 1, 2, 3, 4]
+    # an error in one ticket
+    bad = cases[0][0]
+    bad = ReadBatch(**{**{f: getattr(bad, f) for f in ("tlen", "flag", "mapq", "bc_idx", "l_seq", "n_cigar", "blob_off", "blob")},
+                       "pos": bad.pos[::-1].copy()})
+    t_bad = engine.submit_host(bad, lps[0], outs[0])
+    t_ok = engine.submit_host(cases[1][0], lps[1], outs[1])
+    with pytest.raises(PileupKernelError) as e:
+        engine.wait_host(t_bad)
+    assert e.value.status == 4
+    assert_result_equals_oracle(engine.wait_host(t_ok), oracles[1])
+    # and the blocking call still works afterwards
+    assert_result_equals_oracle(engine.run_host(cases[2][0], lps[2], out=outs[2]), oracles[2])
