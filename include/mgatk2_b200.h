@@ -210,8 +210,8 @@ int mgatk_filter_strand_bias_device(mgatk_handle *h, uint16_t *planes_dev, int32
 int mgatk_pileup_host(mgatk_handle *h, const mgatk_params *params,
                       const mgatk_batch *batch_host, const mgatk_outputs *out_host);
 
-/* The same call in two halves, for callers with more than one batch (one BAM per sample, or the
- * reference's `bulk` runs over many libraries): submit enqueues the upload, the kernels and the
+/* The same call in two halves, for callers with more than one batch (one BAM per sample or per
+ * cell, as in the reference's `call` command, cli/options.py:310,421): submit enqueues the upload, the kernels and the
  * download on three streams and returns; wait blocks until out_host of that ticket is complete
  * (overflow list included) and returns the batch's status. Up to TWO tickets may be in flight:
  * the upload of batch k+1 then runs while batch k computes and downloads (PCIe is full duplex),

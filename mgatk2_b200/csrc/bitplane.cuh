@@ -1,10 +1,12 @@
 // mgatk2_b200 — word-parallel helpers of the bit-plane pileup (stage 3 of the hot path).
 //
-// A read's bases are turned once into four bit masks in QUERY coordinates (bit q of mask X is set iff
-// SEQ[q] == X, the base quality passes and q lies inside the distance-from-end window,
-// pileup.py:67-86). Counting a chunk of 32 reference positions then reduces to picking a 32-bit
-// window out of these masks per aligned block (pileup.py:55-65) and a 32x32 bit transpose across the
-// warp, so that each lane (= position) can popcount the reads that carry a given base there.
+// A read's bases are turned once into three bit planes in QUERY coordinates: bit q of V is set iff
+// SEQ[q] is one of A, C, G, T, the base quality passes and q lies inside the distance-from-end window
+// (pileup.py:67-86); B0 and B1 hold the two bits of the base code (A=0, C=1, G=2, T=3) under V.
+// Counting a chunk of 32 reference positions then reduces to picking a 32-bit window out of these
+// planes per aligned block (pileup.py:55-65) and a 32x32 bit transpose across the warp, so that each
+// lane (= position) can popcount the reads that carry a given base there. Three planes instead of one
+// mask per base: one transpose less per round, and the spare quarter of the matrix takes the Tn5 bit.
 //
 // Everything here is plain integer arithmetic and compiles for the host too: tests/test_bitplane_host.py
 // checks each helper exhaustively / on random words against the obvious per-base loop.
@@ -77,31 +79,38 @@ MG_HD u32 qual_ok8_top(u32 q0, u32 q1, QualGe g) {
 }
 
 // ---- bases: one little-endian word of BAM 4-bit SEQ = eight bases, high nibble first in every byte ----
-// Returns, per base X in A,C,G,T (BAM codes 1,2,4,8), the eight "SEQ[i] == X" flags as the top byte
-// (bit 24+i = base i). Any other code (=, N, IUPAC) matches nothing (pileup.py:83-86).
-struct Eq8 { u32 a, c, g, t; };
+// Returns the eight flags of each plane as the top byte (bit 24+i = base i): v = SEQ[i] is A, C, G or T (BAM codes
+// 1, 2, 4, 8; any other code (=, N, IUPAC) counts nowhere, pileup.py:83-86), b0 = code has bit 1 or 3 (C, T; scrap
+// outside v), b1 = code has bit 2 or 3 (G, T; scrap outside v).
+struct Planes8 { u32 v, b0, b1; };
 
 MG_HD u32 pack_nibble_flags_raw(u32 e) {                // flags at bits 4n (n = 0..7, nothing else set) -> bits 24..31; lower bits are scrap
     const u32 y = (e | (e >> 3)) & 0x03030303u;         // byte k: bits 0,1 = nibbles 2k, 2k+1
     return y * 0x01041040u;
 }
 
-MG_HD Eq8 seq_eq8_raw(u32 s) {                          // top byte = flags, lower bits scrap (AND with a top-byte mask)
+MG_HD Planes8 seq_planes8_raw(u32 s) {                  // top byte = flags, lower bits scrap (AND with a top-byte mask)
     const u32 t0 = ((s & 0x0f0f0f0fu) << 4) | ((s >> 4) & 0x0f0f0f0fu);   // nibble n now holds base n
     const u32 t1 = t0 >> 1, t2 = t0 >> 2, t3 = t0 >> 3;
     const u32 k = 0x11111111u;
-    Eq8 r;
-    r.a = pack_nibble_flags_raw((t0 & ~t1 & ~t2) & (~t3 & k));   // 0001
-    r.c = pack_nibble_flags_raw((~t0 & t1 & ~t2) & (~t3 & k));   // 0010
-    r.g = pack_nibble_flags_raw((~t0 & ~t1 & t2) & (~t3 & k));   // 0100
-    r.t = pack_nibble_flags_raw((~t0 & ~t1 & ~t2) & (t3 & k));   // 1000
+    const u32 one3 = (t0 ^ t1 ^ t2) & ~(t0 & t1 & t2);   // exactly one of the low three code bits
+    const u32 none3 = ~(t0 | t1 | t2);
+    Planes8 r;
+    r.v = pack_nibble_flags_raw(((one3 & ~t3) | (none3 & t3)) & k);       // one-hot code
+    r.b0 = pack_nibble_flags_raw((t1 | t3) & k);
+    r.b1 = pack_nibble_flags_raw((t2 | t3) & k);
     return r;
 }
 
-MG_HD Eq8 seq_eq8_top(u32 s) {
-    Eq8 r = seq_eq8_raw(s);
-    r.a &= 0xff000000u; r.c &= 0xff000000u; r.g &= 0xff000000u; r.t &= 0xff000000u;
+MG_HD Planes8 seq_planes8_top(u32 s) {
+    Planes8 r = seq_planes8_raw(s);
+    r.v &= 0xff000000u; r.b0 &= 0xff000000u; r.b1 &= 0xff000000u;
     return r;
+}
+
+// per-base masks back from the planes (b0, b1 inside v): out = A, C, G, T
+MG_HD void planes_to_bases(u32 v, u32 b0, u32 b1, u32 (&out)[4]) {
+    out[0] = v & ~(b0 | b1); out[1] = b0 & ~b1; out[2] = b1 & ~b0; out[3] = b0 & b1;
 }
 
 // byte G of m <- top byte of v
@@ -126,6 +135,21 @@ MG_HD u32 transpose_stage(u32 mine, u32 other, u32 keep, u32 amt) {
     const u32 moved = rotl32(other, amt);                  // wrapped-around bits fall outside ~keep
     return (mine & keep) | (moved & ~keep);
 }
+// The stages j = 16 and j = 8 move whole bytes: one byte permute of (mine, other) each instead of rotate + select.
+MG_HD u32 byte_perm(u32 a, u32 b, u32 sel) {            // PRMT, selector nibbles 0..7 only
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const unsigned long long ab = ((unsigned long long)b << 32) | a;
+    u32 r = 0;
+    for (int i = 0; i < 4; i++) r |= (u32)((ab >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+#endif
+}
+MG_HD u32 transpose_sel(int lane, int j) {              // j = 16 or 8
+    return j == 16 ? ((lane & 16) ? 0x3276u : 0x5410u) : ((lane & 8) ? 0x3715u : 0x6240u);
+}
+MG_HD u32 transpose_stage_bytes(u32 mine, u32 other, u32 sel) { return byte_perm(mine, other, sel); }
 
 }  // namespace mgatk
 
@@ -135,18 +159,19 @@ MG_HD u32 transpose_stage(u32 mine, u32 other, u32 keep, u32 amt) {
 //     u32  ld32(u32 addr)                    4-byte aligned load
 //     void st128(u32 addr, u32 a, u32 c, u32 g, u32 t)   16-byte aligned store
 //     void ld128(u32 addr, u32 (&v)[4])      16-byte aligned load
-// Layout written at `out`: ceil(L/32) groups of four words (A, C, G, T masks of query bases 32w..32w+31).
+// Layout written at `out`: ceil(L/32) groups of four words (V, B0, B1 planes of query bases 32w..32w+31, B0 and B1
+// cut to V; the fourth word is zero).
 // Loads may run up to 40 bytes past the end of QUAL; whatever they return is masked by the window.
 // ---------------------------------------------------------------------------------------------
 namespace mgatk {
 
-// masks of query bases 32w .. 32w+31 of one read -> four words at out + 16w
+// planes of query bases 32w .. 32w+31 of one read -> four words at out + 16w
 template <class M>
 MG_HD void build_query_mask_group(const M &mem, u32 seq_addr /*4-aligned*/, u32 out /*16-aligned*/, int L, int w, int q_lo, int q_hi, QualGe qg) {
     const u32 qual_addr = seq_addr + (u32)((L + 1) >> 1) + 32u * (u32)w;
     const u32 qsh = (qual_addr & 3u) * 8u;
     const u32 qa = qual_addr & ~3u;
-    u32 mA = 0, mC = 0, mG = 0, mT = 0;
+    u32 mV = 0, m0 = 0, m1 = 0;
     const int lo = q_lo - 32 * w, hi = (q_hi < L ? q_hi : L) - 32 * w;   // window inside this group of 32 bases
 #pragma unroll
     for (int g = 0; g < 4; g++) {
@@ -155,14 +180,14 @@ MG_HD void build_query_mask_group(const M &mem, u32 seq_addr /*4-aligned*/, u32 
         const u32 s = mem.ld32(seq_addr + 16u * w + 4u * g);
         const u32 w0 = mem.ld32(qa + 8u * g), w1 = mem.ld32(qa + 8u * g + 4u), w2 = mem.ld32(qa + 8u * g + 8u);
         const u32 ok = qual_ok8_top(funnel_r(w0, w1, qsh), funnel_r(w1, w2, qsh), qg);
-        const Eq8 e = seq_eq8_raw(s);
-        if (g == 0) { mA = insert_top_byte<0>(mA, e.a & ok); mC = insert_top_byte<0>(mC, e.c & ok); mG = insert_top_byte<0>(mG, e.g & ok); mT = insert_top_byte<0>(mT, e.t & ok); }
-        else if (g == 1) { mA = insert_top_byte<1>(mA, e.a & ok); mC = insert_top_byte<1>(mC, e.c & ok); mG = insert_top_byte<1>(mG, e.g & ok); mT = insert_top_byte<1>(mT, e.t & ok); }
-        else if (g == 2) { mA = insert_top_byte<2>(mA, e.a & ok); mC = insert_top_byte<2>(mC, e.c & ok); mG = insert_top_byte<2>(mG, e.g & ok); mT = insert_top_byte<2>(mT, e.t & ok); }
-        else { mA = insert_top_byte<3>(mA, e.a & ok); mC = insert_top_byte<3>(mC, e.c & ok); mG = insert_top_byte<3>(mG, e.g & ok); mT = insert_top_byte<3>(mT, e.t & ok); }
+        const Planes8 e = seq_planes8_raw(s);
+        if (g == 0) { mV = insert_top_byte<0>(mV, e.v & ok); m0 = insert_top_byte<0>(m0, e.b0); m1 = insert_top_byte<0>(m1, e.b1); }
+        else if (g == 1) { mV = insert_top_byte<1>(mV, e.v & ok); m0 = insert_top_byte<1>(m0, e.b0); m1 = insert_top_byte<1>(m1, e.b1); }
+        else if (g == 2) { mV = insert_top_byte<2>(mV, e.v & ok); m0 = insert_top_byte<2>(m0, e.b0); m1 = insert_top_byte<2>(m1, e.b1); }
+        else { mV = insert_top_byte<3>(mV, e.v & ok); m0 = insert_top_byte<3>(m0, e.b0); m1 = insert_top_byte<3>(m1, e.b1); }
     }
-    const u32 wm = bit_range(q_lo - 32 * w, q_hi - 32 * w);   // pileup.py:67-78 (also cuts bases >= L)
-    mem.st128(out + 16u * w, mA & wm, mC & wm, mG & wm, mT & wm);
+    mV &= bit_range(q_lo - 32 * w, q_hi - 32 * w);            // pileup.py:67-78 (also cuts bases >= L)
+    mem.st128(out + 16u * w, mV, m0 & mV, m1 & mV, 0u);
 }
 
 template <class M>
@@ -171,16 +196,16 @@ MG_HD void build_query_masks(const M &mem, u32 seq_addr /*4-aligned*/, u32 out /
     for (int w = 0; w < nq; w++) build_query_mask_group(mem, seq_addr, out, L, w, q_lo, q_hi, qg);
 }
 
-// 32-bit windows of the four query masks starting at query bit qb (may be negative or beyond the read)
+// 32-bit windows of the three planes (V, B0, B1) starting at query bit qb (may be negative or beyond the read)
 template <class M>
-MG_HD void query_window(const M &mem, u32 masks /*16-aligned*/, int nq, int qb, u32 (&out)[4]) {
+MG_HD void query_window(const M &mem, u32 masks /*16-aligned*/, int nq, int qb, u32 (&out)[3]) {
     const int w0 = qb >> 5;                                // floor
     const u32 sh = (u32)qb & 31u;
     u32 lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
     if (w0 >= 0 && w0 < nq) mem.ld128(masks + 16u * (u32)w0, lo);
     if (w0 + 1 >= 0 && w0 + 1 < nq) mem.ld128(masks + 16u * (u32)(w0 + 1), hi);
 #pragma unroll
-    for (int x = 0; x < 4; x++) out[x] = funnel_r(lo[x], hi[x], sh);
+    for (int x = 0; x < 3; x++) out[x] = funnel_r(lo[x], hi[x], sh);
 }
 
 }  // namespace mgatk

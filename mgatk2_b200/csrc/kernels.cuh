@@ -676,8 +676,8 @@ __host__ __device__ inline size_t pileup_smem_bytes() {
 }
 
 // Per-base form of one aligned block for a read without query masks: chunk bits [pa, pa + span)
-// for query bases q0.. (already clipped to the distance-from-end window).
-__device__ __noinline__ void block_masks_global(const uint8_t *seq, int L, int pa, int span, int q0, int min_baseq, u32 (&m)[4]) {
+// for query bases q0.. (already clipped to the distance-from-end window). m = planes V, B0, B1.
+__device__ __noinline__ void block_masks_global(const uint8_t *seq, int L, int pa, int span, int q0, int min_baseq, u32 (&m)[3]) {
     const int8_t *qual = reinterpret_cast<const int8_t *>(seq) + ((L + 1) >> 1);
     const int b0 = max(pa, 0), b1 = min(pa + span, 32);
     for (int b = b0; b < b1; b++) {
@@ -685,27 +685,34 @@ __device__ __noinline__ void block_masks_global(const uint8_t *seq, int L, int p
         if ((int)__ldg(qual + q) < min_baseq) continue;        // int8 compare, pileup.py:80
         const u32 by = __ldg(seq + (q >> 1));
         const u32 nib = (q & 1) ? (by & 15u) : (by >> 4);
-        if (nib == 1) m[0] |= 1u << b;                         // pileup.py:83-86: A, C, G, T only
-        else if (nib == 2) m[1] |= 1u << b;
-        else if (nib == 4) m[2] |= 1u << b;
-        else if (nib == 8) m[3] |= 1u << b;
+        const u32 bit = 1u << b;
+        if (nib == 1) m[0] |= bit;                             // pileup.py:83-86: A, C, G, T only
+        else if (nib == 2) { m[0] |= bit; m[1] |= bit; }
+        else if (nib == 4) { m[0] |= bit; m[2] |= bit; }
+        else if (nib == 8) { m[0] |= bit; m[1] |= bit; m[2] |= bit; }
     }
 }
 
-struct TransposeConst { u32 keep[5], amt[5]; };          // per-lane constants of the five butterfly stages
+// per-lane constants of the five butterfly stages: byte selectors for j = 16, 8 (whole bytes move), keep mask and
+// rotate amount for j = 4, 2, 1
+struct TransposeConst { u32 sel[2], keep[3], amt[3]; };
 __device__ __forceinline__ TransposeConst make_transpose_const(int lane) {
     TransposeConst tc;
+    tc.sel[0] = transpose_sel(lane, 16); tc.sel[1] = transpose_sel(lane, 8);
+    asm volatile("" : "+r"(tc.sel[0]), "+r"(tc.sel[1]));
 #pragma unroll
-    for (int s = 0; s < 5; s++) {
-        tc.keep[s] = transpose_keep(lane, 16 >> s); tc.amt[s] = transpose_amt(lane, 16 >> s);
+    for (int s = 0; s < 3; s++) {
+        tc.keep[s] = transpose_keep(lane, 4 >> s); tc.amt[s] = transpose_amt(lane, 4 >> s);
         // opaque to the compiler: it would otherwise recompute both with two SELs per stage on the saturated ALU pipe
         asm volatile("" : "+r"(tc.keep[s]), "+r"(tc.amt[s]));
     }
     return tc;
 }
 __device__ __forceinline__ u32 warp_transpose(u32 x, const TransposeConst &tc) {
+    x = transpose_stage_bytes(x, __shfl_xor_sync(kFull, x, 16), tc.sel[0]);
+    x = transpose_stage_bytes(x, __shfl_xor_sync(kFull, x, 8), tc.sel[1]);
 #pragma unroll
-    for (int s = 0; s < 5; s++) x = transpose_stage(x, __shfl_xor_sync(kFull, x, 16 >> s), tc.keep[s], tc.amt[s]);
+    for (int s = 0; s < 3; s++) x = transpose_stage(x, __shfl_xor_sync(kFull, x, 4 >> s), tc.keep[s], tc.amt[s]);
     return x;
 }
 
@@ -768,12 +775,12 @@ __device__ __forceinline__ void stage_reads(const PileupArgs &a, const ReadRec *
         }
         // the groups of 32 bases of the staged reads are dealt to the lanes (a 150 bp read has five, and only a few such
         // reads fit the buffer at a time): item t = (owner lane, group)
-        const u32 ng = now ? (u32)nq : 0u;
-        u32 gincl = ng;
-        for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, gincl, o); if (lane >= o) gincl += v; }
-        const int n_items = (int)__shfl_sync(kFull, gincl, 31);
         // (when every read of the warp fits one pass - 32 reads of 50 bp - one read per lane is already dense)
         if ((gs < 32 || __any_sync(kFull, todo && !now)) && !__any_sync(kFull, now && nq > 8)) {   // n_items <= kMaxItems, three bits hold the group
+            const u32 ng = now ? (u32)nq : 0u;
+            u32 gincl = ng;
+            for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, gincl, o); if (lane >= o) gincl += v; }
+            const int n_items = (int)__shfl_sync(kFull, gincl, 31);
             for (u32 g = 0; g < ng; g++) s_items[gincl - ng + g] = (uint8_t)((lane << 3) | (int)g);
             __syncwarp();
             const u32 seq_a = sb + 4 * ncig;
@@ -826,26 +833,35 @@ __device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un,
     for (int r = first + 32 * part; r < nb; r += 32 * nparts) {
         const int j = r + lane;
         ReadRec rr; rr.pos = 0x7fffffff; rr.off = 0; rr.len = 0; rr.flags = 0;
-        if (j < ns) rr = s_rec[j];
+        if (j < ns) {                                        // the records sit below the mask slots
+            u32 w[4];
+            smem.ld128(mask_addr - (u32)(kStageReads * sizeof(ReadRec)) + 16u * (u32)j, w);
+            rr.pos = (int)w[0]; rr.off = w[1]; rr.len = w[2]; rr.flags = w[3];
+        }
         else if (j < nb) rr = g_rec[j];
         const int pos = rr.pos;
         const u32 m_after = __ballot_sync(kFull, pos >= c1);
         const bool cand = pos < c1 && pos > skip_le && (rr.flags & GF_PROCESS);   // implies j < nb
-        if (__ballot_sync(kFull, cand)) {
+        const u32 cands = __ballot_sync(kFull, cand);
+        if (cands) {
             const int strand = (rr.flags & GF_STRAND) ? 1 : 0;
             const int L = rr.len & 0xffff;
             const int nq = (L + 31) >> 5;
             const bool simple = (rr.flags & GF_SIMPLE) != 0;
             const u32 mask_s = mask_addr + (u32)j * (u32)a.mask_stride;
-            u32 m[4] = {0u, 0u, 0u, 0u};
+            u32 pv = 0u, p0 = 0u, p1 = 0u;                   // planes of this read inside the chunk: valid base, code bits
             u32 m5 = 0u;
             if (cand) {
                 // Tn5 site (pileup.py:43-50): reverse = start + len(SEQ) - 1, forward = start
                 const int t5 = strand ? pos + L - 1 : pos;
-                if (t5 >= c0 && t5 < c1 && t5 < a.P) m5 = 1u << (t5 - c0);
-                // one aligned block over all of SEQ: reference position p <-> query base p - pos; the masks are
+                if ((u32)(t5 - c0) < 32u && t5 < a.P) m5 = 1u << (t5 - c0);
+                // one aligned block over all of SEQ: reference position p <-> query base p - pos; the planes are
                 // already empty outside the distance-from-end window and beyond SEQ
-                if (simple) query_window(smem, mask_s, nq, c0 - pos, m);
+                if (simple) {
+                    u32 wv[3];
+                    query_window(smem, mask_s, nq, c0 - pos, wv);
+                    pv = wv[0]; p0 = wv[1]; p1 = wv[2];
+                }
             }
             if (__any_sync(kFull, cand && !simple)) {        // soft clips, indels, reads without query masks
                 if (cand && !simple) {
@@ -867,14 +883,15 @@ __device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un,
                             ref += n; qp = min(qp + n, kOpCap);          // pileup.py:90-91
                             if (vb > va && r0 + va < c1 && r0 + vb > c0) {
                                 const int pa = r0 + va - c0, span = vb - va, q0 = q00 + va;
+                                u32 wv[3] = {0u, 0u, 0u};
                                 if (masks) {
-                                    u32 wv[4];
                                     query_window(smem, mask_s, nq, q0 - pa, wv);
                                     const u32 rm = bit_range(pa, pa + span);
-                                    m[0] |= wv[0] & rm; m[1] |= wv[1] & rm; m[2] |= wv[2] & rm; m[3] |= wv[3] & rm;
+                                    wv[0] &= rm; wv[1] &= rm; wv[2] &= rm;
                                 } else {
-                                    block_masks_global(reinterpret_cast<const uint8_t *>(cig + ncig), L, pa, span, q0, a.min_baseq, m);
+                                    block_masks_global(reinterpret_cast<const uint8_t *>(cig + ncig), L, pa, span, q0, a.min_baseq, wv);
                                 }
+                                pv |= wv[0]; p0 |= wv[1]; p1 |= wv[2];
                             }
                         } else if (op == 2 || op == 3) ref += n;         // pileup.py:92-93
                         else if (op == 4) qp = min(qp + n, kOpCap);      // pileup.py:94-95; I, H, P: nothing (sic)
@@ -882,19 +899,31 @@ __device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un,
                     }
                 }
             }
-            // lane = read -> lane = position; forward and reverse reads counted apart (pileup.py:88)
-            const u32 rev = __ballot_sync(kFull, cand && strand);
-#pragma unroll
-            for (int x = 0; x < 4; x++) {
-                const u32 t = warp_transpose(m[x], tc);
-                cnt[2 * x] += __popc(t & ~rev);
-                cnt[2 * x + 1] += __popc(t & rev);
+            // lane = read -> lane = position. The four bit matrices of a round (V, B0, B1, Tn5; rows = reads) share one
+            // 32x32 transpose when its candidates sit in lanes 0..7 (one matrix per byte), two when they sit in lanes
+            // 0..15; forward and reverse reads are counted apart (pileup.py:88)
+            u32 rev = __ballot_sync(kFull, cand && strand);
+            u32 v, b0, b1, t5;
+            if (cands <= 0xffu) {
+                const int src = lane & 7;
+                const u32 s0 = __shfl_sync(kFull, p0, src), s1 = __shfl_sync(kFull, p1, src), s5 = __shfl_sync(kFull, m5, src);
+                const u32 x = lane < 16 ? (lane < 8 ? pv : s0) : (lane < 24 ? s1 : s5);
+                const u32 t = warp_transpose(x, tc);
+                v = t & 0xffu; b0 = __byte_perm(t, 0u, 0x4441); b1 = __byte_perm(t, 0u, 0x4442); t5 = t >> 24;
+            } else if (cands <= 0xffffu) {
+                const u32 s0 = __shfl_xor_sync(kFull, p0, 16), s5 = __shfl_xor_sync(kFull, m5, 16);
+                const u32 ta = warp_transpose(lane < 16 ? pv : s0, tc);
+                const u32 tb = warp_transpose(lane < 16 ? p1 : s5, tc);
+                v = ta & 0xffffu; b0 = ta >> 16; b1 = tb & 0xffffu; t5 = tb >> 16;
+            } else {
+                v = warp_transpose(pv, tc); b0 = warp_transpose(p0, tc); b1 = warp_transpose(p1, tc); t5 = warp_transpose(m5, tc);
             }
-            if (__any_sync(kFull, m5 != 0u)) {
-                const u32 t = warp_transpose(m5, tc);
-                cnt[8] += __popc(t & ~rev);
-                cnt[9] += __popc(t & rev);
-            }
+            const u32 any = b0 | b1;
+            cnt[0] += __popc(v & ~any & ~rev); cnt[1] += __popc(v & ~any & rev);       // A: valid, code 0
+            cnt[2] += __popc(b0 & ~b1 & ~rev); cnt[3] += __popc(b0 & ~b1 & rev);       // C
+            cnt[4] += __popc(b1 & ~b0 & ~rev); cnt[5] += __popc(b1 & ~b0 & rev);       // G
+            cnt[6] += __popc(b0 & b1 & ~rev); cnt[7] += __popc(b0 & b1 & rev);         // T
+            cnt[8] += __popc(t5 & ~rev); cnt[9] += __popc(t5 & rev);
         }
         if (m_after) break;
     }
@@ -989,7 +1018,8 @@ k_pileup(PileupArgs a, int batch_reads) {
     uint8_t *s_wbuf = s_mask + kMaskBytes;                                              // [warps][kWarpBuf + slack]
     for (int e = threadIdx.x; e < kSplitChunks * kAccWords; e += blockDim.x) s_acc[e] = 0;
     const int lane = lane_id(), wid = threadIdx.x >> 5;
-    const u32 mask_addr = (u32)__cvta_generic_to_shared(s_mask);
+    u32 mask_addr = (u32)__cvta_generic_to_shared(s_mask);
+    asm volatile("" : "+r"(mask_addr));                      // kept in a register: recomputing it costs S2R + 4 ALU ops per use
     const u32 wbuf_addr = (u32)__cvta_generic_to_shared(s_wbuf) + (u32)wid * (kWarpBuf + kWarpBufSlack);
     const int n_units = *a.n_units;
     const QualGe qg = make_qual_ge(a.min_baseq);

@@ -42,8 +42,12 @@ int main() {
             const u32 nib = (i & 1) ? (byte & 15) : (byte >> 4);
             for (int x = 0; x < 4; x++) if (nib == (1u << x)) want[x] |= 1u << (24 + i);
         }
-        const Eq8 e = seq_eq8_top(s);
-        if (e.a != want[0] || e.c != want[1] || e.g != want[2] || e.t != want[3]) { printf("seq_eq8_top mismatch %08x\n", s); bad++; }
+        const Planes8 e = seq_planes8_top(s);
+        const u32 v = want[0] | want[1] | want[2] | want[3];
+        if (e.v != v || (e.b0 & v) != (want[1] | want[3]) || (e.b1 & v) != (want[2] | want[3])) { printf("seq_planes8_top mismatch %08x\n", s); bad++; }
+        u32 back[4];
+        planes_to_bases(e.v, e.b0 & e.v, e.b1 & e.v, back);
+        for (int x = 0; x < 4; x++) if (back[x] != want[x]) { printf("planes_to_bases mismatch %08x\n", s); bad++; break; }
     }
     // bit_range / funnel_r
     for (int lo = -40; lo <= 40; lo++) for (int hi = -40; hi <= 72; hi++) {
@@ -60,7 +64,10 @@ int main() {
         u32 x[32], y[32], org[32];
         for (int l = 0; l < 32; l++) org[l] = x[l] = rnd() & ((it % 3) ? 0xffffffffu : rnd());
         for (int j = 16; j >= 1; j >>= 1) {
-            for (int l = 0; l < 32; l++) y[l] = transpose_stage(x[l], x[l ^ j], transpose_keep(l, j), transpose_amt(l, j));
+            for (int l = 0; l < 32; l++) {
+                y[l] = transpose_stage(x[l], x[l ^ j], transpose_keep(l, j), transpose_amt(l, j));
+                if (j >= 8 && transpose_stage_bytes(x[l], x[l ^ j], transpose_sel(l, j)) != y[l]) { printf("transpose_stage_bytes j=%d lane=%d\n", j, l); bad++; }
+            }
             memcpy(x, y, sizeof(x));
         }
         for (int p = 0; p < 32; p++) for (int r = 0; r < 32; r++)

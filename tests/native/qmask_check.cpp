@@ -49,11 +49,18 @@ int main() {
             const u32 nibv = (q & 1) ? (seqc[q >> 1] & 15) : (seqc[q >> 1] >> 4);
             for (int x = 0; x < 4; x++) if (nibv == (1u << x)) want[4 * (q >> 5) + x] |= 1u << (q & 31);
         }
-        if (memcmp(want.data(), buf.data() + out, 16 * nq)) { printf("build_query_masks mismatch L=%d d=%d minq=%d ncig=%d\n", L, d, minq, ncig); bad++; break; }
+        std::vector<u32> planes(4 * nq, 0);                  // V, B0, B1, 0 per group of 32 bases
+        for (int w = 0; w < nq; w++) {
+            planes[4 * w] = want[4 * w] | want[4 * w + 1] | want[4 * w + 2] | want[4 * w + 3];
+            planes[4 * w + 1] = want[4 * w + 1] | want[4 * w + 3];
+            planes[4 * w + 2] = want[4 * w + 2] | want[4 * w + 3];
+        }
+        if (memcmp(planes.data(), buf.data() + out, 16 * nq)) { printf("build_query_masks mismatch L=%d d=%d minq=%d ncig=%d\n", L, d, minq, ncig); bad++; break; }
         for (int k = 0; k < 8; k++) {
             const int qb = (int)(rnd() % (L + 100)) - 50;
-            u32 got[4];
-            query_window(mem, out, nq, qb, got);
+            u32 got3[3], got[4];
+            query_window(mem, out, nq, qb, got3);
+            planes_to_bases(got3[0], got3[1], got3[2], got);
             for (int x = 0; x < 4; x++) {
                 u32 w = 0;
                 for (int b = 0; b < 32; b++) { const int q = qb + b; if (q >= 0 && q < 32 * nq && ((want[4 * (q >> 5) + x] >> (q & 31)) & 1)) w |= 1u << b; }
