@@ -821,9 +821,10 @@ __device__ __forceinline__ void stage_reads(const PileupArgs &a, const ReadRec *
 }
 
 // Counts of chunk `ch` of the unit from a batch of nb reads (g_rec[0..nb), the first `ns` with a record in
-// shared memory), part `part` of `nparts`: lane = position on return. `first` is the first read of the batch
-// that can reach the chunk; `first_batch` is set for the batch that holds the unit's leftmost reads.
-__device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un, const ReadRec *g_rec, const ReadRec *s_rec,
+// shared memory, below the plane slots at mask_addr), part `part` of `nparts`: lane = position on return.
+// `first` is the first read of the batch that can reach the chunk; `first_batch` is set for the batch that holds
+// the unit's leftmost reads.
+__device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un, const ReadRec *g_rec,
                                             u32 mask_addr, int first, bool first_batch, int nb, int ns, int ch, int part,
                                             int nparts, int lane, int q_lo, const TransposeConst &tc, u32 (&cnt)[10], bool &extent_err) {
     const SharedMem smem;
@@ -1101,7 +1102,7 @@ k_pileup(PileupArgs a, int batch_reads) {
                 for (int item = wid; item < nseg * nparts; item += kWarpsPerCta) {
                     const int chl = item >> part_shift, part = item & (nparts - 1);
                     u32 cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // 8 base x strand counters, Tn5 fwd / rev; lane = position
-                    count_chunk(a, un, g_rec, s_rec, mask_addr, s_first[chl], rb == 0 && un.t0 == un0.t0, nb, ns, cs + chl, part, nparts, lane, q_lo, tc, cnt, extent_err);
+                    count_chunk(a, un, g_rec, mask_addr, s_first[chl], rb == 0 && un.t0 == un0.t0, nb, ns, cs + chl, part, nparts, lane, q_lo, tc, cnt, extent_err);
                     if (deep) {
 #pragma unroll
                         for (int k = 0; k < 10; k++) if (cnt[k]) atomicAdd(&s_acc[chl * kAccWords + k * 32 + lane], cnt[k]);
