@@ -611,17 +611,19 @@ __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk
 // Stages 3-6 as a bit-plane gather. One CTA per unit (cell, position tile):
 //   phase A every warp takes 32 reads of the unit at a time, one per lane: record from global memory, the
 //           cigar|seq|qual blob through a small per-warp staging buffer (cp.async, L2 -> shared, no L1
-//           pollution), then SEQ/QUAL turned into four bit masks in query coordinates (bitplane.cuh:
-//           base == A/C/G/T, base quality, distance-from-end window; pileup.py:67-86), word-parallel; only the
-//           masks (16 bytes per 32 bases) and the record stay in shared memory. The declared extent is verified
-//           and the per-chunk "first candidate" table is filled in the same pass; warps run independently.
+//           pollution), then SEQ/QUAL turned into three bit planes in query coordinates (bitplane.cuh: V =
+//           base is A/C/G/T, base quality, distance-from-end window, pileup.py:67-86; B0, B1 = the two bits of
+//           the base code), word-parallel; only the planes (16 bytes per 32 bases) and the record stay in shared
+//           memory. The declared extent is verified and the per-chunk "first candidate" table is filled in the
+//           same pass; warps run independently.
 //   phase B the warps take chunks of 32 positions. The candidate reads of a chunk are those starting in
 //           (chunk - extent, chunk + 32); 32 candidates at a time, one per lane: a read with one aligned block
-//           over all of SEQ cuts the 32-bit window at query offset chunk - start out of its masks, any other
-//           read walks its CIGAR (pileup.py:52-95) and ORs the windows of its blocks; a 32x32 bit transpose
-//           across the warp turns "lane = read" into "lane = position", and two popcounts per base (forward /
-//           reverse reads) add up the eight base x strand counters in registers; the Tn5 sites
-//           (pileup.py:43-50) travel as a fifth mask. Nothing is shared between warps, so there are no atomics
+//           over all of SEQ cuts the 32-bit window at query offset chunk - start out of its planes, any other
+//           read walks its CIGAR (pileup.py:52-95) and ORs the windows of its blocks; 32x32 bit transposes
+//           across the warp turn "lane = read" into "lane = position" for the four bit matrices of the round
+//           (V, B0, B1 and the Tn5 sites, pileup.py:43-50; one or two transposes when the candidates fit 8 or
+//           16 lanes), and one LOP3 + popcount per base and strand adds up the ten counters in registers.
+//           Nothing is shared between warps, so there are no atomics
 //           on counters; when the chunk's reads are exhausted the counts are final and the strand-bias filter,
 //           coverage, Tn5 gating (pileup.py:128-154) and the depth statistics are applied in registers and the
 //           11 planes are written once.
