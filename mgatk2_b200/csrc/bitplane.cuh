@@ -151,6 +151,37 @@ MG_HD u32 transpose_sel(int lane, int j) {              // j = 16 or 8
 }
 MG_HD u32 transpose_stage_bytes(u32 mine, u32 other, u32 sel) { return byte_perm(mine, other, sel); }
 
+// ---- one round of phase B: four bit matrices (V, B0, B1, Tn5 site; row = read = lane) through as few transposes as
+// possible. When the candidate reads sit in lanes 0..7 the four matrices share ONE transpose: lanes 8..15 carry the B0
+// rows of lanes 0..7, lanes 16..23 their B1 rows, lanes 24..31 their Tn5 rows (s0, s1, s5 = those rows fetched from lane
+// & 7); after the transpose every byte of a lane's word is the column of one matrix. With candidates in lanes 0..15 two
+// transposes carry (V | B0) and (B1 | Tn5) in their half words.
+MG_HD u32 quarter_row(int lane, u32 v, u32 s0, u32 s1, u32 s5) { return lane < 16 ? (lane < 8 ? v : s0) : (lane < 24 ? s1 : s5); }
+MG_HD void quarter_columns(u32 t, u32 &v, u32 &b0, u32 &b1, u32 &t5) {
+    v = t & 0xffu; b0 = byte_perm(t, 0u, 0x4441); b1 = byte_perm(t, 0u, 0x4442); t5 = t >> 24;
+}
+MG_HD u32 half_row(int lane, u32 mine, u32 from_lane_xor_16) { return lane < 16 ? mine : from_lane_xor_16; }
+MG_HD void half_columns(u32 ta, u32 tb, u32 &v, u32 &b0, u32 &b1, u32 &t5) {
+    v = ta & 0xffffu; b0 = ta >> 16; b1 = tb & 0xffffu; t5 = tb >> 16;
+}
+// columns (bit r = read r) -> the ten counters of a position: A, C, G, T x (forward, reverse), Tn5 forward / reverse.
+// `rev` = reads on the reverse strand (pileup.py:88); b0, b1 lie inside v.
+MG_HD u32 popc32(u32 x) {
+#if defined(__CUDA_ARCH__)
+    return (u32)__popc(x);
+#else
+    return (u32)__builtin_popcount(x);
+#endif
+}
+MG_HD void count_columns(u32 v, u32 b0, u32 b1, u32 t5, u32 rev, u32 (&cnt)[10]) {
+    const u32 any = b0 | b1;
+    cnt[0] += popc32(v & ~any & ~rev); cnt[1] += popc32(v & ~any & rev);       // A: valid, code 0
+    cnt[2] += popc32(b0 & ~b1 & ~rev); cnt[3] += popc32(b0 & ~b1 & rev);       // C
+    cnt[4] += popc32(b1 & ~b0 & ~rev); cnt[5] += popc32(b1 & ~b0 & rev);       // G
+    cnt[6] += popc32(b0 & b1 & ~rev); cnt[7] += popc32(b0 & b1 & rev);         // T
+    cnt[8] += popc32(t5 & ~rev); cnt[9] += popc32(t5 & rev);
+}
+
 }  // namespace mgatk
 
 // ---------------------------------------------------------------------------------------------

@@ -910,23 +910,16 @@ __device__ __forceinline__ void count_chunk(const PileupArgs &a, const Unit &un,
             if (cands <= 0xffu) {
                 const int src = lane & 7;
                 const u32 s0 = __shfl_sync(kFull, p0, src), s1 = __shfl_sync(kFull, p1, src), s5 = __shfl_sync(kFull, m5, src);
-                const u32 x = lane < 16 ? (lane < 8 ? pv : s0) : (lane < 24 ? s1 : s5);
-                const u32 t = warp_transpose(x, tc);
-                v = t & 0xffu; b0 = __byte_perm(t, 0u, 0x4441); b1 = __byte_perm(t, 0u, 0x4442); t5 = t >> 24;
+                quarter_columns(warp_transpose(quarter_row(lane, pv, s0, s1, s5), tc), v, b0, b1, t5);
             } else if (cands <= 0xffffu) {
                 const u32 s0 = __shfl_xor_sync(kFull, p0, 16), s5 = __shfl_xor_sync(kFull, m5, 16);
-                const u32 ta = warp_transpose(lane < 16 ? pv : s0, tc);
-                const u32 tb = warp_transpose(lane < 16 ? p1 : s5, tc);
-                v = ta & 0xffffu; b0 = ta >> 16; b1 = tb & 0xffffu; t5 = tb >> 16;
+                const u32 ta = warp_transpose(half_row(lane, pv, s0), tc);
+                const u32 tb = warp_transpose(half_row(lane, p1, s5), tc);
+                half_columns(ta, tb, v, b0, b1, t5);
             } else {
                 v = warp_transpose(pv, tc); b0 = warp_transpose(p0, tc); b1 = warp_transpose(p1, tc); t5 = warp_transpose(m5, tc);
             }
-            const u32 any = b0 | b1;
-            cnt[0] += __popc(v & ~any & ~rev); cnt[1] += __popc(v & ~any & rev);       // A: valid, code 0
-            cnt[2] += __popc(b0 & ~b1 & ~rev); cnt[3] += __popc(b0 & ~b1 & rev);       // C
-            cnt[4] += __popc(b1 & ~b0 & ~rev); cnt[5] += __popc(b1 & ~b0 & rev);       // G
-            cnt[6] += __popc(b0 & b1 & ~rev); cnt[7] += __popc(b0 & b1 & rev);         // T
-            cnt[8] += __popc(t5 & ~rev); cnt[9] += __popc(t5 & rev);
+            count_columns(v, b0, b1, t5, rev, cnt);
         }
         if (m_after) break;
     }

@@ -2,7 +2,8 @@
 
 The helpers are plain integer arithmetic and compile for the host: two small C++ programs compare them with the
 per-base rule of the reference (pileup.py:67-86) — every int8 quality against every threshold, random SEQ words,
-the 32x32 warp transpose (lanes simulated), and whole reads through build_query_masks / query_window."""
+the 32x32 warp transpose (lanes simulated), whole reads through build_query_masks / query_window, and whole phase-B
+rounds (one, two or four transposes for the four bit matrices of up to 32 candidate reads) against the obvious loop."""
 import os
 import shutil
 import subprocess
@@ -12,7 +13,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("prog", ["bitplane_check", "qmask_check"])
+@pytest.mark.parametrize("prog", ["bitplane_check", "qmask_check", "round_check"])
 def test_bitplane_helpers_on_host(prog, tmp_path):
     gxx = shutil.which("g++")
     assert gxx, "g++ is part of the image"
