@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <stddef.h>
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -22,6 +23,7 @@
 #include "../../include/mgatk2_bamio.h"
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -55,6 +57,75 @@ struct Bytes {                                                     // growable b
     void drop_front(size_t k) { memmove(p, p + k, n - k); n -= k; }
 };
 
+// growable array that is never value-initialised: its pages are first touched by the decoding threads, not by a
+// zero fill on the calling thread (which used to cost more than the decode itself)
+template <class T> struct Arr {
+    T *p = nullptr; size_t n = 0, cap = 0;
+    Arr() = default;
+    Arr(const Arr &) = delete;
+    Arr &operator=(const Arr &) = delete;
+    ~Arr() { free(p); }
+    bool resize(size_t want) {
+        if (want > cap) {
+            size_t c = cap ? cap : (size_t)1 << 16;
+            while (c < want) c += c / 2;
+            T *q = (T *)realloc(p, c * sizeof(T));       // large blocks move by mremap, not by copying
+            if (!q) return false;
+            p = q; cap = c;
+        }
+        n = want;
+        return true;
+    }
+    void clear() { n = 0; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+};
+
+// distinct tag values of one thread: open addressing on a 64-bit hash, no std::string per record
+struct TagTable {
+    std::vector<int32_t> slot;                       // id + 1, 0 = empty
+    std::vector<uint64_t> hash;
+    std::vector<std::string> names;                  // first-appearance order
+    size_t mask = 0;
+    static uint64_t hash_of(const char *z, size_t n) {
+        uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)n;
+        size_t i = 0;
+        for (; i + 8 <= n; i += 8) { uint64_t w; memcpy(&w, z + i, 8); h = (h ^ w) * 0x9e3779b97f4a7c15ull; h ^= h >> 29; }
+        uint64_t w = 0;
+        if (i < n) memcpy(&w, z + i, n - i);
+        h = (h ^ w) * 0x9e3779b97f4a7c15ull;
+        return h ^ (h >> 32);
+    }
+    void rehash(size_t cap) {
+        slot.assign(cap, 0); hash.assign(cap, 0); mask = cap - 1;
+        for (size_t id = 0; id < names.size(); id++) {
+            const uint64_t h = hash_of(names[id].data(), names[id].size());
+            size_t k = (size_t)h & mask;
+            while (slot[k]) k = (k + 1) & mask;
+            slot[k] = (int32_t)id + 1; hash[k] = h;
+        }
+    }
+    int32_t get(const char *z, size_t n) {
+        if (names.size() * 2 >= slot.size()) rehash(slot.empty() ? 1024 : slot.size() * 4);
+        const uint64_t h = hash_of(z, n);
+        size_t k = (size_t)h & mask;
+        while (slot[k]) {
+            if (hash[k] == h) {
+                const std::string &s = names[(size_t)slot[k] - 1];
+                if (s.size() == n && memcmp(s.data(), z, n) == 0) return slot[k] - 1;
+            }
+            k = (k + 1) & mask;
+        }
+        names.emplace_back(z, n);
+        slot[k] = (int32_t)names.size(); hash[k] = h;
+        return (int32_t)names.size() - 1;
+    }
+};
+
 }  // namespace
 
 struct mgatk_bam {
@@ -67,11 +138,11 @@ struct mgatk_bam {
     size_t first_record_coff = 0;       // BGZF block that holds the first alignment record
     uint32_t first_record_uoff = 0;
     // decoded records of the last fetch
-    std::vector<int32_t> pos, tlen, bc_id;
-    std::vector<uint16_t> flag, l_seq, n_cigar;
-    std::vector<uint8_t> mapq, qual_missing;
-    std::vector<uint32_t> blob_off;
-    std::vector<uint8_t> blob;
+    Arr<int32_t> pos, tlen, bc_id;
+    Arr<uint16_t> flag, l_seq, n_cigar;
+    Arr<uint8_t> mapq, qual_missing;
+    Arr<uint32_t> blob_off;
+    Arr<uint8_t> blob;
     std::vector<std::string> barcodes;  // distinct tag values in order of first appearance
     std::unordered_map<std::string, int32_t> barcode_ids;
 };
@@ -342,7 +413,11 @@ int mgatk_bam_fetch(mgatk_bam *h, int ref_id, const char *tag, int n_threads, in
     struct Loc { size_t off; uint32_t bs; size_t blob_at; };      // record body in s, its size, its place in the blob
     std::vector<Loc> locs;
     const int T = std::max(1, n_threads);
+    const bool timing = getenv("MGATK_BAM_TIMING") != nullptr;          // phase times on stderr (tools/bench_bamio.py)
+    double t_inflate = 0, t_scan = 0, t_decode = 0, t_merge = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     while (!done) {
+        double tp = now();
         // ---- inflate the next batch of blocks (in parallel) ----
         if (cur > 0) { s.drop_front(cur); cur = 0; }
         const size_t before = s.size();
@@ -353,6 +428,7 @@ int mgatk_bam_fetch(mgatk_bam *h, int ref_id, const char *tag, int n_threads, in
             if (s.size() - cur == 0) break;      // clean end of file
             return fail(h, 2, "truncated BAM record at end of file");
         }
+        t_inflate += now() - tp; tp = now();
         // ---- scan record borders (sequential, a few loads per record) ----
         locs.clear();
         size_t blob_at = h->blob.size();
@@ -375,17 +451,18 @@ int mgatk_bam_fetch(mgatk_bam *h, int ref_id, const char *tag, int n_threads, in
             blob_at += (nbytes + 15) & ~(size_t)15;
             if (max_records >= 0 && (int64_t)(h->pos.size() + locs.size()) >= max_records) { done = true; break; }
         }
+        t_scan += now() - tp; tp = now();
         if (locs.empty()) continue;
         // ---- decode the records of the batch (in parallel: fields, blob copy, barcode tag) ----
         const size_t n0 = h->pos.size(), k = locs.size();
-        h->pos.resize(n0 + k); h->tlen.resize(n0 + k); h->bc_id.resize(n0 + k); h->flag.resize(n0 + k);
-        h->l_seq.resize(n0 + k); h->n_cigar.resize(n0 + k); h->mapq.resize(n0 + k); h->qual_missing.resize(n0 + k);
-        h->blob_off.resize(n0 + k);
-        h->blob.resize(blob_at, 0);
+        if (!(h->pos.resize(n0 + k) && h->tlen.resize(n0 + k) && h->bc_id.resize(n0 + k) && h->flag.resize(n0 + k) &&
+              h->l_seq.resize(n0 + k) && h->n_cigar.resize(n0 + k) && h->mapq.resize(n0 + k) &&
+              h->qual_missing.resize(n0 + k) && h->blob_off.resize(n0 + k) && h->blob.resize(blob_at)))
+            return fail(h, 2, "out of memory");
         const int nt = (int)std::min<size_t>((size_t)T, (k + 4095) / 4096);
-        std::vector<std::vector<std::string>> local_names(nt);            // distinct tag values per thread, first appearance order
+        std::vector<TagTable> tables(nt);                                 // distinct tag values per thread, first appearance order
         auto work = [&](int t) {
-            std::unordered_map<std::string, int32_t> ids;
+            TagTable &ids = tables[t];
             const size_t i0 = k * (size_t)t / nt, i1 = k * (size_t)(t + 1) / nt;
             for (size_t i = i0; i < i1; i++) {
                 const uint8_t *r = s.data() + locs[i].off;
@@ -400,21 +477,14 @@ int mgatk_bam_fetch(mgatk_bam *h, int ref_id, const char *tag, int n_threads, in
                 h->tlen[n0 + i] = rdi32(r + 28);
                 h->blob_off[n0 + i] = (uint32_t)(locs[i].blob_at / 16);
                 memcpy(h->blob.data() + locs[i].blob_at, blob, nbytes);
+                memset(h->blob.data() + locs[i].blob_at + nbytes, 0, (size_t)(-(ptrdiff_t)nbytes & 15));   // padding to 16 bytes
                 h->qual_missing[n0 + i] = lseq > 0 && blob[4 * (size_t)ncig + (lseq + 1) / 2] == 0xff;
                 bool has;
                 const char *z;
                 size_t zl;
                 find_tag(blob + nbytes, r + locs[i].bs, tag, &has, &z, &zl);
                 int32_t id = has ? -2 : -1;                                 // -1 no tag, -2 tag that is not a string
-                if (z) {
-                    std::string key(z, zl);
-                    auto it = ids.find(key);
-                    if (it == ids.end()) {
-                        id = (int32_t)local_names[t].size();
-                        ids.emplace(key, id);
-                        local_names[t].push_back(std::move(key));
-                    } else id = it->second;
-                }
+                if (z) id = ids.get(z, zl);
                 h->bc_id[n0 + i] = id;                                      // local id, made global below
             }
         };
@@ -424,21 +494,26 @@ int mgatk_bam_fetch(mgatk_bam *h, int ref_id, const char *tag, int n_threads, in
             for (int t = 0; t < nt; t++) th.emplace_back(work, t);
             for (auto &x : th) x.join();
         }
+        t_decode += now() - tp; tp = now();
         // distinct barcodes in order of first appearance in the file: threads own consecutive record ranges
         for (int t = 0; t < nt; t++) {
-            std::vector<int32_t> global(local_names[t].size());
-            for (size_t j = 0; j < local_names[t].size(); j++) {
-                auto it = h->barcode_ids.find(local_names[t][j]);
+            const std::vector<std::string> &names = tables[t].names;
+            std::vector<int32_t> global(names.size());
+            for (size_t j = 0; j < names.size(); j++) {
+                auto it = h->barcode_ids.find(names[j]);
                 if (it == h->barcode_ids.end()) {
                     global[j] = (int32_t)h->barcodes.size();
-                    h->barcode_ids.emplace(local_names[t][j], global[j]);
-                    h->barcodes.push_back(local_names[t][j]);
+                    h->barcode_ids.emplace(names[j], global[j]);
+                    h->barcodes.push_back(names[j]);
                 } else global[j] = it->second;
             }
             const size_t i0 = k * (size_t)t / nt, i1 = k * (size_t)(t + 1) / nt;
             for (size_t i = i0; i < i1; i++) if (h->bc_id[n0 + i] >= 0) h->bc_id[n0 + i] = global[h->bc_id[n0 + i]];
         }
+        t_merge += now() - tp;
     }
+    if (timing) fprintf(stderr, "[bamio] inflate %.3f s, scan %.3f s, decode %.3f s, barcode merge %.3f s (%zu records, %d threads)\n",
+                        t_inflate, t_scan, t_decode, t_merge, h->pos.size(), T);
     return 0;
 }
 

@@ -102,3 +102,35 @@ def test_errors(tmp_path):
     write_bam(q, b, ["A-1"])
     with pytest.raises(BAMReadError):
         read_bam_chrM(q, cfg, {"A-1": 0})
+
+
+def test_many_distinct_barcodes_first_appearance_order(tmp_path):
+    """The tag table of the decoder (open addressing, one per thread, merged in record order): thousands of distinct
+    18-character barcodes, more than one thread, table growth; ids must follow first appearance in the file and the
+    padding bytes between blobs must be zero whatever memory the decoder was handed."""
+    n_cells, n = 6000, 24_000
+    batch = synth_batch(n_cells, n, "atac50", seed=11)
+    rng = np.random.default_rng(5)
+    barcodes = ["".join("ACGT"[k] for k in rng.integers(0, 4, 16)) + "-1" for _ in range(n_cells)]
+    assert len(set(barcodes)) == n_cells
+    cb = [barcodes[int(c)] if c >= 0 else (None if i % 2 else "NNNNNNNNNNNNNNNN-1") for i, c in enumerate(batch.bc_idx)]
+    path = str(tmp_path / "many.bam")
+    write_bam(path, batch, barcodes, cb_strings=cb, block_bytes=30000)
+    with BamFile(path) as bam:
+        for threads in (1, 4):
+            got, names, _ = bam.fetch("chrM", "CB", threads=threads)
+            first = []
+            seen = set()
+            for s in cb:
+                if s is not None and s not in seen:
+                    seen.add(s)
+                    first.append(s)
+            assert names == first
+            idx = {s: k for k, s in enumerate(first)}
+            want = np.array([idx[s] if s is not None else -1 for s in cb], dtype=np.int32)
+            np.testing.assert_array_equal(got.bc_idx, want)
+            sizes = 4 * got.n_cigar.astype(np.int64) + (got.l_seq.astype(np.int64) + 1) // 2 + got.l_seq.astype(np.int64)
+            starts = got.blob_off.astype(np.int64) * 16
+            for s0, sz in zip(starts[:: max(1, n // 500)], sizes[:: max(1, n // 500)]):
+                pad = got.blob[s0 + sz: s0 + (sz + 15) // 16 * 16]
+                assert not pad.any()
