@@ -8,7 +8,7 @@
  *     bam.references                               readers.py:42          -> mgatk_bam_n_refs / _ref_name / _ref_len
  *     bam.fetch(mito_chr) + per-record attributes  readers.py:54-55,87-162; barcode_extraction.py:22-32
  *         reference_start, mapping_quality, flag, template_length, cigartuples, query_sequence,
- *         query_qualities, has_tag / get_tag(barcode_tag)                 -> mgatk_bam_fetch + mgatk_bam_export
+ *         query_qualities, has_tag / get_tag(barcode_tag)                 -> mgatk_bam_fetch + mgatk_bam_export / _detach
  *
  * fetch(contig) semantics kept: every record placed on the contig in file order, unmapped mates placed there
  * included; reference_start = POS (0-based); the cigar|seq|qual region of each record is copied verbatim into the
@@ -52,6 +52,14 @@ int64_t     mgatk_bam_barcode_bytes(const mgatk_bam *h);
 int         mgatk_bam_export(const mgatk_bam *h, int32_t *pos, int32_t *tlen, uint16_t *flag, uint8_t *mapq, int32_t *bc_id,
                              uint16_t *l_seq, uint16_t *n_cigar, uint32_t *blob_off, uint8_t *blob, uint8_t *qual_missing,
                              char *barcode_chars, int64_t *barcode_end);
+
+/* The same hand-over without the copy: the ten record arrays of the last fetch become the caller's (one malloc block
+ * each, exactly n_records / blob_bytes elements; NULL when empty), to be released with mgatk_bam_free(). The handle is
+ * left without records. Writing every record twice costs first-touch page faults that bound the ingest on hosts where
+ * those are slow (virtual machines); arrays[] order: pos, tlen, flag, mapq, bc_id, l_seq, n_cigar, blob_off, blob,
+ * qual_missing. barcode_chars / barcode_end as in mgatk_bam_export. */
+int         mgatk_bam_detach(mgatk_bam *h, void *arrays[10], char *barcode_chars, int64_t *barcode_end);
+void        mgatk_bam_free(void *p);
 
 #ifdef __cplusplus
 }

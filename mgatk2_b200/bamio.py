@@ -9,6 +9,7 @@ distinct values only. `write_bam()` is the inverse (pure Python, zlib): it turns
 from __future__ import annotations
 
 import ctypes
+import weakref
 import os
 import struct
 import subprocess
@@ -25,7 +26,8 @@ SRC_PATH = os.path.join(HERE, "csrc", "bamio.cpp")
 MITO_NAMES = ("chrM", "MT", "M", "chrMT")              # readers.py:43 order
 EXPORTS = ("mgatk_bam_open", "mgatk_bam_close", "mgatk_bam_error", "mgatk_bam_n_refs", "mgatk_bam_ref_name",
            "mgatk_bam_ref_len", "mgatk_bam_coordinate_sorted", "mgatk_bam_fetch", "mgatk_bam_n_records",
-           "mgatk_bam_blob_bytes", "mgatk_bam_n_barcodes", "mgatk_bam_barcode_bytes", "mgatk_bam_export")
+           "mgatk_bam_blob_bytes", "mgatk_bam_n_barcodes", "mgatk_bam_barcode_bytes", "mgatk_bam_export", "mgatk_bam_detach",
+           "mgatk_bam_free")
 _lib = None
 
 
@@ -57,6 +59,9 @@ def load():
             getattr(lib, f).argtypes = [ctypes.c_void_p]
             getattr(lib, f).restype = ctypes.c_int64
         lib.mgatk_bam_export.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 12
+        lib.mgatk_bam_detach.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p * 10), ctypes.c_void_p, ctypes.c_void_p]
+        lib.mgatk_bam_free.argtypes = [ctypes.c_void_p]
+        lib.mgatk_bam_free.restype = None
         _lib = lib
     return _lib
 
@@ -103,21 +108,37 @@ class BamFile:
             raise BAMReadError(self.path, f"Read error: {self.lib.mgatk_bam_error(self.h).decode()}")
         n = int(self.lib.mgatk_bam_n_records(self.h))
         nb, nbc = int(self.lib.mgatk_bam_blob_bytes(self.h)), int(self.lib.mgatk_bam_n_barcodes(self.h))
-        a = dict(pos=np.empty(n, np.int32), tlen=np.empty(n, np.int32), flag=np.empty(n, np.uint16),
-                 mapq=np.empty(n, np.uint8), bc_idx=np.empty(n, np.int32), l_seq=np.empty(n, np.uint16),
-                 n_cigar=np.empty(n, np.uint16), blob_off=np.empty(n, np.uint32), blob=np.empty(nb, np.uint8))
-        qm = np.empty(n, np.uint8)
         chars = np.empty(max(int(self.lib.mgatk_bam_barcode_bytes(self.h)), 1), np.uint8)
         ends = np.empty(max(nbc, 1), np.int64)
         p = lambda x: x.ctypes.data_as(ctypes.c_void_p)
-        self.lib.mgatk_bam_export(self.h, p(a["pos"]), p(a["tlen"]), p(a["flag"]), p(a["mapq"]), p(a["bc_idx"]),
-                                  p(a["l_seq"]), p(a["n_cigar"]), p(a["blob_off"]), p(a["blob"]), p(qm), p(chars), p(ends))
+        # the arrays change hands without a copy (mgatk_bam_detach): numpy views over the library's malloc blocks, freed
+        # when the last view of a block is gone
+        ptrs = (ctypes.c_void_p * 10)()
+        self.lib.mgatk_bam_detach(self.h, ctypes.byref(ptrs), p(chars), p(ends))
+        layout = (("pos", np.int32, n), ("tlen", np.int32, n), ("flag", np.uint16, n), ("mapq", np.uint8, n),
+                  ("bc_idx", np.int32, n), ("l_seq", np.uint16, n), ("n_cigar", np.uint16, n), ("blob_off", np.uint32, n),
+                  ("blob", np.uint8, nb), ("qm", np.uint8, n))
+        a = {}
+        for (name, dt, count), ptr in zip(layout, ptrs):
+            a[name] = _adopt(self.lib, ptr, np.dtype(dt), count)
+        qm = a.pop("qm")
         raw = chars.tobytes()
         barcodes, o = [], 0
         for i in range(nbc):
             barcodes.append(raw[o:int(ends[i])].decode("ascii", "replace"))
             o = int(ends[i])
         return ReadBatch(**a), barcodes, qm.astype(bool)
+
+
+def _adopt(lib, ptr, dtype, count):
+    """numpy array over a malloc block handed over by the library; the block is freed with the last view of it."""
+    if not ptr or count == 0:
+        if ptr:
+            lib.mgatk_bam_free(ptr)
+        return np.empty(0, dtype)
+    buf = (ctypes.c_uint8 * (count * dtype.itemsize)).from_address(ptr)
+    weakref.finalize(buf, lib.mgatk_bam_free, ptr)
+    return np.frombuffer(buf, dtype=dtype)
 
 
 def pick_mito_contig(references) -> str | None:

@@ -77,6 +77,13 @@ template <class T> struct Arr {
         return true;
     }
     void clear() { n = 0; }
+    T *release() {                                   // ownership to the caller, trimmed to size
+        T *q = p;
+        if (q && n < cap) { T *r = (T *)realloc(q, (n ? n : 1) * sizeof(T)); if (r) q = r; }
+        if (q && n == 0) { free(q); q = nullptr; }
+        p = nullptr; n = cap = 0;
+        return q;
+    }
     T *data() { return p; }
     const T *data() const { return p; }
     size_t size() const { return n; }
@@ -547,5 +554,21 @@ int mgatk_bam_export(const mgatk_bam *h, int32_t *pos, int32_t *tlen, uint16_t *
     }
     return 0;
 }
+
+int mgatk_bam_detach(mgatk_bam *h, void *arrays[10], char *barcode_chars, int64_t *barcode_end) {
+    if (!h || !arrays) return 1;
+    arrays[0] = h->pos.release(); arrays[1] = h->tlen.release(); arrays[2] = h->flag.release(); arrays[3] = h->mapq.release();
+    arrays[4] = h->bc_id.release(); arrays[5] = h->l_seq.release(); arrays[6] = h->n_cigar.release();
+    arrays[7] = h->blob_off.release(); arrays[8] = h->blob.release(); arrays[9] = h->qual_missing.release();
+    int64_t o = 0;
+    for (size_t i = 0; i < h->barcodes.size(); i++) {
+        memcpy(barcode_chars + o, h->barcodes[i].data(), h->barcodes[i].size());
+        o += (int64_t)h->barcodes[i].size();
+        barcode_end[i] = o;
+    }
+    return 0;
+}
+
+void mgatk_bam_free(void *p) { free(p); }
 
 }  // extern "C"
