@@ -34,6 +34,12 @@ def build_bamio(force: bool = False) -> str:
     return _b(force)
 
 
+def build_textio(force: bool = False) -> str:
+    """Host-only dense-plane text writer (g++, zlib): csrc/textio.cpp -> libmgatk2_textio.so."""
+    from .textio import build_textio as _b
+    return _b(force)
+
+
 def build_extension(force: bool = False, verbose: bool = False) -> str:
     if force or is_stale():
         cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB, *SOURCES]
