@@ -565,7 +565,7 @@ int mgatk_pileup_host_submit(mgatk_handle *h, const mgatk_params *p, const mgatk
     od.planes = (uint16_t *)sl.planes.p; od.cell_qc = (mgatk_cell_qc *)sl.qc.p; od.stats = (mgatk_stats *)sl.stats.p;
     od.base_totals = (int64_t *)sl.totals.p; od.overflow = o->overflow_capacity ? (mgatk_overflow *)sl.ovf.p : nullptr;
     rc = run_device(h, p, &bd, &od, h->ws.p, ws_bytes, s);
-    if (rc) { cudaStreamSynchronize(s); return rc; }
+    if (rc) { cudaStreamSynchronize(h->s_h2d); cudaStreamSynchronize(s); return rc; }   // nothing of this batch stays in flight
     CU(cudaEventRecord(sl.compute_done, s));
     // download
     CU(cudaStreamWaitEvent(h->s_d2h, sl.compute_done, 0));
