@@ -443,6 +443,12 @@ int mgatk_bam_fetch(mgatk_bam *h, int ref_id, const char *tag, int n_threads, in
             const uint32_t bs = rd32(s.data() + cur);
             const uint8_t *r = s.data() + cur + 4;
             if (bs < 32) return fail(h, 2, "BAM record shorter than its fixed part");
+            // the walk is a chain of dependent loads, one or two cache lines per record: records of a file have
+            // similar sizes, so the headers a few records ahead are fetched on a guess
+            if (cur + 6 * (size_t)(bs + 4) + 64 < s.size()) {
+                __builtin_prefetch(s.data() + cur + 4 * (size_t)(bs + 4));
+                __builtin_prefetch(s.data() + cur + 6 * (size_t)(bs + 4));
+            }
             const int32_t rid = rdi32(r);
             cur += 4 + (size_t)bs;
             if (rid != ref_id) {
