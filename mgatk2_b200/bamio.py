@@ -33,7 +33,8 @@ _lib = None
 
 def build_bamio(force: bool = False) -> str:
     """g++ -O2 -shared -fPIC csrc/bamio.cpp -lz -pthread -> libmgatk2_bamio.so (in-tree, host only)."""
-    stale = not os.path.exists(LIB_PATH) or os.path.getmtime(SRC_PATH) > os.path.getmtime(LIB_PATH)
+    deps = (SRC_PATH, os.path.join(HERE, "csrc", "fast_inflate.h"), os.path.join(HERE, "..", "include", "mgatk2_bamio.h"))
+    stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if force or stale:
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", LIB_PATH, SRC_PATH, "-lz", "-pthread"], check=True)
     return LIB_PATH

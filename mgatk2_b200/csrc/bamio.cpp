@@ -21,8 +21,10 @@
 #include <zlib.h>
 
 #include "../../include/mgatk2_bamio.h"
+#include "fast_inflate.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <string>
 #include <thread>
@@ -177,19 +179,36 @@ bool block_at(const mgatk_bam *h, size_t off, Block *b) {
     return true;
 }
 
+std::atomic<long long> g_blocks_fast{0}, g_blocks_zlib{0};      // blocks decoded by fast_inflate.h / by zlib (MGATK_BAM_TIMING)
+
 bool inflate_block(const mgatk_bam *h, const Block &b, uint8_t *dst) {
     const uint8_t *p = h->map + b.off;
     const uint32_t xlen = rd16(p + 10);
+    const uint8_t *data = p + 12 + xlen;
+    const size_t data_len = b.csize - 12 - xlen - 8;
+    if (b.isize == 0) return true;
+    // own decoder first (fast_inflate.h); the block trailer's CRC-32 decides whether its output stands. The eight
+    // trailer bytes are handed over as slack for the bit reader, they are never part of a valid stream.
+    static const bool use_fast = getenv("MGATK_BAM_ZLIB_ONLY") == nullptr;
+    if (use_fast) {
+        thread_local mgatk_inflate::Tables tables;
+        if (mgatk_inflate::inflate_raw(data, data_len + 8, dst, b.isize, tables) &&
+            (uint32_t)crc32(0L, dst, b.isize) == rd32(data + data_len)) {
+            g_blocks_fast.fetch_add(1, std::memory_order_relaxed);
+            return true;
+        }
+    }
+    g_blocks_zlib.fetch_add(1, std::memory_order_relaxed);
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
     if (inflateInit2(&zs, -15) != Z_OK) return false;
-    zs.next_in = const_cast<Bytef *>(p + 12 + xlen);
-    zs.avail_in = b.csize - 12 - xlen - 8;
+    zs.next_in = const_cast<Bytef *>(data);
+    zs.avail_in = (uInt)data_len;
     zs.next_out = dst;
     zs.avail_out = b.isize;
-    const int rc = b.isize ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+    const int rc = inflate(&zs, Z_FINISH);
     inflateEnd(&zs);
-    return (rc == Z_STREAM_END || (b.isize == 0)) && zs.avail_out == 0;
+    return rc == Z_STREAM_END && zs.avail_out == 0 && (uint32_t)crc32(0L, dst, b.isize) == rd32(data + data_len);
 }
 
 // Inflates consecutive blocks starting at file offset `off` until `want` more bytes are available in `out`
@@ -525,8 +544,9 @@ int mgatk_bam_fetch(mgatk_bam *h, int ref_id, const char *tag, int n_threads, in
         }
         t_merge += now() - tp;
     }
-    if (timing) fprintf(stderr, "[bamio] inflate %.3f s, scan %.3f s, decode %.3f s, barcode merge %.3f s (%zu records, %d threads)\n",
-                        t_inflate, t_scan, t_decode, t_merge, h->pos.size(), T);
+    if (timing) fprintf(stderr, "[bamio] inflate %.3f s, scan %.3f s, decode %.3f s, barcode merge %.3f s (%zu records, %d threads; "
+                        "blocks so far: %lld own decoder, %lld zlib)\n",
+                        t_inflate, t_scan, t_decode, t_merge, h->pos.size(), T, g_blocks_fast.load(), g_blocks_zlib.load());
     return 0;
 }
 
