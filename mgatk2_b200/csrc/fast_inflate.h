@@ -15,6 +15,7 @@ namespace mgatk_inflate {
 
 constexpr int kLitRoot = 11, kDistRoot = 8, kMaxLen = 15;
 constexpr uint32_t kLiteral = 1u << 12, kEndOfBlock = 2u << 12, kSubtable = 4u << 12, kInvalid = 8u << 12;
+constexpr uint32_t kPair = 1u << 8;        // with kLiteral: two literals (value = first | second << 8)
 // entry: bits 0..7 code length (bits to drop), 8..11 extra bits (or subtable bits), 12..15 flags, 16..31 value
 
 struct Tables {
@@ -22,14 +23,15 @@ struct Tables {
     uint32_t dist[(1 << kDistRoot) + 32 * 128];
 };
 
-inline uint32_t reverse_bits(uint32_t v, int n) {
-    uint32_t r = 0;
-    for (int i = 0; i < n; i++) { r = (r << 1) | (v & 1); v >>= 1; }
-    return r;
+struct Rev8 { uint8_t r[256]; Rev8() { for (int i = 0; i < 256; i++) { int v = i, x = 0; for (int b = 0; b < 8; b++) { x = (x << 1) | (v & 1); v >>= 1; } r[i] = (uint8_t)x; } } };
+inline uint32_t reverse_bits(uint32_t v, int n) {          // the low n <= 16 bits of v, reversed
+    static const Rev8 t;
+    return (((uint32_t)t.r[v & 0xff] << 8) | t.r[(v >> 8) & 0xff]) >> (16 - n);
 }
 
 // canonical Huffman code of `n` symbols with lengths lens[] -> lookup table; payload[sym] = value << 16 | extra << 8 | flags
-inline bool build_table(const uint8_t *lens, int n, const uint32_t *payload, uint32_t *table, int root, size_t capacity) {
+inline bool build_table(const uint8_t *lens, int n, const uint32_t *payload, uint32_t *table, int root, size_t capacity,
+                        bool pair_literals = false) {
     int count[kMaxLen + 1] = {0};
     for (int i = 0; i < n; i++) count[lens[i]]++;
     if (count[0] == n) {                                   // no codes at all: every lookup is invalid
@@ -49,11 +51,13 @@ inline bool build_table(const uint8_t *lens, int n, const uint32_t *payload, uin
         for (int len = 1; len <= kMaxLen; len++) { c = (c + (uint32_t)prev) << 1; next_code[len] = c; prev = count[len]; }
     }
     const uint32_t root_mask = (1u << root) - 1u;
-    for (int i = 0; i < (1 << root); i++) table[i] = kInvalid | 1u;
+    if (left > 0) for (int i = 0; i < (1 << root); i++) table[i] = kInvalid | 1u;     // a complete code fills every entry
     // longest code below every root prefix that needs a second level
     uint8_t sub_bits[1 << kLitRoot];
-    memset(sub_bits, 0, sizeof(sub_bits));
-    {
+    int long_codes = 0;
+    for (int len = root + 1; len <= kMaxLen; len++) long_codes += count[len];
+    if (long_codes) memset(sub_bits, 0, (size_t)1 << root);
+    if (long_codes) {
         uint32_t nc[kMaxLen + 2];
         memcpy(nc, next_code, sizeof(nc));
         for (int s = 0; s < n; s++) {
@@ -67,7 +71,7 @@ inline bool build_table(const uint8_t *lens, int n, const uint32_t *payload, uin
         }
     }
     size_t next_sub = (size_t)1 << root;
-    for (uint32_t p = 0; p <= root_mask; p++) {
+    for (uint32_t p = 0; long_codes && p <= root_mask; p++) {
         if (!sub_bits[p]) continue;
         const size_t size = (size_t)1 << sub_bits[p];
         if (next_sub + size > capacity) return false;
@@ -89,6 +93,21 @@ inline bool build_table(const uint8_t *lens, int n, const uint32_t *payload, uin
             const int sb = (int)((head >> 8) & 15);
             const uint32_t e = payload[s] | (uint32_t)(len - root);
             for (uint32_t i = rev >> root; i < (1u << sb); i += 1u << (len - root)) table[start + i] = e;
+        }
+    }
+    if (pair_literals) {
+        // two short literal codes that fit the root bits together decode with one lookup: entry = both bytes, summed
+        // length, kPair. Walking down keeps table[i >> len] (a smaller index) in its single form while it is read.
+        for (uint32_t i = root_mask;; i--) {
+            const uint32_t e = table[i];
+            const int l1 = (int)(e & 0xff);
+            if ((e & kLiteral) && l1 < root) {
+                const uint32_t e2 = table[i >> l1];
+                const int l2 = (int)(e2 & 0xff);
+                if ((e2 & kLiteral) && !(e2 & kPair) && l1 + l2 <= root)
+                    table[i] = kLiteral | kPair | (uint32_t)(l1 + l2) | (e & 0x00ff0000u) | ((e2 & 0x00ff0000u) << 8);
+            }
+            if (i == 0) break;
         }
     }
     return true;
@@ -165,7 +184,7 @@ inline bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t o
             for (int i = 256; i < 280; i++) lens[i] = 7;
             for (int i = 280; i < 288; i++) lens[i] = 8;
             for (int i = 0; i < 32; i++) lens[288 + i] = 5;
-            if (!build_table(lens, 288, pl.lit, t.lit, kLitRoot, sizeof(t.lit) / 4) ||
+            if (!build_table(lens, 288, pl.lit, t.lit, kLitRoot, sizeof(t.lit) / 4, true) ||
                 !build_table(lens + 288, 32, pl.dist, t.dist, kDistRoot, sizeof(t.dist) / 4)) return false;
         } else {                                               // dynamic code
             br.refill();
@@ -208,7 +227,7 @@ inline bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t o
             memset(dl, 0, sizeof(dl));
             memcpy(dl, lens + hlit, (size_t)hdist);
             memset(lens + hlit, 0, sizeof(lens) - (size_t)hlit);
-            if (!build_table(lens, 288, pl.lit, t.lit, kLitRoot, sizeof(t.lit) / 4) ||
+            if (!build_table(lens, 288, pl.lit, t.lit, kLitRoot, sizeof(t.lit) / 4, true) ||
                 !build_table(dl, 32, pl.dist, t.dist, kDistRoot, sizeof(t.dist) / 4)) return false;
         }
         // ---- symbols ----
@@ -220,30 +239,28 @@ inline bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t o
                 e = t.lit[(e >> 16) + br.peek((int)((e >> 8) & 15))];
             }
             if (e & kLiteral) {
-                // fast path: up to three literals per refill (3 x 15 bits < 56)
-                if (o_end - o < 3) {
-                    if (o >= o_end) return false;
-                    br.drop((int)(e & 0xff));
-                    *o++ = (uint8_t)(e >> 16);
-                    if (br.cnt < 0) return false;
-                    continue;
-                }
-                br.drop((int)(e & 0xff));
-                *o++ = (uint8_t)(e >> 16);
-                e = t.lit[br.peek(kLitRoot)];
-                if (e & kLiteral) {
-                    br.drop((int)(e & 0xff));
-                    *o++ = (uint8_t)(e >> 16);
+                if (o_end - o >= 8) {
+                    // up to three lookups (six literals) per refill: 15 + 11 + 11 bits; every store writes two bytes
+#define MGATK_PUT_LITERALS { br.drop((int)(e & 0xff)); o[0] = (uint8_t)(e >> 16); o[1] = (uint8_t)(e >> 24); o += 1 + ((e >> 8) & 1); }
+                    MGATK_PUT_LITERALS
                     e = t.lit[br.peek(kLitRoot)];
                     if (e & kLiteral) {
-                        br.drop((int)(e & 0xff));
-                        *o++ = (uint8_t)(e >> 16);
-                        if (br.cnt < 0) return false;
-                        continue;
+                        MGATK_PUT_LITERALS
+                        e = t.lit[br.peek(kLitRoot)];
+                        if (e & kLiteral) MGATK_PUT_LITERALS
                     }
+#undef MGATK_PUT_LITERALS
+                    if (br.cnt < 0) return false;
+                    continue;                                  // a non-literal entry is decoded after the refill
                 }
+                const int nl = 1 + (int)((e >> 8) & 1);        // last bytes of the output: exact stores
+                if (o_end - o < nl) return false;
+                br.drop((int)(e & 0xff));
+                o[0] = (uint8_t)(e >> 16);
+                if (nl == 2) o[1] = (uint8_t)(e >> 24);
+                o += nl;
                 if (br.cnt < 0) return false;
-                continue;                                      // the non-literal entry is decoded after a refill
+                continue;
             }
             if (e & kInvalid) return false;
             br.drop((int)(e & 0xff));
