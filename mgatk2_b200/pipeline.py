@@ -82,6 +82,7 @@ class MtDNAPipeline:
             logger.error("No reads found for any barcodes!")
             return {}
         n_cells_input = len(reads_by_barcode)
+        t_write = time.time()
         writer = DenseTextWriter(self.output_dir, self.config, self.barcode_list)
         cell_results = CellProcessor(self.config, self.output_dir).process_cells_progressive(reads_by_barcode, writer)
         if not cell_results:
@@ -89,6 +90,7 @@ class MtDNAPipeline:
             return {}
         qc_dir = self.output_dir / "qc"
         writer.finalize(qc_dir)
+        self.timings = dict(getattr(reader, "timings", {}), write_s=time.time() - t_write, total_s=time.time() - start)
         c = self.config
         write_run_summary({                                               # analysis/qc.py:68-93
             "mgatk_version": VERSION, "run_date": datetime.datetime.now().isoformat(), "input_bam": str(self.bam_path),

@@ -105,12 +105,18 @@ class BAMReader:
         return batch
 
     def collect_reads_by_barcode(self):
+        import time
+        self.timings = {}                       # seconds per phase of the last call (tools/bench_pipeline.py)
         try:
+            t0 = time.perf_counter()
             batch = self._load_batch()
             if not batch.is_sorted():
                 raise ValueError("records are not sorted by reference_start")
             params = self.config.to_params(len(self.barcode_list), batch.max_read_extent())
+            self.timings["ingest_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
             res = get_engine(self.device).run_host(batch, params, overflow_capacity=1 << 16)
+            self.timings["gpu_host_abi_s"] = time.perf_counter() - t0
             if res.stats["n_empty_seq"]:
                 raise ValueError("record without SEQ passed the filters")       # readers.py:157 raises here
         except BAMReadError:
