@@ -24,7 +24,8 @@ with tempfile.TemporaryDirectory() as d:
         p = MtDNAPipeline(bam, barcodes, out, PipelineConfig())
         t0 = time.perf_counter(); res = p.run(); t_run = time.perf_counter() - t0
     size = sum(f.stat().st_size for f in (out / "output").iterdir())
-print(f"{cells} cells x {n} records ({os.path.getsize(bam) / 1e6:.0f} MB BAM written by the Python test writer in {t_bam:.0f} s): "
+    bam_mb = os.path.getsize(bam) / 1e6
+print(f"{cells} cells x {n} records ({bam_mb:.0f} MB BAM written by the Python test writer in {t_bam:.0f} s): "
       f"run {t_run:.2f} s = ingest {p.timings['ingest_s']:.2f} + GPU through the host ABI {p.timings['gpu_host_abi_s']:.2f} "
       f"+ text outputs {p.timings['write_s']:.2f} (gzip level {os.environ.get('MGATK_TXT_GZIP_LEVEL', '9')}, {size / 1e6:.0f} MB); "
       f"{res['cells_passed_qc']} cells passed, {n / t_run / 1e6:.2f} M records/s end to end")
