@@ -41,6 +41,12 @@ int         mgatk_bam_coordinate_sorted(const mgatk_bam *h);       /* @HD SO:coo
  * characters (config.barcode_tag). Uses <path>.bai / <stem>.bai for the start offset when present. */
 int         mgatk_bam_fetch(mgatk_bam *h, int ref_id, const char *tag, int n_threads, int64_t max_records);
 
+/* Goes on where a fetch that stopped at max_records left off: the next up to max_records records of the same contig
+ * (0 records once the contig is exhausted). bc_id keeps indexing one table of distinct tag values that grows over the
+ * parts. For inputs larger than host memory: the parts, cut on reference_start borders by the caller
+ * (mgatk2_b200.bamio.iter_bam_chrM), feed the accumulating device path (MGATK_FLAG_ACCUMULATE, include/mgatk2_b200.h). */
+int         mgatk_bam_fetch_more(mgatk_bam *h, int n_threads, int64_t max_records);
+
 int64_t     mgatk_bam_n_records(const mgatk_bam *h);
 int64_t     mgatk_bam_blob_bytes(const mgatk_bam *h);
 int64_t     mgatk_bam_n_barcodes(const mgatk_bam *h);              /* distinct tag values, first-appearance order */

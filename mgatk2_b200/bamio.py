@@ -27,7 +27,7 @@ MITO_NAMES = ("chrM", "MT", "M", "chrMT")              # readers.py:43 order
 EXPORTS = ("mgatk_bam_open", "mgatk_bam_close", "mgatk_bam_error", "mgatk_bam_n_refs", "mgatk_bam_ref_name",
            "mgatk_bam_ref_len", "mgatk_bam_coordinate_sorted", "mgatk_bam_fetch", "mgatk_bam_n_records",
            "mgatk_bam_blob_bytes", "mgatk_bam_n_barcodes", "mgatk_bam_barcode_bytes", "mgatk_bam_export", "mgatk_bam_detach",
-           "mgatk_bam_free")
+           "mgatk_bam_free", "mgatk_bam_fetch_more")
 _lib = None
 
 
@@ -56,6 +56,7 @@ def load():
         lib.mgatk_bam_ref_len.restype = ctypes.c_int64
         lib.mgatk_bam_coordinate_sorted.argtypes = [ctypes.c_void_p]
         lib.mgatk_bam_fetch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int64]
+        lib.mgatk_bam_fetch_more.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64]
         for f in ("mgatk_bam_n_records", "mgatk_bam_blob_bytes", "mgatk_bam_n_barcodes", "mgatk_bam_barcode_bytes"):
             getattr(lib, f).argtypes = [ctypes.c_void_p]
             getattr(lib, f).restype = ctypes.c_int64
@@ -105,6 +106,15 @@ class BamFile:
             raise BAMReadError(self.path, f"barcode tag {tag!r} is not two characters")
         threads = threads or min(16, os.cpu_count() or 1)
         rc = self.lib.mgatk_bam_fetch(self.h, self.references.index(contig), tag.encode(), int(threads), int(max_records))
+        return self._collect(rc)
+
+    def fetch_more(self, threads: int | None = None, max_records: int = -1):
+        """The next part of a fetch that stopped at max_records (same return value; no records when the contig is done).
+        Barcode indices of all parts refer to one growing table, returned in full every time."""
+        threads = threads or min(16, os.cpu_count() or 1)
+        return self._collect(self.lib.mgatk_bam_fetch_more(self.h, int(threads), int(max_records)))
+
+    def _collect(self, rc: int):
         if rc:
             raise BAMReadError(self.path, f"Read error: {self.lib.mgatk_bam_error(self.h).decode()}")
         n = int(self.lib.mgatk_bam_n_records(self.h))
@@ -150,6 +160,57 @@ def pick_mito_contig(references) -> str | None:
     return None
 
 
+def _finish_part(path, config, wl_index, batch, barcodes, qual_missing, first_part: bool):
+    """Whitelist mapping and the per-record refusals of read_bam_chrM for one part of a fetch."""
+    has_tag = batch.bc_idx != -1
+    if first_part and batch.n_records > 1000 and not has_tag[:1001].any():     # readers.py:54-59
+        raise NoBarcodeTagsError(str(path), config.barcode_tag, 1000)
+    if set(wl_index) == {"bulk"}:
+        bc = np.zeros(batch.n_records, np.int32)
+    else:
+        table = np.array([wl_index.get(b, -1) for b in barcodes] + [-1, -1], dtype=np.int32)   # ids -2 / -1 -> -1
+        bc = table[batch.bc_idx] if batch.n_records else np.zeros(0, np.int32)
+    batch.bc_idx = np.ascontiguousarray(bc, dtype=np.int32)
+    ok = ((batch.flag & 0x904) == 0) & (batch.bc_idx >= 0)
+    if (qual_missing & ok).any():                                               # readers.py:158
+        raise BAMReadError(str(path), "Read error: record without base qualities")
+    return batch
+
+
+def iter_bam_chrM(path: str, config, wl_index: dict, max_records: int, threads: int | None = None):
+    """read_bam_chrM in parts of about `max_records` records for inputs that do not fit host memory (BASELINE
+    configs[4]): yields ReadBatches in file order, cut between different reference_start values - all candidates for a
+    duplicate of a read share its start (readers.py:118-150) - which is what `PileupEngine.run_stream` takes. The
+    records of the last start position of a part wait for the next part."""
+    if max_records < 1:
+        raise ValueError("max_records must be positive")
+    with BamFile(path) as bam:
+        mito = pick_mito_contig(bam.references)
+        if mito is None:
+            raise NoChrMReadsError(str(path), bam.references)
+        part = bam.fetch(mito, config.barcode_tag, threads, max_records)
+        first, carry = True, None
+        while True:
+            batch, barcodes, qm = part
+            got = batch.n_records
+            batch = _finish_part(path, config, wl_index, batch, barcodes, qm, first)
+            first = False
+            merged = batch if carry is None else ReadBatch.concat([carry, batch])
+            if got < max_records:                      # the contig is exhausted
+                if merged.n_records:
+                    yield merged
+                return
+            if not merged.is_sorted():
+                raise BAMReadError(str(path), "Read error: records are not sorted by reference_start")
+            k = int(np.searchsorted(merged.pos, merged.pos[-1], side="left"))
+            if k > 0:
+                yield merged.slice(0, k)
+                carry = merged.slice(k, merged.n_records)
+            else:
+                carry = merged                         # one start position so far: keep collecting
+            part = bam.fetch_more(threads, max_records)
+
+
 def read_bam_chrM(path: str, config, wl_index: dict, threads: int | None = None):
     """BAMReader._validate_bam_file + the fetch loop's record decode (readers.py:35-61,85-111,153-165).
 
@@ -161,21 +222,7 @@ def read_bam_chrM(path: str, config, wl_index: dict, threads: int | None = None)
         if mito is None:
             raise NoChrMReadsError(str(path), bam.references)
         batch, barcodes, qual_missing = bam.fetch(mito, config.barcode_tag, threads)
-    # readers.py:54-59: a file whose first 1001 chrM records carry no barcode tag is refused
-    has_tag = batch.bc_idx != -1
-    if batch.n_records > 1000 and not has_tag[:1001].any():
-        raise NoBarcodeTagsError(str(path), config.barcode_tag, 1000)
-    if set(wl_index) == {"bulk"}:
-        bc = np.zeros(batch.n_records, np.int32)
-    else:
-        table = np.array([wl_index.get(b, -1) for b in barcodes] + [-1, -1], dtype=np.int32)   # ids -2 / -1 -> -1
-        bc = table[batch.bc_idx] if batch.n_records else np.zeros(0, np.int32)
-    batch.bc_idx = np.ascontiguousarray(bc, dtype=np.int32)
-    # readers.py:158: query_qualities is None when QUAL is absent (0xFF); the reference then raises on the first record
-    # it materialises. Refused here for every record that passes the flag / whitelist filter.
-    ok = ((batch.flag & 0x904) == 0) & (batch.bc_idx >= 0)
-    if (qual_missing & ok).any():
-        raise BAMReadError(str(path), "Read error: record without base qualities")
+    batch = _finish_part(path, config, wl_index, batch, barcodes, qual_missing, True)
     return batch, mito
 
 

@@ -138,6 +138,43 @@ class ReadBatch:
         cuts.append(n)
         return [self.take(np.arange(a, b)) for a, b in zip(cuts[:-1], cuts[1:])]
 
+    def slice(self, a: int, b: int) -> "ReadBatch":
+        """Records [a, b) of a batch whose blobs lie in record order (every ingest batch): views, no gather."""
+        a, b = max(0, int(a)), min(self.n_records, int(b))
+        if b <= a:
+            return self.take(np.zeros(0, np.int64))
+        units = self.blob_units()
+        off = self.blob_off.astype(np.int64)
+        if not np.array_equal(off[a + 1: b], off[a: b - 1] + units[a: b - 1]):
+            return self.take(np.arange(a, b))
+        lo, hi = int(off[a]) * 16, (int(off[b - 1]) + int(units[b - 1])) * 16
+        return ReadBatch(pos=self.pos[a:b], tlen=self.tlen[a:b], flag=self.flag[a:b], mapq=self.mapq[a:b],
+                         bc_idx=self.bc_idx[a:b], l_seq=self.l_seq[a:b], n_cigar=self.n_cigar[a:b],
+                         blob_off=(off[a:b] - off[a]).astype(np.uint32), blob=self.blob[lo:hi])
+
+    @staticmethod
+    def concat(parts: list) -> "ReadBatch":
+        """Batches one after the other (blobs packed in record order in every part)."""
+        parts = [p for p in parts if p.n_records]
+        if not parts:
+            return ReadBatch.from_records([])
+        if len(parts) == 1:
+            return parts[0]
+        packed = []
+        for p in parts:
+            units = p.blob_units()
+            off = p.blob_off.astype(np.int64)
+            ok = int(off[0]) == 0 and np.array_equal(off[1:], off[:-1] + units[:-1]) and len(p.blob) == int(units.sum()) * 16
+            packed.append(p if ok else p.take(np.arange(p.n_records)))
+        shift, offs = 0, []
+        for p in packed:
+            offs.append(p.blob_off.astype(np.int64) + shift)
+            shift += len(p.blob) // 16
+        cat = lambda f: np.concatenate([getattr(p, f) for p in packed])
+        return ReadBatch(pos=cat("pos"), tlen=cat("tlen"), flag=cat("flag"), mapq=cat("mapq"), bc_idx=cat("bc_idx"),
+                         l_seq=cat("l_seq"), n_cigar=cat("n_cigar"), blob_off=np.concatenate(offs).astype(np.uint32),
+                         blob=cat("blob"))
+
     def take(self, index: np.ndarray) -> "ReadBatch":
         """Records `index` (kept in the given order) with a freshly packed blob."""
         index = np.asarray(index, dtype=np.int64)

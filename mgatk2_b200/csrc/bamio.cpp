@@ -152,7 +152,15 @@ struct mgatk_bam {
     Arr<uint8_t> mapq, qual_missing;
     Arr<uint32_t> blob_off;
     Arr<uint8_t> blob;
-    std::vector<std::string> barcodes;  // distinct tag values in order of first appearance
+    std::vector<std::string> barcodes;  // distinct tag values in order of first appearance (of the whole fetch, all parts)
+    // where a fetch that stopped at max_records goes on (mgatk_bam_fetch_more)
+    struct Resume {
+        Bytes s;                        // inflated stream; s[cur..] is not scanned yet
+        size_t cur = 0, coff = 0, skip = 0;
+        bool first = true, finished = true;
+        int ref_id = -1;
+        char tag[2] = {0, 0};
+    } resume;
     std::unordered_map<std::string, int32_t> barcode_ids;
 };
 
@@ -418,24 +426,44 @@ int64_t mgatk_bam_ref_len(const mgatk_bam *h, int i) { return (h && i >= 0 && i 
 int mgatk_bam_coordinate_sorted(const mgatk_bam *h) { return h && h->coordinate_sorted; }
 
 // Decode every record placed on ref_id, in file order; at most max_records (< 0: all). tag: two characters.
+static int fetch_run(mgatk_bam *h, int n_threads, int64_t max_records);
+
 int mgatk_bam_fetch(mgatk_bam *h, int ref_id, const char *tag, int n_threads, int64_t max_records) {
     if (!h || !tag || ref_id < 0 || ref_id >= (int)h->refs.size()) return 1;
     h->err.clear();
-    h->pos.clear(); h->tlen.clear(); h->bc_id.clear(); h->flag.clear(); h->l_seq.clear(); h->n_cigar.clear();
-    h->mapq.clear(); h->qual_missing.clear(); h->blob_off.clear(); h->blob.clear(); h->barcodes.clear(); h->barcode_ids.clear();
-    size_t coff = h->first_record_coff;
-    size_t skip = h->first_record_uoff;
+    h->barcodes.clear(); h->barcode_ids.clear();
+    mgatk_bam::Resume &st = h->resume;
+    st.s.n = 0; st.cur = 0; st.first = true; st.finished = false; st.ref_id = ref_id; st.tag[0] = tag[0]; st.tag[1] = tag[1];
+    st.coff = h->first_record_coff;
+    st.skip = h->first_record_uoff;
     uint64_t voff = 0;
     bool empty = false;
     const bool indexed = h->coordinate_sorted && bai_start(h, ref_id, &voff, &empty);
     if (indexed) {
-        if (empty) return 0;
-        coff = (size_t)(voff >> 16);
-        skip = (size_t)(voff & 0xffff);
+        if (empty) { st.finished = true; return fetch_run(h, n_threads, max_records); }
+        st.coff = (size_t)(voff >> 16);
+        st.skip = (size_t)(voff & 0xffff);
     }
-    Bytes s;                                     // inflated stream; s[cur..] is not scanned yet
-    size_t cur = 0;
-    bool first = true, done = false;
+    return fetch_run(h, n_threads, max_records);
+}
+
+int mgatk_bam_fetch_more(mgatk_bam *h, int n_threads, int64_t max_records) {
+    if (!h || h->resume.ref_id < 0) return 1;
+    h->err.clear();
+    return fetch_run(h, n_threads, max_records);
+}
+
+// the records of the next part: up to max_records (all that are left if negative) into the arrays of the handle
+static int fetch_run(mgatk_bam *h, int n_threads, int64_t max_records) {
+    h->pos.clear(); h->tlen.clear(); h->bc_id.clear(); h->flag.clear(); h->l_seq.clear(); h->n_cigar.clear();
+    h->mapq.clear(); h->qual_missing.clear(); h->blob_off.clear(); h->blob.clear();
+    mgatk_bam::Resume &st = h->resume;
+    if (st.finished || max_records == 0) return 0;
+    const int ref_id = st.ref_id;
+    const char *tag = st.tag;
+    Bytes &s = st.s;
+    size_t &cur = st.cur, &coff = st.coff;
+    bool done = false;
     struct Loc { size_t off; uint32_t bs; size_t blob_at; };      // record body in s, its size, its place in the blob
     std::vector<Loc> locs;
     const int T = std::max(1, n_threads);
@@ -444,15 +472,18 @@ int mgatk_bam_fetch(mgatk_bam *h, int ref_id, const char *tag, int n_threads, in
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     while (!done) {
         double tp = now();
-        // ---- inflate the next batch of blocks (in parallel) ----
-        if (cur > 0) { s.drop_front(cur); cur = 0; }
-        const size_t before = s.size();
-        const size_t want = (s.size() - cur >= 4) ? 4 + (size_t)rd32(s.data() + cur) : 0;
-        if (!inflate_more(h, &coff, &s, std::max<size_t>(want, 1u << 25), n_threads, &h->err)) return 2;
-        if (first) { cur = std::min(skip, s.size()); first = false; }
-        if (s.size() == before) {
-            if (s.size() - cur == 0) break;      // clean end of file
-            return fail(h, 2, "truncated BAM record at end of file");
+        // ---- inflate the next batch of blocks (in parallel) unless a whole record is still waiting (resumed fetch) ----
+        if (st.first || s.size() - cur < 4 || s.size() - cur < 4 + (size_t)rd32(s.data() + cur)) {
+            if (cur > 0) { s.drop_front(cur); cur = 0; }
+            const size_t before = s.size();
+            const size_t want = (s.size() - cur >= 4) ? 4 + (size_t)rd32(s.data() + cur) : 0;
+            if (!inflate_more(h, &coff, &s, std::max<size_t>(want, 1u << 25), n_threads, &h->err)) return 2;
+            if (st.first) { cur = std::min(st.skip, s.size()); st.first = false; }
+            if (s.size() == before) {
+                st.finished = true;
+                if (s.size() - cur == 0) break;      // clean end of file
+                return fail(h, 2, "truncated BAM record at end of file");
+            }
         }
         t_inflate += now() - tp; tp = now();
         // ---- scan record borders (sequential, a few loads per record) ----
@@ -471,7 +502,7 @@ int mgatk_bam_fetch(mgatk_bam *h, int ref_id, const char *tag, int n_threads, in
             const int32_t rid = rdi32(r);
             cur += 4 + (size_t)bs;
             if (rid != ref_id) {
-                if (h->coordinate_sorted && (rid > ref_id || rid < 0)) { done = true; break; }    // past the contig
+                if (h->coordinate_sorted && (rid > ref_id || rid < 0)) { done = true; st.finished = true; break; }    // past the contig
                 continue;
             }
             const uint32_t l_name = r[8], ncig = rd16(r + 12), lseq = rd32(r + 16);

@@ -134,3 +134,33 @@ def test_many_distinct_barcodes_first_appearance_order(tmp_path):
             for s0, sz in zip(starts[:: max(1, n // 500)], sizes[:: max(1, n // 500)]):
                 pad = got.blob[s0 + sz: s0 + (sz + 15) // 16 * 16]
                 assert not pad.any()
+
+
+@pytest.mark.parametrize("max_records,index", [(1500, True), (7000, False), (100000, True), (1, True)])
+def test_parts_equal_one_read(tmp_path, max_records, index):
+    """iter_bam_chrM (mgatk_bam_fetch + mgatk_bam_fetch_more): the parts, in order, are the records of the one-shot
+    read; every border lies between two different reference_start values (what the accumulating device path needs);
+    barcode indices stay consistent over the parts although the tag table grows."""
+    from mgatk2_b200.bamio import iter_bam_chrM
+    n_cells, n = 300, 20_000 if max_records > 1 else 300
+    batch = synth_batch(n_cells, n, "stress150", seed=21)
+    barcodes = [f"CELL{i:04d}AAAACCCCGGGG-1" for i in range(n_cells)]
+    path = str(tmp_path / "p.bam")
+    write_bam(path, batch, barcodes, extra=[("chr1", 5), ("chrX", 9), (None, -1)], write_index=index, block_bytes=25000)
+    cfg = PipelineConfig()
+    wl = {b: i for i, b in enumerate(barcodes)}
+    whole, _ = read_bam_chrM(path, cfg, wl, threads=3)
+    parts = list(iter_bam_chrM(path, cfg, wl, max_records=max_records, threads=3))
+    assert sum(p.n_records for p in parts) == whole.n_records
+    if max_records < n:
+        assert len(parts) > 1
+    for a, b in zip(parts[:-1], parts[1:]):
+        assert a.n_records and a.pos[-1] < b.pos[0]
+    joined = ReadBatch.concat(parts)
+    assert_same_records(whole, joined)
+    np.testing.assert_array_equal(joined.bc_idx, whole.bc_idx)
+    np.testing.assert_array_equal(joined.blob, whole.blob)
+    np.testing.assert_array_equal(joined.blob_off, whole.blob_off)
+    # slices of a batch are views with their own offsets
+    s = whole.slice(10, 200)
+    assert s.n_records == 190 and s.blob_off[0] == 0 and s.record(0) == whole.record(10) and s.record(189) == whole.record(199)
