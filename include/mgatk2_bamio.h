@@ -47,6 +47,11 @@ int         mgatk_bam_fetch(mgatk_bam *h, int ref_id, const char *tag, int n_thr
  * (mgatk2_b200.bamio.iter_bam_chrM), feed the accumulating device path (MGATK_FLAG_ACCUMULATE, include/mgatk2_b200.h). */
 int         mgatk_bam_fetch_more(mgatk_bam *h, int n_threads, int64_t max_records);
 
+/* on != 0: a fetch / fetch_more that reaches max_records does not stop there but after the last record with the same
+ * reference_start, so that every part ends on a start border (all candidates for a duplicate of a read share its start,
+ * readers.py:118-150, and the accumulating device path needs no state across parts). Off by default. */
+int         mgatk_bam_align_parts(mgatk_bam *h, int on);
+
 int64_t     mgatk_bam_n_records(const mgatk_bam *h);
 int64_t     mgatk_bam_blob_bytes(const mgatk_bam *h);
 int64_t     mgatk_bam_n_barcodes(const mgatk_bam *h);              /* distinct tag values, first-appearance order */

@@ -27,7 +27,7 @@ MITO_NAMES = ("chrM", "MT", "M", "chrMT")              # readers.py:43 order
 EXPORTS = ("mgatk_bam_open", "mgatk_bam_close", "mgatk_bam_error", "mgatk_bam_n_refs", "mgatk_bam_ref_name",
            "mgatk_bam_ref_len", "mgatk_bam_coordinate_sorted", "mgatk_bam_fetch", "mgatk_bam_n_records",
            "mgatk_bam_blob_bytes", "mgatk_bam_n_barcodes", "mgatk_bam_barcode_bytes", "mgatk_bam_export", "mgatk_bam_detach",
-           "mgatk_bam_free", "mgatk_bam_fetch_more")
+           "mgatk_bam_free", "mgatk_bam_fetch_more", "mgatk_bam_align_parts")
 _lib = None
 
 
@@ -57,6 +57,7 @@ def load():
         lib.mgatk_bam_coordinate_sorted.argtypes = [ctypes.c_void_p]
         lib.mgatk_bam_fetch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int64]
         lib.mgatk_bam_fetch_more.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64]
+        lib.mgatk_bam_align_parts.argtypes = [ctypes.c_void_p, ctypes.c_int]
         for f in ("mgatk_bam_n_records", "mgatk_bam_blob_bytes", "mgatk_bam_n_barcodes", "mgatk_bam_barcode_bytes"):
             getattr(lib, f).argtypes = [ctypes.c_void_p]
             getattr(lib, f).restype = ctypes.c_int64
@@ -180,34 +181,30 @@ def _finish_part(path, config, wl_index, batch, barcodes, qual_missing, first_pa
 def iter_bam_chrM(path: str, config, wl_index: dict, max_records: int, threads: int | None = None):
     """read_bam_chrM in parts of about `max_records` records for inputs that do not fit host memory (BASELINE
     configs[4]): yields ReadBatches in file order, cut between different reference_start values - all candidates for a
-    duplicate of a read share its start (readers.py:118-150) - which is what `PileupEngine.run_stream` takes. The
-    records of the last start position of a part wait for the next part."""
+    duplicate of a read share its start (readers.py:118-150) - which is what `PileupEngine.run_stream` takes. A part
+    holds at least `max_records` records (it runs on to the next start border) unless it is the last."""
     if max_records < 1:
         raise ValueError("max_records must be positive")
     with BamFile(path) as bam:
         mito = pick_mito_contig(bam.references)
         if mito is None:
             raise NoChrMReadsError(str(path), bam.references)
+        bam.lib.mgatk_bam_align_parts(bam.h, 1)        # the reader itself runs every part on to the next start border
         part = bam.fetch(mito, config.barcode_tag, threads, max_records)
-        first, carry = True, None
+        first, last_pos = True, None
         while True:
             batch, barcodes, qm = part
-            got = batch.n_records
+            if batch.n_records == 0:
+                return
             batch = _finish_part(path, config, wl_index, batch, barcodes, qm, first)
             first = False
-            merged = batch if carry is None else ReadBatch.concat([carry, batch])
-            if got < max_records:                      # the contig is exhausted
-                if merged.n_records:
-                    yield merged
-                return
-            if not merged.is_sorted():
+            if not batch.is_sorted() or (last_pos is not None and int(batch.pos[0]) <= last_pos):
                 raise BAMReadError(str(path), "Read error: records are not sorted by reference_start")
-            k = int(np.searchsorted(merged.pos, merged.pos[-1], side="left"))
-            if k > 0:
-                yield merged.slice(0, k)
-                carry = merged.slice(k, merged.n_records)
-            else:
-                carry = merged                         # one start position so far: keep collecting
+            last_pos = int(batch.pos[-1])
+            got = batch.n_records
+            yield batch
+            if got < max_records:                      # the contig is exhausted
+                return
             part = bam.fetch_more(threads, max_records)
 
 

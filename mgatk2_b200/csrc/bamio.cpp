@@ -153,6 +153,7 @@ struct mgatk_bam {
     Arr<uint32_t> blob_off;
     Arr<uint8_t> blob;
     std::vector<std::string> barcodes;  // distinct tag values in order of first appearance (of the whole fetch, all parts)
+    bool align_parts = false;          // mgatk_bam_align_parts: a part that reaches max_records runs on to the next start border
     // where a fetch that stopped at max_records goes on (mgatk_bam_fetch_more)
     struct Resume {
         Bytes s;                        // inflated stream; s[cur..] is not scanned yet
@@ -447,6 +448,12 @@ int mgatk_bam_fetch(mgatk_bam *h, int ref_id, const char *tag, int n_threads, in
     return fetch_run(h, n_threads, max_records);
 }
 
+int mgatk_bam_align_parts(mgatk_bam *h, int on) {
+    if (!h) return 1;
+    h->align_parts = on != 0;
+    return 0;
+}
+
 int mgatk_bam_fetch_more(mgatk_bam *h, int n_threads, int64_t max_records) {
     if (!h || h->resume.ref_id < 0) return 1;
     h->err.clear();
@@ -463,7 +470,8 @@ static int fetch_run(mgatk_bam *h, int n_threads, int64_t max_records) {
     const char *tag = st.tag;
     Bytes &s = st.s;
     size_t &cur = st.cur, &coff = st.coff;
-    bool done = false;
+    bool done = false, limit_hit = false;
+    int32_t limit_pos = 0;
     struct Loc { size_t off; uint32_t bs; size_t blob_at; };      // record body in s, its size, its place in the blob
     std::vector<Loc> locs;
     const int T = std::max(1, n_threads);
@@ -505,6 +513,11 @@ static int fetch_run(mgatk_bam *h, int n_threads, int64_t max_records) {
                 if (h->coordinate_sorted && (rid > ref_id || rid < 0)) { done = true; st.finished = true; break; }    // past the contig
                 continue;
             }
+            if (limit_hit && rdi32(r + 4) != limit_pos) {     // the part ends before the first record of another start
+                cur -= 4 + (size_t)bs;
+                done = true;
+                break;
+            }
             const uint32_t l_name = r[8], ncig = rd16(r + 12), lseq = rd32(r + 16);
             const size_t nbytes = 4 * (size_t)ncig + (lseq + 1) / 2 + lseq;
             if (32 + (size_t)l_name + nbytes > bs) return fail(h, 2, "BAM record fields exceed the record size");
@@ -512,7 +525,11 @@ static int fetch_run(mgatk_bam *h, int n_threads, int64_t max_records) {
             if (blob_at / 16 > 0xffffffffull) return fail(h, 3, "more than 64 GiB of cigar|seq|qual in one fetch");
             locs.push_back({(size_t)(r - s.data()), bs, blob_at});
             blob_at += (nbytes + 15) & ~(size_t)15;
-            if (max_records >= 0 && (int64_t)(h->pos.size() + locs.size()) >= max_records) { done = true; break; }
+            if (!limit_hit && max_records >= 0 && (int64_t)(h->pos.size() + locs.size()) >= max_records) {
+                if (!h->align_parts) { done = true; break; }
+                limit_hit = true;                             // go on while reference_start stays the same
+                limit_pos = rdi32(r + 4);
+            }
         }
         t_scan += now() - tp; tp = now();
         if (locs.empty()) continue;
