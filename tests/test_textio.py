@@ -79,3 +79,50 @@ def test_empty_and_errors(tmp_path):
         write_plane_file(tmp_path / "no_such_dir" / "f.gz", planes, 100, None, 0, 1, [0], ["x"])
     with pytest.raises(ValueError):
         write_plane_file(path, planes, 100, None, 0, 1, [0, 1], ["x"])
+
+
+@pytest.mark.parametrize("name", ["synth_run_default", "synth_tenx"])
+def test_dense_writer_reproduces_reference_files(tmp_path, name):
+    """DenseTextWriter (native rows + gzip members, Python for the small tables) on the result the oracle gives for a
+    golden input: every file the reference's own IncrementalTextWriter wrote for those records (tests/golden, generated
+    by running the reference) comes out byte for byte after gunzip. CPU only: the oracle stands in for the GPU here;
+    tests/test_gpu_dropin.py does the same through the CUDA path."""
+    from mgatk2_b200 import PipelineConfig
+    from mgatk2_b200.engine import N_PLANES, PileupResult
+    from mgatk2_b200.readers import ReadsByBarcode
+    from mgatk2_b200.writers import DenseTextWriter
+    from oracle.oracle import make_params, run_oracle
+    from tests.helpers import load_golden
+    d, batch, barcodes, params = load_golden(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    if "txt_A" not in d:
+        pytest.skip("golden without text outputs")
+    n_cells, P = len(barcodes), 16569
+    ora = run_oracle(batch, make_params(n_cells, params["min_baseq"], params["min_mapq"], params["min_distance_from_end"],
+                                        params["dedup_mode"], params["max_strand_bias"], params["min_reads_per_cell"],
+                                        max_read_extent=batch.max_read_extent()), n_threads=4)
+    planes = np.zeros((n_cells, N_PLANES, pos_pad(P)), np.uint16)
+    for b in range(4):
+        for s in range(2):
+            planes[:, 2 * b + s, :P] = np.minimum(ora.counts[:, :, b, s], 65535)
+    planes[:, 8, :P] = np.minimum(ora.tn5[:, :, 0], 65535)
+    planes[:, 9, :P] = np.minimum(ora.tn5[:, :, 1], 65535)
+    planes[:, 10, :P] = np.minimum(ora.coverage, 65535)
+    assert ora.coverage.max() < 65535                                  # (no overflow list needed for these inputs)
+    res = PileupResult(planes, ora.cell_qc, dict(ora.stats), ora.base_totals, np.zeros(0, OVERFLOW_DTYPE), P,
+                       params["min_reads_per_cell"])
+    ok = ((batch.flag & 0x904) == 0) & (batch.bc_idx >= 0)
+    cells, first = np.unique(batch.bc_idx[ok], return_index=True)      # first-seen order, as BAMReader hands it on
+    order = cells[np.argsort(first, kind="stable")]
+    order = order[ora.cell_qc["n_reads"][order] > 0]
+    cfg = PipelineConfig(min_baseq=params["min_baseq"], min_mapq=params["min_mapq"], max_strand_bias=params["max_strand_bias"],
+                         skip_deduplication=params["dedup_mode"] == 2, use_fragment_length_dedup=params["dedup_mode"] == 0,
+                         min_reads_per_cell=params["min_reads_per_cell"], sequential=True)
+    writer = DenseTextWriter(tmp_path, cfg, barcodes, compresslevel=6)
+    results = writer.write_result(ReadsByBarcode(barcodes, order, res), cfg)
+    writer.finalize(tmp_path / "qc")
+    assert len(results) == int(d["exp_alive"].sum())
+    for base in ("A", "C", "G", "T", "coverage"):
+        assert gzip.open(tmp_path / "output" / f"output.{base}.txt.gz").read() == d[f"txt_{base}"].tobytes(), base
+    assert (tmp_path / "output" / "output.depthTable.txt").read_bytes() == d["txt_depthTable"].tobytes()
+    assert (tmp_path / "output" / "chrM_refAllele.txt").read_bytes() == d["txt_refAllele"].tobytes()
+    assert (tmp_path / "qc" / "cell_stats.csv").read_bytes() == d["txt_cell_stats"].tobytes()
