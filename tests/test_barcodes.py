@@ -1,6 +1,5 @@
 """Whitelist loaders and barcode discovery (mgatk2_b200/barcodes.py) against the reference's rules
 (utils.py:14-69, barcode_extraction.py:12-46, pipeline.py:214-230)."""
-import numpy as np
 import pytest
 
 from mgatk2_b200.bamio import write_bam

@@ -3,7 +3,6 @@ barcode sharding (including a world_size-2 gloo run that recombines per-rank res
 import os
 
 import numpy as np
-import pytest
 
 from mgatk2_b200.batch import ReadBatch
 from mgatk2_b200.sharding import assign_cells, combine_columns, combine_stats, shard_batch
