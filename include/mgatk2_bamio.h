@@ -72,6 +72,12 @@ int         mgatk_bam_export(const mgatk_bam *h, int32_t *pos, int32_t *tlen, ui
 int         mgatk_bam_detach(mgatk_bam *h, void *arrays[10], char *barcode_chars, int64_t *barcode_end);
 void        mgatk_bam_free(void *p);
 
+/* The entry of reference `ref_id` in a .bai file (the same parser the fetch uses for its start offset; the reference
+ * relies on pysam.fetch(contig) -> htslib's index walk, readers.py:85-88): out = { n_ref, real bins, chunks in them,
+ * linear-index intervals, smallest chunk virtual offset (-1: no chunk), pseudo-bin 37450 present, then its four
+ * values ref_beg, ref_end, n_mapped, n_unmapped }. 1 = cannot read, 2 = not a well-formed BAI covering ref_id. */
+int         mgatk_bai_inspect(const char *bai_path, int ref_id, int64_t out[10]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@ MITO_NAMES = ("chrM", "MT", "M", "chrMT")              # readers.py:43 order
 EXPORTS = ("mgatk_bam_open", "mgatk_bam_close", "mgatk_bam_error", "mgatk_bam_n_refs", "mgatk_bam_ref_name",
            "mgatk_bam_ref_len", "mgatk_bam_coordinate_sorted", "mgatk_bam_fetch", "mgatk_bam_n_records",
            "mgatk_bam_blob_bytes", "mgatk_bam_n_barcodes", "mgatk_bam_barcode_bytes", "mgatk_bam_export", "mgatk_bam_detach",
-           "mgatk_bam_free", "mgatk_bam_fetch_more", "mgatk_bam_align_parts")
+           "mgatk_bam_free", "mgatk_bam_fetch_more", "mgatk_bam_align_parts", "mgatk_bai_inspect")
 _lib = None
 
 
@@ -38,6 +38,18 @@ def build_bamio(force: bool = False) -> str:
     if force or stale:
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", LIB_PATH, SRC_PATH, "-lz", "-pthread"], check=True)
     return LIB_PATH
+
+
+def inspect_bai(bai_path: str, ref_id: int) -> dict | None:
+    """Entry of reference `ref_id` in a BAM index, through the parser the native fetch uses for its start offset:
+    counts of references / bins / chunks / linear-index intervals, the smallest chunk virtual offset and — when the
+    index carries htslib's metadata pseudo-bin — the file range of the reference and its mapped / unmapped-placed
+    record counts (what `fetch(contig)` will return, readers.py:85-93). None when the file is not a BAI covering it."""
+    out = (ctypes.c_int64 * 10)()
+    if load().mgatk_bai_inspect(str(bai_path).encode(), int(ref_id), out):
+        return None
+    keys = ("n_ref", "n_bin", "n_chunk", "n_intv", "min_voff", "has_meta", "ref_beg", "ref_end", "n_mapped", "n_unmapped")
+    return dict(zip(keys, (int(v) for v in out)))
 
 
 def load():
@@ -65,6 +77,7 @@ def load():
         lib.mgatk_bam_detach.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p * 10), ctypes.c_void_p, ctypes.c_void_p]
         lib.mgatk_bam_free.argtypes = [ctypes.c_void_p]
         lib.mgatk_bam_free.restype = None
+        lib.mgatk_bai_inspect.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
         _lib = lib
     return _lib
 

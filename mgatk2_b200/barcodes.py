@@ -16,41 +16,51 @@ from .exceptions import InvalidInputError
 logger = logging.getLogger(__name__)
 
 
+def _coerce(text: str):
+    """One metadata cell: empty -> 0, integer text -> int, other numeric text -> float, anything else unchanged."""
+    if not text:
+        return 0
+    for cast in (int, float):
+        try:
+            return cast(text)
+        except ValueError:
+            continue
+    return text
+
+
+_TEXT_COLUMNS = frozenset(("barcode", "excluded_reason"))
+
+
 def load_singlecell_csv(csv_file):
-    """cellranger-atac singlecell.csv -> (barcodes with is__cell_barcode == 1 in file order, column -> values)."""
+    """cellranger-atac singlecell.csv -> (barcodes of the rows with is__cell_barcode == "1" in file order,
+    {column: values of those rows}); numeric columns are coerced cell by cell, `barcode` and `excluded_reason`
+    stay text (utils.py:14-69). (None, None) without a file; InvalidInputError for a missing file, a file without
+    header or without the `is__cell_barcode` column, or no cell row."""
     if csv_file is None:
         return None, None
     try:
-        barcodes, metadata = [], {}
-        with open(csv_file) as f:
-            reader = csv.DictReader(f)
-            headers = reader.fieldnames
-            if headers is None:
+        with open(csv_file, newline="") as f:
+            rows = csv.reader(f)
+            header = next(rows, None)
+            if not header:
                 raise InvalidInputError("CSV file has no headers")
-            if "is__cell_barcode" not in headers:
+            if "is__cell_barcode" not in header:
                 raise InvalidInputError("singlecell.csv missing 'is__cell_barcode' column")
-            for h in headers:
-                metadata[h] = []
-            for row in reader:
-                if row.get("is__cell_barcode") != "1":
-                    continue
-                barcodes.append(row["barcode"])
-                for h in headers:
-                    value = row[h]
-                    if h not in ("barcode", "excluded_reason"):      # utils.py:48-56: int, else float, else the string
-                        try:
-                            value = int(value) if value else 0
-                        except ValueError:
-                            try:
-                                value = float(value) if value else 0.0
-                            except ValueError:
-                                pass
-                    metadata[h].append(value)
-        if not barcodes:
-            raise InvalidInputError(f"No cells found with is__cell_barcode == 1 in {csv_file}")
-        return barcodes, metadata
+            flag_col = header.index("is__cell_barcode")
+            width = len(header)
+            # DictReader semantics: short rows are padded with None, long rows are cut to the header
+            cells = [(r + [None] * width)[:width] for r in rows if r and len(r) > flag_col and r[flag_col] == "1"]
     except FileNotFoundError as e:
         raise InvalidInputError(f"singlecell.csv file not found: {csv_file}") from e
+    if not cells:
+        raise InvalidInputError(f"No cells found with is__cell_barcode == 1 in {csv_file}")
+    columns = list(zip(*cells))
+    metadata = {}
+    for name, column in zip(header, columns):                # a repeated column name keeps its last occurrence ...
+        values = list(column) if name in _TEXT_COLUMNS else [_coerce(v) for v in column]
+        k = header.count(name)                               # ... and, as in the reference, lists every row k times
+        metadata[name] = values if k == 1 else [v for v in values for _ in range(k)]
+    return list(metadata["barcode"]), metadata
 
 
 def extract_barcodes_from_bam(bam_path: str, barcode_tag: str = "CB", mito_chr: str = "chrM", min_reads: int = 10) -> list:

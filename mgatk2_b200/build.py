@@ -9,7 +9,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmgatk2_b200.so")
 SOURCES = ("api.cu",)
-DEPS = ("api.cu", "kernels.cuh", os.path.join("..", "..", "include", "mgatk2_b200.h"))
+def _deps():
+    """Everything the CUDA library is compiled from: every .cu / .cuh under csrc/ and the public header."""
+    names = [f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    return [os.path.join(CSRC, f) for f in names] + [os.path.join(HERE, "..", "include", "mgatk2_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
 
@@ -25,7 +28,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build_bamio(force: bool = False) -> str:

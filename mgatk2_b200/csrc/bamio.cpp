@@ -180,11 +180,13 @@ bool block_at(const mgatk_bam *h, size_t off, Block *b) {
     for (uint32_t x = 0; x + 4 <= xlen;) {                 // extra subfields: SI1 SI2 SLEN data
         const uint8_t *s = p + 12 + x;
         const uint32_t slen = rd16(s + 2);
+        if (4 + slen > xlen - x) return false;             // subfield runs past the extra field
         if (s[0] == 'B' && s[1] == 'C' && slen == 2) bsize = (uint32_t)rd16(s + 4) + 1;
         x += 4 + slen;
     }
-    if (bsize < 12 + xlen + 8 || off + bsize > h->size) return false;
+    if (bsize < 12 + xlen + 8 || off + bsize > h->size) return false;      // bsize <= 65536 by construction (16-bit + 1)
     b->off = off; b->csize = bsize; b->isize = rd32(p + bsize - 4);
+    if (b->isize > 65536u) return false;                   // BGZF: at most 64 KiB of data per block
     return true;
 }
 
@@ -259,45 +261,77 @@ bool inflate_more(const mgatk_bam *h, size_t *off, Bytes *out, size_t want, int 
     return true;
 }
 
+// One reference of a .bai (SAM spec 5.2): smallest chunk offset over its real bins, the chunk and interval counts, and the
+// two chunks of the metadata pseudo-bin 37450 that htslib writes (file range of the reference, mapped / unmapped-placed
+// record counts). `has_meta` is false for indexes written without the pseudo-bin.
+struct BaiRef { int32_t n_ref = 0, n_bin = 0, n_chunk = 0, n_intv = 0; uint64_t min_voff = ~0ull, ref_beg = 0, ref_end = 0, n_mapped = 0, n_unmapped = 0, first_intv = 0; bool has_meta = false; };
+
+bool read_file(const std::string &p, std::vector<uint8_t> &d) {
+    FILE *f = fopen(p.c_str(), "rb");
+    if (!f) return false;
+    uint8_t buf[1 << 16];
+    size_t n;
+    d.clear();
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) d.insert(d.end(), buf, buf + n);
+    fclose(f);
+    return true;
+}
+
+// walks the index up to `ref_id`; false when the bytes are not a well-formed BAI covering that reference
+bool parse_bai(const std::vector<uint8_t> &d, int ref_id, BaiRef *out) {
+    if (d.size() < 8 || memcmp(d.data(), "BAI\1", 4) != 0) return false;
+    size_t o = 4;
+    BaiRef R;
+    R.n_ref = rdi32(d.data() + o); o += 4;
+    if (ref_id < 0 || ref_id >= R.n_ref) return false;
+    for (int r = 0; r <= ref_id; r++) {
+        const bool mine = r == ref_id;
+        if (o + 4 > d.size()) return false;
+        const int32_t n_bin = rdi32(d.data() + o); o += 4;
+        if (n_bin < 0) return false;
+        for (int b = 0; b < n_bin; b++) {
+            if (o + 8 > d.size()) return false;
+            const uint32_t bin = rd32(d.data() + o);
+            const int32_t n_chunk = rdi32(d.data() + o + 4);
+            o += 8;
+            if (n_chunk < 0 || o + 16 * (size_t)n_chunk > d.size()) return false;
+            if (mine) {
+                if (bin == 37450) {                          // metadata pseudo-bin: (ref_beg, ref_end), (n_mapped, n_unmapped)
+                    if (n_chunk == 2) {
+                        R.has_meta = true;
+                        R.ref_beg = rd64(d.data() + o); R.ref_end = rd64(d.data() + o + 8);
+                        R.n_mapped = rd64(d.data() + o + 16); R.n_unmapped = rd64(d.data() + o + 24);
+                    }
+                } else {
+                    R.n_bin++; R.n_chunk += n_chunk;
+                    for (int c = 0; c < n_chunk; c++) R.min_voff = std::min(R.min_voff, rd64(d.data() + o + 16 * (size_t)c));
+                }
+            }
+            o += 16 * (size_t)n_chunk;
+        }
+        if (o + 4 > d.size()) return false;
+        const int32_t n_intv = rdi32(d.data() + o); o += 4;
+        if (n_intv < 0 || o + 8 * (size_t)n_intv > d.size()) return false;
+        if (mine) {
+            R.n_intv = n_intv;
+            for (int i = 0; i < n_intv && !R.first_intv; i++) R.first_intv = rd64(d.data() + o + 8 * (size_t)i);
+        }
+        o += 8 * (size_t)n_intv;
+    }
+    *out = R;
+    return true;
+}
+
 // smallest virtual offset of the chunks of `ref_id` in the .bai next to the BAM; false when there is no usable index
 bool bai_start(const mgatk_bam *h, int ref_id, uint64_t *voff, bool *empty) {
     std::string cand[2] = {h->path + ".bai", h->path};
     if (h->path.size() > 4 && h->path.substr(h->path.size() - 4) == ".bam") cand[1] = h->path.substr(0, h->path.size() - 4) + ".bai";
     for (const std::string &p : cand) {
-        FILE *f = fopen(p.c_str(), "rb");
-        if (!f) continue;
         std::vector<uint8_t> d;
-        uint8_t buf[1 << 16];
-        size_t n;
-        while ((n = fread(buf, 1, sizeof(buf), f)) > 0) d.insert(d.end(), buf, buf + n);
-        fclose(f);
-        if (d.size() < 8 || memcmp(d.data(), "BAI\1", 4) != 0) continue;
-        size_t o = 4;
-        const int32_t n_ref = rdi32(d.data() + o); o += 4;
-        if (ref_id >= n_ref) continue;
-        bool good = true;
-        uint64_t best = ~0ull;
-        for (int r = 0; r <= ref_id && good; r++) {
-            if (o + 4 > d.size()) { good = false; break; }
-            const int32_t n_bin = rdi32(d.data() + o); o += 4;
-            for (int b = 0; b < n_bin && good; b++) {
-                if (o + 8 > d.size()) { good = false; break; }
-                const uint32_t bin = rd32(d.data() + o);
-                const int32_t n_chunk = rdi32(d.data() + o + 4);
-                o += 8;
-                if (n_chunk < 0 || o + 16 * (size_t)n_chunk > d.size()) { good = false; break; }
-                if (r == ref_id && bin != 37450)               // 37450: the metadata pseudo-bin
-                    for (int c = 0; c < n_chunk; c++) best = std::min(best, rd64(d.data() + o + 16 * (size_t)c));
-                o += 16 * (size_t)n_chunk;
-            }
-            if (!good || o + 4 > d.size()) { good = false; break; }
-            const int32_t n_intv = rdi32(d.data() + o); o += 4;
-            if (n_intv < 0 || o + 8 * (size_t)n_intv > d.size()) { good = false; break; }
-            o += 8 * (size_t)n_intv;
-        }
-        if (!good) continue;
-        *empty = best == ~0ull;
-        *voff = best;
+        BaiRef R;
+        if (!read_file(p, d) || !parse_bai(d, ref_id, &R)) continue;
+        *empty = R.min_voff == ~0ull;
+        *voff = R.min_voff;
         return true;
     }
     return false;
@@ -644,5 +678,16 @@ int mgatk_bam_detach(mgatk_bam *h, void *arrays[10], char *barcode_chars, int64_
 }
 
 void mgatk_bam_free(void *p) { free(p); }
+
+int mgatk_bai_inspect(const char *bai_path, int ref_id, int64_t out[10]) {
+    std::vector<uint8_t> d;
+    BaiRef R;
+    if (!bai_path || !out || !read_file(bai_path, d)) return 1;
+    if (!parse_bai(d, ref_id, &R)) return 2;
+    out[0] = R.n_ref; out[1] = R.n_bin; out[2] = R.n_chunk; out[3] = R.n_intv;
+    out[4] = R.min_voff == ~0ull ? -1 : (int64_t)R.min_voff; out[5] = R.has_meta ? 1 : 0;
+    out[6] = (int64_t)R.ref_beg; out[7] = (int64_t)R.ref_end; out[8] = (int64_t)R.n_mapped; out[9] = (int64_t)R.n_unmapped;
+    return 0;
+}
 
 }  // extern "C"

@@ -22,8 +22,15 @@ class BAMReadError(ProcessingError):
         self.bam_path = bam_path
 
 
-class BAMFormatError(BAMReadError):
-    """The file is not a readable BAM (src/core/exceptions.py: raised when pysam cannot open it)."""
+class BAMFormatError(InvalidInputError):
+    """The file is not a readable BAM (src/core/exceptions.py:66-73; raised by readers.py:38-39 when the file cannot
+    be opened). An input error like the reference's, not a `BAMReadError`."""
+
+    def __init__(self, bam_path: str, details: str = ""):
+        message = f"BAM file appears corrupted or is not a valid BAM format: {bam_path}"
+        if details:
+            message += f"\n{details}"
+        super().__init__(message)
 
 
 class NoChrMReadsError(BAMReadError):

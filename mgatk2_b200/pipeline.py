@@ -23,17 +23,14 @@ VERSION = "mgatk2_b200 round 1"
 
 
 def write_run_summary(run_metadata: dict, output_path: Path):
-    """file_io/formats.py:49-57."""
-    with open(output_path, "w") as f:
-        f.write("mgatk2 Run Summary\n")
-        f.write("=" * 20 + "\n")
-        for key, value in run_metadata.items():
-            if key != "parameters":
-                f.write(f"{key}: {value}\n")
-        if "parameters" in run_metadata:
-            f.write("\nParameters:\n")
-            for k, v in run_metadata["parameters"].items():
-                f.write(f"  {k}: {v}\n")
+    """`qc/summary.txt` in the layout of file_io/formats.py:49-57: title, rule, `key: value` lines, then the indented
+    `parameters` block when there is one."""
+    params = run_metadata.get("parameters")
+    lines = ["mgatk2 Run Summary", "=" * 20]
+    lines += [f"{k}: {v}" for k, v in run_metadata.items() if k != "parameters"]
+    if "parameters" in run_metadata:
+        lines += ["", "Parameters:"] + [f"  {k}: {v}" for k, v in params.items()]
+    Path(output_path).write_text("\n".join(lines) + "\n")
 
 
 class MtDNAPipeline:

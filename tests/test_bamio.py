@@ -164,3 +164,41 @@ def test_parts_equal_one_read(tmp_path, max_records, index):
     # slices of a batch are views with their own offsets
     s = whole.slice(10, 200)
     assert s.n_records == 190 and s.blob_off[0] == 0 and s.record(0) == whole.record(10) and s.record(189) == whole.record(199)
+
+
+def test_reference_bai_known_answers():
+    """A pin at the htslib boundary that does not come from this repo's own writer: the index the reference ships next
+    to its (missing) test BAM, `tests/outs/possorted_bam.bam.bai`, copied to tests/golden/reference_files/. samtools
+    wrote it; the native parser must read what SURVEY §4 recovered from it: 194 references, only reference 22 (chrM of
+    the 10x GRCh38 layout) populated, 228 149 mapped + 1 619 unmapped-placed records (= the ~230 k records
+    `fetch("chrM")` returns, readers.py:85-93), records from virtual offset 2959 << 16 (right behind the header) to
+    about 11.6 MB. Cross-checked against a plain struct walk of the same bytes."""
+    import os
+    import struct
+    from mgatk2_b200.bamio import inspect_bai
+    path = os.path.join(os.path.dirname(__file__), "golden", "reference_files", "possorted_bam.bam.bai")
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"BAI\1" and struct.unpack_from("<i", raw, 4)[0] == 194
+    o, populated = 8, {}
+    for r in range(194):                                          # independent walk (SAM spec 5.2)
+        n_bin = struct.unpack_from("<i", raw, o)[0]; o += 4
+        bins = {}
+        for _ in range(n_bin):
+            b, n_chunk = struct.unpack_from("<Ii", raw, o); o += 8
+            bins[b] = [struct.unpack_from("<QQ", raw, o + 16 * c) for c in range(n_chunk)]; o += 16 * n_chunk
+        n_intv = struct.unpack_from("<i", raw, o)[0]; o += 4 + 8 * n_intv
+        if n_bin:
+            populated[r] = (bins, n_intv)
+    assert list(populated) == [22] and struct.unpack_from("<Q", raw, o)[0] == 0 and o + 8 == len(raw)
+    bins, n_intv = populated[22]
+    real = [c for b, cs in bins.items() if b != 37450 for c in cs]
+    got = inspect_bai(path, 22)
+    assert got == dict(n_ref=194, n_bin=3, n_chunk=len(real), n_intv=n_intv, min_voff=min(c[0] for c in real), has_meta=1,
+                       ref_beg=bins[37450][0][0], ref_end=bins[37450][0][1], n_mapped=228149, n_unmapped=1619)
+    assert got["n_chunk"] == 10 and got["n_intv"] == 2
+    assert got["min_voff"] == got["ref_beg"] == 2959 << 16 and got["ref_end"] >> 16 == 11588294
+    for r in (0, 21, 23, 193):                                    # unpopulated references: parsed, no chunk
+        e = inspect_bai(path, r)
+        assert e["n_ref"] == 194 and e["n_bin"] == 0 and e["min_voff"] == -1 and e["has_meta"] == 0
+    assert inspect_bai(path, 194) is None and inspect_bai(path, -1) is None
+    assert inspect_bai(__file__, 0) is None                       # not a BAI

@@ -29,7 +29,7 @@ def test_exports_match_header(lib):
 
 def test_bamio_exports_match_header():
     header = open(os.path.join(ROOT, "include", "mgatk2_bamio.h")).read()
-    declared = set(re.findall(r"\b(mgatk_bam_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(mgatk_ba[mi]_[a-z_]+)\s*\(", header))
     from mgatk2_b200 import bamio
     assert declared == set(bamio.EXPORTS)
     lib = bamio.load()
