@@ -203,7 +203,7 @@ def run_b200(a):
         pinned[name] = torch.empty_like(src, pin_memory=True).copy_(src)
     pbatch = ReadBatch(**{name: pinned[name].numpy() for name, _ in FIELDS})
     dbatch = eng.upload(pbatch, pinned_src=pinned)
-    dout = eng.alloc_device_outputs(a.cells, 16569, batch.n_records)
+    dout = eng.alloc_device_outputs(a.cells, 16569, batch.n_records, max_read_extent=extent)
     torch.cuda.synchronize()
 
     def barrier():

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MGATK_ABI_VERSION 1
+#define MGATK_ABI_VERSION 2
 
 /* ---- status codes -------------------------------------------------------- */
 typedef enum mgatk_status {
@@ -183,8 +183,10 @@ int         mgatk_create(mgatk_handle **out, int device);
 int         mgatk_destroy(mgatk_handle *h);
 const char *mgatk_last_error(const mgatk_handle *h);
 
-/* size of the device workspace the _device entry point needs for a batch shape */
-int64_t     mgatk_workspace_bytes(int64_t n_records, int32_t n_cells);
+/* size of the device workspace the _device entry point needs for a batch shape; max_read_extent as in mgatk_params
+ * (it selects the slot layout: 32 bytes per read up to an extent of 56, 16 + 16 * ceil(extent / 32) bytes beyond, at
+ * most 144). -1 when the shape is outside the limits. */
+int64_t     mgatk_workspace_bytes(int64_t n_records, int32_t n_cells, int32_t max_read_extent);
 
 /* Stages 1-6 on device-resident buffers; enqueues on `stream`, never blocks.
  * After the stream has drained, mgatk_check_stats turns a host copy of

@@ -20,7 +20,7 @@ EXPORTS = (
 N_PLANES = 11
 FLAG_RAW_PILEUP = 1
 FLAG_ACCUMULATE = 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class ParamsC(ctypes.Structure):
@@ -66,7 +66,7 @@ def load():
     lib.mgatk_last_error.restype = ctypes.c_char_p
     lib.mgatk_last_error.argtypes = [ctypes.c_void_p]
     lib.mgatk_workspace_bytes.restype = ctypes.c_int64
-    lib.mgatk_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int32]
+    lib.mgatk_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]
     lib.mgatk_pileup_device.argtypes = [ctypes.c_void_p, ctypes.POINTER(ParamsC), ctypes.POINTER(MgatkBatchC),
                                         ctypes.POINTER(OutputsC), ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     lib.mgatk_check_stats.argtypes = [ctypes.c_void_p]

@@ -8,7 +8,10 @@
 #include <string>
 #include <vector>
 
-#include "kernels.cuh"
+#include "partition.cuh"
+#include "dedup.cuh"
+#include "pileup.cuh"
+#include "epilogue.cuh"
 
 using namespace mgatk;
 
@@ -20,18 +23,31 @@ constexpr int kMaxStages = 16;
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+int env_int(const char *name, int fallback) {
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : fallback;
+}
+
 struct Layout {          // carve-up of the caller's workspace
     int64_t n; int32_t n_cells;
     int nchunks; int64_t chunk; int ngroups;
     int passes, bits[2], shift[2];
-    int unit_reads; int64_t max_units;
-    size_t grp[2];           // grouped records (two generations for a two-digit partition)
-    size_t recs, mat, part, cell_start, unit_start, units, units_overflow, scan_state, scalars, total;
+    SlotFmt fmt;
+    int stage_bytes, cap_reads, unit_reads; int64_t max_units;
+    size_t slots[2];         // two slot arrays: partition output(s) and the compacted reads to pile up
+    size_t mat, part, cell_start, unit_start, units, units_big, scan_state, scalars, total;
     int64_t dedup_blocks;
 };
 
-bool make_layout(int64_t n, int32_t n_cells, Layout &L) {
-    if (n < 0 || n_cells < 0 || n >= (int64_t)0x7fffff00) return false;
+// bytes of one stage of the main pileup kernel (= the slots of one unit) and the reads it holds
+int stage_bytes_for(const SlotFmt &f) {
+    int b = env_int("MGATK_STAGE_BYTES", f.compact ? 16384 : 32768);
+    if (b < 32 * f.bytes) b = 32 * f.bytes;
+    return (b + 127) / 128 * 128;
+}
+
+bool make_layout(int64_t n, int32_t n_cells, int extent, Layout &L) {
+    if (n < 0 || n_cells < 0 || n >= (int64_t)0x7fffff00 || extent < 1) return false;
     L.n = n; L.n_cells = n_cells;
     int64_t nch = (n + 4095) / 4096;
     L.nchunks = (int)(nch < 1 ? 1 : nch > kMaxChunks ? kMaxChunks : nch);
@@ -44,29 +60,31 @@ bool make_layout(int64_t n, int32_t n_cells, Layout &L) {
     L.passes = bits <= kMaxDigitBits ? 1 : 2;
     if (L.passes == 1) { L.bits[0] = bits; L.shift[0] = 0; L.bits[1] = 0; L.shift[1] = 0; }
     else { L.bits[0] = (bits + 1) / 2; L.shift[0] = 0; L.bits[1] = bits - L.bits[0]; L.shift[1] = L.bits[0]; }
-    L.unit_reads = 32;                                   // lower bound: sizes the unit table for any setting
+    L.fmt = slot_format(extent, L.passes);
+    L.stage_bytes = stage_bytes_for(L.fmt);
+    L.cap_reads = L.stage_bytes / L.fmt.bytes;
+    {   // reads per unit: leave room for the reads of the halo and of the chunk the tile border is rounded down to
+        const int v = env_int("MGATK_UNIT_READS", 0);
+        L.unit_reads = v > 0 ? (v < 32 ? 32 : v) : (int)(0.8 * L.cap_reads);
+        if (L.unit_reads < 32) L.unit_reads = 32;
+    }
     L.max_units = (int64_t)n_cells + n / L.unit_reads + 1;
     const int max_bins = 1 << (L.bits[0] > L.bits[1] ? L.bits[0] : L.bits[1]);
     size_t o = 0;
     const size_t cap = (size_t)(n > 0 ? n : 1);
-    for (int gen = 0; gen < 2; gen++) {
-        L.grp[gen] = o; if (gen < L.passes) o += align_up(cap * sizeof(GroupRec));
-    }
-    L.recs = o; o += align_up(cap * sizeof(ReadRec));
+    for (int gen = 0; gen < 2; gen++) { L.slots[gen] = o; o += align_up(cap * (size_t)L.fmt.bytes); }
     L.mat = o; o += align_up((size_t)L.nchunks * max_bins * 4);
     L.part = o; o += align_up((size_t)L.ngroups * max_bins * 4);
     L.cell_start = o; o += align_up(((size_t)n_cells + 1) * 4);
     L.unit_start = o; o += align_up(((size_t)n_cells + 1) * 4);
     L.units = o; o += align_up((size_t)L.max_units * sizeof(Unit));
-    L.units_overflow = o; o += align_up((size_t)L.max_units * sizeof(Unit));
+    L.units_big = o; o += align_up((size_t)L.max_units * sizeof(Unit));
     L.dedup_blocks = (n + kDedupTile - 1) / kDedupTile + 1;
     L.scan_state = o; o += align_up((size_t)L.dedup_blocks * 8);
     L.scalars = o; o += 256;
     L.total = o;
     return true;
 }
-
-GroupRec *grouped_at(char *ws, const Layout &L, int gen) { return (GroupRec *)(ws + L.grp[gen]); }
 
 struct DevBuf { void *p = nullptr; size_t cap = 0; };
 
@@ -136,37 +154,54 @@ void mark(mgatk_handle *h, cudaStream_t s, const char *name) {
     }
 }
 
+// histogram of the pass's digit per chunk and its exclusive scan in (digit, chunk) order
 template <class Src>
-int partition_pass(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout &L, int pass, char *ws,
-                   const int32_t *sorted_pos, u64 *error_bits, int64_t *m_out, GroupRec *dst) {
+int histogram_and_scan(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout &L, int pass, char *ws, int64_t *m_out) {
     const int bins = 1 << L.bits[pass];
     u32 *mat = (u32 *)(ws + L.mat), *part = (u32 *)(ws + L.part);
-    const int grid = L.nchunks;
-    const size_t smem_h = (size_t)bins * 4, smem = scatter_smem_bytes(bins);
-    k_hist<Src><<<grid, kHistThreads, smem_h, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat);
+    k_hist<Src><<<L.nchunks, kHistThreads, (size_t)bins * 4, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat);
     dim3 sg((bins + 255) / 256, L.ngroups);
     k_scan_group_sums<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part);
     k_scan_bases<<<1, 1024, 0, s>>>(part, L.ngroups, bins, m_out);
     k_scan_apply<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part);
-    k_scatter<Src><<<grid, kPartThreads, smem, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, dst, error_bits);
-    h->launches += 5;
+    h->launches += 4;
+    CU(cudaGetLastError());
+    return MGATK_OK;
+}
+
+// bytes of one per-warp blob staging buffer of the scatter: what 32 blobs of the batch's average size need, with headroom
+int warp_buffer_for(const mgatk_batch *b) {
+    const int64_t avg = b->n_records > 0 ? (b->blob_bytes / b->n_records + 15) / 16 * 16 : 80;
+    int64_t w = 32 * (avg > 16 ? avg : 16) * 5 / 4;
+    const int64_t lo = 2560, hi = env_int("MGATK_WBUF_MAX", 10240);
+    w = w < lo ? lo : w > hi ? hi : w;
+    return (int)((w + 127) / 128 * 128);
+}
+
+template <bool kCompact>
+int launch_scatter(mgatk_handle *h, cudaStream_t s, const ScatterArgs &a) {
+    const size_t smem = scatter_smem_bytes(a.bins, a.wbuf, a.words, kCompact);
+    CU(cudaFuncSetAttribute(k_scatter_planes<kCompact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_scatter_planes<kCompact><<<a.nchunks, kPartThreads, smem, s>>>(a);
+    h->launches += 1;
     CU(cudaGetLastError());
     return MGATK_OK;
 }
 
 constexpr int kChrMPpad = (int)MGATK_POS_PAD(16569);    // the plane pitch of chrM is compiled in
 
-template <int kPpad>
-int launch_pileup_t(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, const PileupArgs &a_overflow, int batch_reads) {
-    const size_t smem = pileup_smem_bytes();
-    CU(cudaFuncSetAttribute(k_pileup<kPpad, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(k_pileup<kPpad, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup<kPpad, false>, kThreads, smem));
+template <bool kCompact, int kPpad>
+int launch_pileup_t(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, const PileupArgs &a_big, int stage_bytes) {
+    const size_t smem_main = (size_t)kStages * stage_bytes, smem_big = (size_t)stage_bytes;
+    CU(cudaFuncSetAttribute(k_pileup_main<kCompact, kPpad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_main));
+    CU(cudaFuncSetAttribute(k_pileup_big<kCompact, kPpad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+    int per_sm = 0, per_sm_big = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pileup_main<kCompact, kPpad>, kThreads + 32, smem_main));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_big, k_pileup_big<kCompact, kPpad>, kThreads, smem_big));
     if (per_sm < 1) per_sm = 1;
-    // Tiles with more reads than mask slots (hot spots) are walked in sub-tiles by the kSplit instance. The list is
-    // usually short: the kernel goes first on a side stream, most of its CTAs leave at once and the CTAs of the main
-    // kernel take their place, so both run side by side (they write disjoint tiles).
+    if (per_sm_big < 1) per_sm_big = 1;
+    // The list of big units is usually short or empty: its kernel goes first on a side stream, most of its CTAs leave at
+    // once and the CTAs of the main kernel take their place, so both run side by side (they write disjoint tiles).
     if (!h->side) {
         CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -174,42 +209,19 @@ int launch_pileup_t(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, const 
     }
     CU(cudaEventRecord(h->ev_fork, s));
     CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    k_pileup<kPpad, true><<<h->sm_count * per_sm, kThreads, smem, h->side>>>(a_overflow, batch_reads);
+    k_pileup_big<kCompact, kPpad><<<h->sm_count * per_sm_big, kThreads, smem_big, h->side>>>(a_big);
     CU(cudaEventRecord(h->ev_join, h->side));
-    k_pileup<kPpad, false><<<h->sm_count * per_sm, kThreads, smem, s>>>(a, batch_reads);    // persistent CTAs pulling units
+    k_pileup_main<kCompact, kPpad><<<h->sm_count * per_sm, kThreads + 32, smem_main, s>>>(a, stage_bytes);   // persistent CTAs pulling units
     CU(cudaStreamWaitEvent(s, h->ev_join, 0));
     h->launches += 2;
     CU(cudaGetLastError());
     return MGATK_OK;
 }
 
-int launch_pileup(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, const PileupArgs &a_overflow, int batch_reads) {
-    return a.ppad == kChrMPpad ? launch_pileup_t<kChrMPpad>(h, s, a, a_overflow, batch_reads)
-                               : launch_pileup_t<0>(h, s, a, a_overflow, batch_reads);
-}
-
-// mask slot of one read and the number of slots a CTA holds, from the declared extent (l_seq <= extent)
-int mask_stride_for(int extent) { return 16 * ((extent + 31) / 32); }
-int cap_reads_for(int extent) {
-    const int k = kMaskBytes / mask_stride_for(extent);
-    return k > kStageReads ? kStageReads : k;
-}
-
-// reads beyond the mask slots that a tile may carry before it goes to the overflow list (they take the per-base path)
-int overflow_slack_for(int extent) {
-    const char *e = getenv("MGATK_OVERFLOW_SLACK");
-    if (e) return atoi(e);
-    return cap_reads_for(extent) >> 5;
-}
-
-// reads per unit: leave room for the reads of the halo and of the chunk the tile border is rounded down to
-int unit_reads_for(int extent) {
-    const char *e = getenv("MGATK_UNIT_READS");
-    const int v = e ? atoi(e) : 0;
-    const int cap = cap_reads_for(extent);
-    if (v > 0) return v < 32 ? 32 : v;
-    const int k = (int)(0.8 * cap);
-    return k < 32 ? 32 : k;
+int launch_pileup(mgatk_handle *h, cudaStream_t s, bool compact, const PileupArgs &a, const PileupArgs &a_big, int stage_bytes) {
+    if (a.ppad == kChrMPpad)
+        return compact ? launch_pileup_t<true, kChrMPpad>(h, s, a, a_big, stage_bytes) : launch_pileup_t<false, kChrMPpad>(h, s, a, a_big, stage_bytes);
+    return compact ? launch_pileup_t<true, 0>(h, s, a, a_big, stage_bytes) : launch_pileup_t<false, 0>(h, s, a, a_big, stage_bytes);
 }
 
 int validate(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, const mgatk_outputs *o) {
@@ -237,9 +249,8 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     int rc = validate(h, p, b, o);
     if (rc) return rc;
     Layout L;
-    if (!make_layout(b->n_records, p->n_cells, L)) return fail(h, MGATK_ERR_RANGE, "n_records / n_cells outside limits");
+    if (!make_layout(b->n_records, p->n_cells, p->max_read_extent, L)) return fail(h, MGATK_ERR_RANGE, "n_records / n_cells outside limits");
     if ((int64_t)L.total > ws_bytes || !ws_v) return fail(h, MGATK_ERR_WORKSPACE, "workspace too small");
-    L.unit_reads = unit_reads_for(p->max_read_extent);
     char *ws = (char *)ws_v;
     CU(cudaSetDevice(h->device));
     if (!h->events_ready) {
@@ -270,31 +281,44 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     if (C == 0) { mark(h, s, "init"); return MGATK_OK; }
     // a cell that is below min_reads_per_cell so far may pass it with a later batch: the gate waits for the finish pass
     const int min_reads = accumulate ? 0 : p->min_reads_per_cell;
+    const bool compact = L.fmt.compact != 0;
 
-    // ---- stage 1 + partition by cell ----
+    // ---- stage 1 + stage 3: filter, reference-coordinate planes, partition by cell ----
     SrcUser su; su.b = *b; su.n_cells = C;
     su.vec4 = (((uintptr_t)b->bc_idx & 15) == 0 && ((uintptr_t)b->flag & 7) == 0) ? 1 : 0;
-    GroupRec *g0 = grouped_at(ws, L, 0);
-    rc = partition_pass(h, s, su, L, 0, ws, b->pos, error_bits, m_ptr, g0);
-    if (rc) return rc;
-    GroupRec *g = g0;
+    uint8_t *slots_a = (uint8_t *)(ws + L.slots[0]), *slots_b = (uint8_t *)(ws + L.slots[1]);
+    if ((rc = histogram_and_scan(h, s, su, L, 0, ws, m_ptr))) return rc;
+    ScatterArgs sa;
+    sa.b = *b; sa.n_cells = C; sa.chunk = L.chunk; sa.nchunks = L.nchunks; sa.shift = L.shift[0]; sa.bins = 1 << L.bits[0];
+    sa.mat = (const u32 *)(ws + L.mat); sa.dst = slots_a; sa.error_bits = error_bits;
+    sa.words = L.fmt.words; sa.slot_bytes = L.fmt.bytes;
+    sa.min_baseq = p->min_baseq; sa.dist = p->min_distance_from_end; sa.min_mapq = p->min_mapq; sa.extent = p->max_read_extent;
+    sa.wbuf = warp_buffer_for(b);
+    if ((rc = compact ? launch_scatter<true>(h, s, sa) : launch_scatter<false>(h, s, sa))) return rc;
+    uint8_t *grouped = slots_a, *piled = slots_b;
     if (L.passes == 2) {
-        SrcGrouped sg; sg.a = g0; sg.m = m_ptr;
-        GroupRec *g1 = grouped_at(ws, L, 1);
-        rc = partition_pass(h, s, sg, L, 1, ws, nullptr, error_bits, nullptr, g1);
-        if (rc) return rc;
-        g = g1;
+        SrcSlots ss; ss.a = slots_a; ss.m = m_ptr; ss.slot_bytes = L.fmt.bytes;
+        if ((rc = histogram_and_scan(h, s, ss, L, 1, ws, nullptr))) return rc;
+        const int bins = 1 << L.bits[1];
+        k_scatter_slots<<<L.nchunks, kPartThreads, rank_smem_bytes(bins), s>>>(ss, L.chunk, L.nchunks, L.shift[1], bins, (const u32 *)(ws + L.mat), slots_b);
+        h->launches += 1;
+        CU(cudaGetLastError());
+        grouped = slots_b; piled = slots_a;
     }
     k_publish_m<<<1, 1, 0, s>>>(o->stats, m_ptr, accumulate);
     h->launches += 1;
-    mark(h, s, "filter+partition");
+    mark(h, s, "filter+planes+partition");
 
     // ---- stage 2: dedup, mapq gate, compaction of the reads to pile up ----
-    ReadRec *recs = (ReadRec *)(ws + L.recs);
     int32_t *cell_start = (int32_t *)(ws + L.cell_start);
     CU(cudaMemsetAsync(ws + L.scan_state, 0, (size_t)L.dedup_blocks * 8, s));
-    k_dedup<<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(g, m_ptr, recs, p->dedup_mode, p->min_mapq, o->cell_qc, o->stats,
-                                                              ticket, (u64 *)(ws + L.scan_state), n_proc);
+    DedupArgs da;
+    da.slots = grouped; da.out = piled; da.slot_bytes = L.fmt.bytes; da.m_ptr = m_ptr;
+    da.cell_first = (const u32 *)(ws + L.mat); da.n_first = 1 << L.bits[0];      // row 0 of the scanned histogram (one pass)
+    da.dedup_mode = p->dedup_mode; da.qc = o->cell_qc; da.stats = o->stats;
+    da.ticket = ticket; da.scan_state = (u64 *)(ws + L.scan_state); da.n_proc_out = n_proc;
+    if (compact) k_dedup<true><<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(da);
+    else k_dedup<false><<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(da);
     h->launches += 1;
     mark(h, s, "dedup");
 
@@ -302,18 +326,15 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     int32_t *unit_start = (int32_t *)(ws + L.unit_start);
     Unit *units = (Unit *)(ws + L.units);
     k_plan_scan<<<1, 1024, 0, s>>>(o->cell_qc, C, min_reads, L.unit_reads, ppad, cell_start, unit_start, n_units);
-    k_plan_units<<<(unsigned)((L.max_units + 255) / 256), 256, 0, s>>>(cell_start, o->cell_qc, recs, unit_start, C,
-                                                                      min_reads, L.unit_reads, ppad,
-                                                                      p->max_read_extent, units,
-                                                                      cap_reads_for(p->max_read_extent) < 32 ? 32 : cap_reads_for(p->max_read_extent),
-                                                                      overflow_slack_for(p->max_read_extent),
-                                                                      (Unit *)(ws + L.units_overflow), work_counter + 4);
+    k_plan_units<<<(unsigned)((L.max_units + 255) / 256), 256, 0, s>>>(cell_start, o->cell_qc, piled, L.fmt.bytes, unit_start, C,
+                                                                      min_reads, L.unit_reads, ppad, p->max_read_extent, units,
+                                                                      L.cap_reads, (Unit *)(ws + L.units_big), work_counter + 4);
     h->launches += 2;
     mark(h, s, "plan");
 
-    // ---- stages 3-6 ----
+    // ---- stages 4-6 ----
     PileupArgs a;
-    a.recs = recs; a.blob = b->blob;
+    a.slots = piled; a.blob = b->blob; a.blob_bytes = b->blob_bytes;
     a.units = units; a.n_units = n_units; a.work_counter = work_counter;
     a.planes = o->planes; a.qc = o->cell_qc; a.stats = o->stats; a.ovf = o->overflow; a.ovf_cap = o->overflow_capacity;
     a.P = P; a.ppad = ppad; a.min_baseq = p->min_baseq; a.dist = p->min_distance_from_end;
@@ -322,26 +343,11 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     a.apply_bias = !a.raw && !(p->max_strand_bias >= 1.0);   // max(f,r)/total never exceeds 1.0
     a.accumulate = accumulate;
     a.extent = p->max_read_extent;
-    a.mask_stride = mask_stride_for(p->max_read_extent);
-    a.cap_reads = cap_reads_for(p->max_read_extent);
-    {   // reads per staging group: what one pass through the 2.5 KB warp buffer holds at the batch's average blob size
-        const int64_t avg = b->n_records > 0 ? (b->blob_bytes / b->n_records + 15) / 16 * 16 : 80;
-        const int64_t g = kWarpBuf / (avg > 16 ? avg : 16);
-        a.group_reads = (int)(g >= 32 ? 32 : g < 4 ? 4 : g);
-    }
-#ifdef MGATK_TIMING
-    a.dbg = (unsigned long long *)(ws + L.scalars + 64);
-    cudaMemsetAsync(a.dbg, 0, 64, s);
-#endif
+    a.slot_bytes = L.fmt.bytes; a.words = L.fmt.words;
+    a.cap_reads = L.cap_reads;
     PileupArgs a2 = a;
-    a2.units = (Unit *)(ws + L.units_overflow); a2.n_units = work_counter + 4; a2.work_counter = work_counter + 5;
-    rc = launch_pileup(h, s, a, a2, a.cap_reads < 32 ? 32 : a.cap_reads);
-#ifdef MGATK_TIMING                                       // profiling build: share of warp-cycles per phase of k_pileup
-    { unsigned long long hd[6]; cudaStreamSynchronize(s); cudaMemcpy(hd, a.dbg, 48, cudaMemcpyDeviceToHost);
-      double tot = 0; for (int k = 0; k < 6; k++) tot += (double)hd[k];
-      fprintf(stderr, "[timing] wait-for-slowest-warp(unit end) %.1f%% phaseA %.1f%% wait(phase A end) %.1f%% phaseB %.1f%% unit-setup %.1f%% epilogue %.1f%% (warp-cycles %.3g)\n",
-              100 * hd[0] / tot, 100 * hd[1] / tot, 100 * hd[2] / tot, 100 * hd[3] / tot, 100 * hd[4] / tot, 100 * hd[5] / tot, tot); }
-#endif
+    a2.units = (Unit *)(ws + L.units_big); a2.n_units = work_counter + 4; a2.work_counter = work_counter + 5;
+    rc = launch_pileup(h, s, compact, a, a2, L.stage_bytes);
     if (rc) return rc;
     mark(h, s, "pileup");
     if (accumulate) return MGATK_OK;                     // filters, coverage, statistics: mgatk_stream_finish_device
@@ -428,9 +434,9 @@ int mgatk_destroy(mgatk_handle *h) {
 
 const char *mgatk_last_error(const mgatk_handle *h) { return h ? h->err.c_str() : "null handle"; }
 
-int64_t mgatk_workspace_bytes(int64_t n_records, int32_t n_cells) {
+int64_t mgatk_workspace_bytes(int64_t n_records, int32_t n_cells, int32_t max_read_extent) {
     Layout L;
-    if (!make_layout(n_records, n_cells, L)) return -1;
+    if (!make_layout(n_records, n_cells, max_read_extent, L)) return -1;
     return (int64_t)L.total;
 }
 
@@ -536,7 +542,7 @@ int mgatk_pileup_host_submit(mgatk_handle *h, const mgatk_params *p, const mgatk
     const size_t n = (size_t)b->n_records, C = (size_t)p->n_cells, P = (size_t)p->mito_length;
     const size_t ppad = (size_t)MGATK_POS_PAD(P);
     const size_t planes_bytes = C * MGATK_N_PLANES * ppad * 2;
-    const int64_t ws_bytes = mgatk_workspace_bytes(b->n_records, p->n_cells);
+    const int64_t ws_bytes = mgatk_workspace_bytes(b->n_records, p->n_cells, p->max_read_extent);
     if (ws_bytes < 0) return fail(h, MGATK_ERR_RANGE, "n_records / n_cells outside limits");
     const void *src[9] = {b->pos, b->tlen, b->flag, b->mapq, b->bc_idx, b->l_seq, b->n_cigar, b->blob_off, b->blob};
     const size_t bytes[9] = {4 * n, 4 * n, 2 * n, n, 4 * n, 2 * n, 2 * n, 4 * n, (size_t)b->blob_bytes};

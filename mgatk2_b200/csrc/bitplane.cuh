@@ -196,9 +196,9 @@ MG_HD void count_columns(u32 v, u32 b0, u32 b1, u32 t5, u32 rev, u32 (&cnt)[10])
 // ---------------------------------------------------------------------------------------------
 namespace mgatk {
 
-// planes of query bases 32w .. 32w+31 of one read -> four words at out + 16w
+// planes of query bases 32w .. 32w+31 of one read, in registers (B0 and B1 cut to V)
 template <class M>
-MG_HD void build_query_mask_group(const M &mem, u32 seq_addr /*4-aligned*/, u32 out /*16-aligned*/, int L, int w, int q_lo, int q_hi, QualGe qg) {
+MG_HD void query_mask_group(const M &mem, u32 seq_addr /*4-aligned*/, int L, int w, int q_lo, int q_hi, QualGe qg, u32 &oV, u32 &o0, u32 &o1) {
     const u32 qual_addr = seq_addr + (u32)((L + 1) >> 1) + 32u * (u32)w;
     const u32 qsh = (qual_addr & 3u) * 8u;
     const u32 qa = qual_addr & ~3u;
@@ -217,8 +217,16 @@ MG_HD void build_query_mask_group(const M &mem, u32 seq_addr /*4-aligned*/, u32 
         else if (g == 2) { mV = insert_top_byte<2>(mV, e.v & ok); m0 = insert_top_byte<2>(m0, e.b0); m1 = insert_top_byte<2>(m1, e.b1); }
         else { mV = insert_top_byte<3>(mV, e.v & ok); m0 = insert_top_byte<3>(m0, e.b0); m1 = insert_top_byte<3>(m1, e.b1); }
     }
-    mV &= bit_range(q_lo - 32 * w, q_hi - 32 * w);            // pileup.py:67-78 (also cuts bases >= L)
-    mem.st128(out + 16u * w, mV, m0 & mV, m1 & mV, 0u);
+    mV &= bit_range(lo, (q_hi < L ? q_hi : L) - 32 * w);      // pileup.py:67-78 (also cuts bases >= L)
+    oV = mV; o0 = m0 & mV; o1 = m1 & mV;
+}
+
+// the same -> four words at out + 16w
+template <class M>
+MG_HD void build_query_mask_group(const M &mem, u32 seq_addr /*4-aligned*/, u32 out /*16-aligned*/, int L, int w, int q_lo, int q_hi, QualGe qg) {
+    u32 mV, m0, m1;
+    query_mask_group(mem, seq_addr, L, w, q_lo, q_hi, qg, mV, m0, m1);
+    mem.st128(out + 16u * w, mV, m0, m1, 0u);
 }
 
 template <class M>
@@ -238,5 +246,84 @@ MG_HD void query_window(const M &mem, u32 masks /*16-aligned*/, int nq, int qb, 
 #pragma unroll
     for (int x = 0; x < 3; x++) out[x] = funnel_r(lo[x], hi[x], sh);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Query coordinates -> reference coordinates. The CIGAR walk of pileup.py:52-95 moves runs of query
+// bases to reference positions: an aligned block (M, =, X) of length n places query bases
+// [qp, qp + n) on reference offsets [ref, ref + n) (relative to reference_start) and advances both;
+// D / N advance the reference only, S the query only; I, H and P advance NOTHING (the reference's
+// quirk, SURVEY Q3: the bases after an insertion are read from the inserted query positions).
+// ref_group() builds one group of 32 reference offsets [32k, 32k + 32) of the three planes from the
+// query planes: per overlapping block, a 32-bit window of the query planes cut to the block.
+//   M: ld32(addr) of the cigar words;  Q: window(qb, out[3]) = query-plane bits [qb, qb + 32)
+// After this, stages 4-6 never see a CIGAR: a read is three bit planes anchored at its start.
+// ---------------------------------------------------------------------------------------------
+constexpr int kOpCap = 1 << 20;     // cigar lengths above this cannot be valid for a short-read batch
+constexpr int kRefCap = 1 << 28;    // running offsets saturate here (65535 ops x 2^20 would overflow an int)
+
+MG_HD bool cigar_op_aligned(int op) { return op == 0 || op == 7 || op == 8; }      // pileup.py:56
+MG_HD bool cigar_op_ref_only(int op) { return op == 2 || op == 3; }                 // pileup.py:92-93
+
+// reference span of a read (sum of M/=/X/D/N lengths), saturating
+template <class M>
+MG_HD int cigar_ref_span(const M &mem, u32 cig_addr, int ncig) {
+    int span = 0;
+    for (int ci = 0; ci < ncig; ci++) {
+        const u32 w = mem.ld32(cig_addr + 4u * (u32)ci);
+        const int op = (int)(w & 15u);
+        if (cigar_op_aligned(op) || cigar_op_ref_only(op)) { span += (int)(w >> 4) < kOpCap ? (int)(w >> 4) : kOpCap; if (span > kRefCap) span = kRefCap; }
+    }
+    return span;
+}
+
+template <class M, class Q>
+MG_HD void ref_group(const M &mem, u32 cig_addr, int ncig, const Q &qplanes, int k, u32 (&out)[3]) {
+    out[0] = 0u; out[1] = 0u; out[2] = 0u;
+    const int lo = 32 * k, hi = lo + 32;
+    int ref = 0, qp = 0;
+    for (int ci = 0; ci < ncig; ci++) {
+        const u32 w = mem.ld32(cig_addr + 4u * (u32)ci);
+        const int op = (int)(w & 15u);
+        const int n = (int)(w >> 4) < kOpCap ? (int)(w >> 4) : kOpCap;
+        if (cigar_op_aligned(op)) {
+            if (ref < hi && ref + n > lo) {
+                u32 wv[3];
+                qplanes.window(lo - ref + qp, wv);             // query bit of reference offset `lo`
+                const u32 rm = bit_range(ref - lo, ref + n - lo);
+                out[0] |= wv[0] & rm; out[1] |= wv[1] & rm; out[2] |= wv[2] & rm;
+            }
+            ref += n; qp += n;                                 // pileup.py:90-91
+            if (ref > kRefCap) ref = kRefCap;
+            if (qp > kRefCap) qp = kRefCap;
+        } else if (cigar_op_ref_only(op)) {
+            ref += n;
+            if (ref > kRefCap) ref = kRefCap;
+        } else if (op == 4) {                                  // pileup.py:94-95
+            qp += n;
+            if (qp > kRefCap) qp = kRefCap;
+        }
+        if (ref >= hi) break;                                  // blocks only move right
+    }
+}
+
+// query planes of a read of at most 64 bases held in three 64-bit words
+struct QueryPlanes64 {
+    unsigned long long v, b0, b1;
+    MG_HD static u32 win(unsigned long long x, int qb) {
+        if (qb >= 64 || qb <= -32) return 0u;
+        return qb >= 0 ? (u32)(x >> qb) : (u32)(x << (-qb));
+    }
+    MG_HD void window(int qb, u32 (&out)[3]) const { out[0] = win(v, qb); out[1] = win(b0, qb); out[2] = win(b1, qb); }
+};
+
+// query planes stored as groups of four words (V, B0, B1, 0 per 32 bases) behind an accessor with ld128
+template <class M>
+struct QueryPlanesMem {
+    const M &mem; u32 addr; int nq;
+    MG_HD void window(int qb, u32 (&out)[3]) const {
+        if (qb >= 32 * nq || qb <= -32) { out[0] = 0u; out[1] = 0u; out[2] = 0u; return; }
+        query_window(mem, addr, nq, qb, out);
+    }
+};
 
 }  // namespace mgatk

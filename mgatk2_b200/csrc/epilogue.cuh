@@ -1,0 +1,152 @@
+// mgatk2_b200 — passes over finished planes: reference-allele totals (writers.py:220-222), median depth
+// (writers.py:190), the stand-alone strand-bias filter (pileup.py:128-154) and the finish pass of the streaming mode.
+#pragma once
+#include "pileup.cuh"
+
+namespace mgatk {
+
+// ---------------------------------------------------------------------------------------------
+// Reference-allele vote input (writers.py:220-222): per position and base, the sum over cells of
+// fwd+rev after filtering. One thread owns two positions and a group of 32 cells.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTotalsCellGroup = 32;
+__global__ void __launch_bounds__(128)
+k_base_totals(const uint16_t *__restrict__ planes, int n_cells, int P, int ppad, u64 *__restrict__ totals) {
+    const int pp = blockIdx.x * blockDim.x + threadIdx.x;          // position pair
+    if (2 * pp >= ppad) return;
+    const int c0 = blockIdx.y * kTotalsCellGroup, c1 = min(n_cells, c0 + kTotalsCellGroup);
+    u32 s[4][2] = {};
+    for (int c = c0; c < c1; c++) {
+        const u32 *row = reinterpret_cast<const u32 *>(planes + (size_t)c * MGATK_N_PLANES * ppad) + pp;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const u32 f = __ldg(row + (size_t)(2 * b) * (ppad / 2)), r = __ldg(row + (size_t)(2 * b + 1) * (ppad / 2));
+            s[b][0] += (f & 0xffff) + (r & 0xffff);
+            s[b][1] += (f >> 16) + (r >> 16);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int p = 2 * pp + k;
+        if (p < P)
+#pragma unroll
+            for (int b = 0; b < 4; b++) if (s[b][k]) atomicAdd(&totals[(size_t)p * 4 + b], (u64)s[b][k]);
+    }
+}
+
+__global__ void k_base_totals_overflow(const mgatk_overflow *__restrict__ ovf, const mgatk_stats *__restrict__ stats,
+                                       int64_t cap, int P, u64 *__restrict__ totals) {
+    const int64_t n = min((int64_t)stats->n_overflow, cap);
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int pl = ovf[k].plane_pos >> 24, p = ovf[k].plane_pos & 0xffffff;
+        if (pl < 8 && p < P) atomicAdd(&totals[(size_t)p * 4 + pl / 2], (u64)(ovf[k].value - 65535u));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PileupGenerator.filter_strand_bias (pileup.py:128-154) as a stand-alone pass over raw planes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_filter_planes(uint16_t *__restrict__ planes, int n_cells, int P, int ppad, double max_bias) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (p >= P || c >= n_cells) return;
+    uint16_t *row = planes + (size_t)c * MGATK_N_PLANES * ppad + p;
+    u32 cov = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        u32 f = row[(size_t)(2 * b) * ppad], r = row[(size_t)(2 * b + 1) * ppad];
+        const u32 t = f + r;
+        if (t > 0) {
+            const double bias = (double)max(f, r) / (double)t;
+            if (bias > max_bias) { f = 0; r = 0; row[(size_t)(2 * b) * ppad] = 0; row[(size_t)(2 * b + 1) * ppad] = 0; }
+        }
+        cov += f + r;
+    }
+    row[(size_t)MGATK_PLANE_COVERAGE * ppad] = (uint16_t)min(cov, 65535u);
+    if (cov == 0) { row[(size_t)MGATK_PLANE_TN5_FWD * ppad] = 0; row[(size_t)MGATK_PLANE_TN5_REV * ppad] = 0; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming (batches cut on reference_start borders, planes resident and accumulating): the per-batch kernels only add
+// raw counts; this pass turns the accumulated planes into the final ones exactly as a one-batch run would have written
+// them: cell gate (processors.py:22), strand-bias filter, coverage, Tn5 gating (pileup.py:128-154), depth statistics.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_stream_finish(PileupArgs a, int n_cells, int min_reads) {
+    const int lane = lane_id();
+    const int warps = (int)((gridDim.x * (size_t)blockDim.x) >> 5), gw = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int chunks = a.ppad >> 5;
+    for (long long w = gw; w < (long long)n_cells * chunks; w += warps) {
+        const int cell = (int)(w / chunks), ch = (int)(w - (long long)cell * chunks);
+        const bool dead = cell_dead(a.qc[cell], min_reads);
+        const uint16_t *in = a.planes + (size_t)cell * MGATK_N_PLANES * a.ppad + 32 * ch + lane;
+        u32 cnt[10];
+#pragma unroll
+        for (int k = 0; k < 10; k++) cnt[k] = dead ? 0u : (u32)in[(size_t)k * a.ppad];
+        u64 sum = 0; u32 covered = 0, maxd = 0;
+        finish_chunk<0>(a, cell, 32 * ch, lane, cnt, sum, covered, maxd);
+        if (__any_sync(kFull, covered != 0)) {
+            u64 tot = sum;
+            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(kFull, tot, o);
+            const u32 cv = __reduce_add_sync(kFull, covered), mx = __reduce_max_sync(kFull, maxd);
+            if (lane == 0) {
+                atomicAdd((u64 *)&a.qc[cell].sum_depth, tot);
+                atomicAdd(&a.qc[cell].covered, cv);
+                atomicMax(&a.qc[cell].max_depth, mx);
+            }
+        }
+    }
+}
+
+// k_dedup parks the per-cell count of reads to pile up in median_lo: cleared before every streamed batch
+__global__ void k_clear_parked(mgatk_cell_qc *__restrict__ qc, int n_cells) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_cells) qc[c].median_lo = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Median depth over covered positions (writers.py:190): the two middle order statistics by a
+// two-level (high byte, low byte) counting select on the coverage plane. One CTA per cell.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_median(const uint16_t *__restrict__ planes, int P, int ppad, mgatk_cell_qc *__restrict__ qc) {
+    __shared__ u32 hist[256];
+    __shared__ u32 sel[4];                                   // bin, remainder for lo / hi
+    const int c = blockIdx.x, t = threadIdx.x;
+    const uint16_t *cov = planes + ((size_t)c * MGATK_N_PLANES + MGATK_PLANE_COVERAGE) * ppad;
+    hist[t] = 0;
+    __syncthreads();
+    for (int p = t; p < P; p += 256) { const u32 v = cov[p]; if (v) atomicAdd(&hist[v >> 8], 1u); }
+    __syncthreads();
+    u32 res[2] = {0, 0};
+    if (t == 0) {
+        u32 n = 0;
+        for (int b = 0; b < 256; b++) n += hist[b];
+        sel[0] = sel[2] = 0xffffffffu;
+        if (n) {
+            const u32 k[2] = {(n - 1) / 2, n / 2};
+            for (int s = 0; s < 2; s++) {
+                u32 acc = 0;
+                for (int b = 0; b < 256; b++) { if (k[s] < acc + hist[b]) { sel[2 * s] = b; sel[2 * s + 1] = k[s] - acc; break; } acc += hist[b]; }
+            }
+        }
+    }
+    __syncthreads();
+    if (sel[0] == 0xffffffffu) { if (t == 0) { qc[c].median_lo = 0; qc[c].median_hi = 0; } return; }
+    for (int s = 0; s < 2; s++) {
+        const u32 bin = sel[2 * s], rem = sel[2 * s + 1];
+        if (s == 1 && bin == sel[0]) {                       // same high byte: low-byte histogram is still valid
+            if (t == 0) { u32 acc = 0; for (int b = 0; b < 256; b++) { if (rem < acc + hist[b]) { res[1] = (bin << 8) | b; break; } acc += hist[b]; } }
+            break;
+        }
+        __syncthreads();
+        hist[t] = 0;
+        __syncthreads();
+        for (int p = t; p < P; p += 256) { const u32 v = cov[p]; if (v && (v >> 8) == bin) atomicAdd(&hist[v & 255], 1u); }
+        __syncthreads();
+        if (t == 0) { u32 acc = 0; for (int b = 0; b < 256; b++) { if (rem < acc + hist[b]) { res[s] = (bin << 8) | b; break; } acc += hist[b]; } }
+    }
+    if (t == 0) { qc[c].median_lo = res[0]; qc[c].median_hi = res[1]; }
+}
+
+}  // namespace mgatk

@@ -1,0 +1,450 @@
+// mgatk2_b200 — stage 1 + stage 3 of the hot path in ONE streaming pass over the batch (sm_100a).
+//
+//   k_hist / k_scan_*        per-chunk histograms of the cell index of the records that pass the flag + whitelist filter
+//                            (readers.py:96-111) and their exclusive scan in (cell, chunk) order
+//   k_scatter_planes         walks the batch in BAM order. Every warp streams the cigar|seq|qual blobs of its next 32
+//                            records into shared memory with ONE bulk asynchronous copy (TMA, mbarrier-signalled, one step
+//                            ahead), turns SEQ / QUAL / CIGAR of each surviving record into reference-coordinate bit
+//                            planes (pileup.py:52-86: aligned blocks, base quality, distance-from-end window, A/C/G/T only)
+//                            and writes the finished slot (common.cuh) at the record's rank inside its cell: a stable
+//                            counting partition by cell, so dedup and counting see (cell, start, BAM order) order.
+//   k_scatter_slots          second digit pass of the partition for more than 2048 cells (moves finished slots).
+#pragma once
+#include "common.cuh"
+
+namespace mgatk {
+
+constexpr int kScanGroup = 16;        // chunks per scan group
+
+// ---------------------------------------------------------------------------------------------
+// Sources of the partition passes
+// ---------------------------------------------------------------------------------------------
+struct SrcUser {          // pass 0: reads the caller's SoA batch and applies the stage-1 filter
+    mgatk_batch b;
+    int32_t n_cells;
+    int vec4;             // bc_idx is 16-byte and flag 8-byte aligned: k_hist loads four records at a time
+    __device__ __forceinline__ void cell4(int64_t i, int (&c)[4]) const {      // i % 4 == 0, i + 3 < count()
+        const int4 bc = *reinterpret_cast<const int4 *>(b.bc_idx + i);
+        const uint2 fl = *reinterpret_cast<const uint2 *>(b.flag + i);
+        const int cc[4] = {bc.x, bc.y, bc.z, bc.w};
+        const u32 ff[4] = {fl.x & 0xffffu, fl.x >> 16, fl.y & 0xffffu, fl.y >> 16};
+#pragma unroll
+        for (int k = 0; k < 4; k++) c[k] = ((ff[k] & 0x904u) || cc[k] < 0 || cc[k] >= n_cells) ? -1 : cc[k];
+    }
+    __device__ __forceinline__ int64_t count() const { return b.n_records; }
+    __device__ __forceinline__ int cell(int64_t i) const {
+        // readers.py:96-97 unmapped/secondary/supplementary; :104-111 tag absent or not whitelisted
+        const int c = b.bc_idx[i];
+        return ((b.flag[i] & 0x904) || c < 0 || c >= n_cells) ? -1 : c;
+    }
+};
+
+struct SrcSlots {         // pass 1 of a two-digit partition: wide slots, already filtered, count on the device
+    const uint8_t *a;
+    const int64_t *m;
+    int slot_bytes;
+    static constexpr int vec4 = 0;
+    __device__ __forceinline__ void cell4(int64_t, int (&)[4]) const {}
+    __device__ __forceinline__ int64_t count() const { return *m; }
+    __device__ __forceinline__ int cell(int64_t i) const {
+        return (int)(reinterpret_cast<const u32 *>(a + (size_t)i * slot_bytes)[2] & 0xffffffu);
+    }
+};
+
+#ifndef MGATK_PART_THREADS
+#define MGATK_PART_THREADS 256
+#endif
+constexpr int kPartThreads = MGATK_PART_THREADS;  // records per CTA step of the scatter
+constexpr int kHistAhead = 4;      // steps loaded before counting (k_hist)
+
+// Per-CTA digit histogram of a contiguous chunk of records (order does not matter for counting).
+constexpr int kHistThreads = 1024;
+template <class Src>
+__global__ void __launch_bounds__(kHistThreads)
+k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict__ mat) {
+    extern __shared__ u32 smem[];
+    u32 *h = smem;
+    for (int b = threadIdx.x; b < bins; b += kHistThreads) h[b] = 0;
+    __syncthreads();
+    const int64_t n = src.count();
+    int64_t beg = (int64_t)blockIdx.x * chunk, end = beg + chunk;
+    if (end > n) end = n;
+    if (src.vec4) {                                          // four records per thread and load, two loads in flight
+        const int64_t end4 = beg + ((end - beg) & ~(int64_t)3);
+        for (int64_t i0 = beg + 4 * (int64_t)threadIdx.x; i0 < end4; i0 += 8 * kHistThreads) {
+            int c[2][4];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int64_t i = i0 + 4 * (int64_t)kHistThreads * k;
+#pragma unroll
+                for (int q = 0; q < 4; q++) c[k][q] = -1;
+                if (i < end4) src.cell4(i, c[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (c[k][q] >= 0) atomicAdd(&h[(c[k][q] >> shift) & (bins - 1)], 1u);
+        }
+        for (int64_t i = end4 + threadIdx.x; i < end; i += kHistThreads) {
+            const int c = src.cell(i);
+            if (c >= 0) atomicAdd(&h[(c >> shift) & (bins - 1)], 1u);
+        }
+    } else
+    for (int64_t i0 = beg + threadIdx.x; i0 < end; i0 += kHistThreads * kHistAhead) {
+        int d[kHistAhead];
+#pragma unroll
+        for (int k = 0; k < kHistAhead; k++) {
+            const int64_t i = i0 + (int64_t)kHistThreads * k;
+            d[k] = -1;
+            if (i < end) {
+                const int c = src.cell(i);
+                if (c >= 0) d[k] = (c >> shift) & (bins - 1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kHistAhead; k++) if (d[k] >= 0) atomicAdd(&h[d[k]], 1u);
+    }
+    __syncthreads();
+    u32 *row = mat + (size_t)blockIdx.x * bins;
+    for (int b = threadIdx.x; b < bins; b += kHistThreads) row[b] = h[b];
+}
+
+// scan of mat[chunk][bin] in (bin, chunk) order: S1 group sums, S2 bases, S3 in-place exclusive prefixes
+__global__ void k_scan_group_sums(const u32 *__restrict__ mat, int nchunks, int bins, u32 *__restrict__ part) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
+    if (b >= bins) return;
+    const int w0 = g * kScanGroup;
+    u32 v[kScanGroup];
+#pragma unroll
+    for (int k = 0; k < kScanGroup; k++) v[k] = w0 + k < nchunks ? mat[(size_t)(w0 + k) * bins + b] : 0u;
+    u32 s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanGroup; k++) s += v[k];
+    part[(size_t)g * bins + b] = s;
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_bases(u32 *__restrict__ part, int ngroups, int bins, int64_t *__restrict__ total_out) {
+    __shared__ u32 warp_sums[32];
+    __shared__ u32 carry_s;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < bins; b0 += 1024) {
+        const int b = b0 + t;
+        u32 tot = 0;
+        if (b < bins) {
+#pragma unroll 8
+            for (int g = 0; g < ngroups; g++) tot += part[(size_t)g * bins + b];       // independent loads, eight in flight
+        }
+        u32 inc = tot;                                   // inclusive block scan of bin totals
+        for (int o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            u32 v = warp_sums[lane], s = v;
+            for (int o = 1; o < 32; o <<= 1) { u32 x = __shfl_up_sync(kFull, s, o); if (lane >= o) s += x; }
+            warp_sums[lane] = s - v;                     // exclusive
+        }
+        __syncthreads();
+        const u32 carry = carry_s;
+        u32 run = carry + warp_sums[wid] + inc - tot;    // exclusive base of bin b
+        if (b < bins) for (int g0 = 0; g0 < ngroups; g0 += 8) {
+            u32 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = g0 + k < ngroups ? part[(size_t)(g0 + k) * bins + b] : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (g0 + k < ngroups) { part[(size_t)(g0 + k) * bins + b] = run; run += v[k]; }
+        }
+        __syncthreads();
+        if (t == 1023) carry_s = carry + warp_sums[31] + inc;
+        __syncthreads();
+    }
+    if (t == 0 && total_out) *total_out = carry_s;
+}
+
+__global__ void k_scan_apply(u32 *__restrict__ mat, int nchunks, int bins, const u32 *__restrict__ part) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
+    if (b >= bins) return;
+    const int w0 = g * kScanGroup;
+    u32 v[kScanGroup];
+#pragma unroll
+    for (int k = 0; k < kScanGroup; k++) v[k] = w0 + k < nchunks ? mat[(size_t)(w0 + k) * bins + b] : 0u;
+    u32 run = part[(size_t)g * bins + b];
+#pragma unroll
+    for (int k = 0; k < kScanGroup; k++) if (w0 + k < nchunks) { mat[(size_t)(w0 + k) * bins + b] = run; run += v[k]; }
+}
+
+constexpr int kPartWarps = kPartThreads / 32;
+static_assert(kPartWarps == 8 || kPartWarps == 4, "the packed per-digit counter holds one byte per warp");
+
+// packed per-digit counter of a step: one byte per warp
+template <int kWarps> struct Packed;
+template <> struct Packed<4> {
+    u32 x;
+    __device__ __forceinline__ void clear() { x = 0u; }
+    __device__ __forceinline__ static void add(Packed *p, int wid, u32 n) { atomicAdd(&p->x, n << (8 * wid)); }
+    __device__ __forceinline__ u32 before(int wid) const { return __dp4a(x & (wid == 0 ? 0u : (0xffffffffu >> (32 - 8 * wid))), 0x01010101u, 0u); }
+    __device__ __forceinline__ bool first(int wid) const { return (x & (wid == 0 ? 0u : (0xffffffffu >> (32 - 8 * wid)))) == 0u; }
+    __device__ __forceinline__ u32 total() const { return __dp4a(x, 0x01010101u, 0u); }
+};
+template <> struct Packed<8> {
+    u32 x, y;                                              // x: warps 0-3, y: warps 4-7
+    __device__ __forceinline__ void clear() { x = 0u; y = 0u; }
+    __device__ __forceinline__ static void add(Packed *p, int wid, u32 n) { atomicAdd(wid < 4 ? &p->x : &p->y, n << (8 * (wid & 3))); }
+    __device__ __forceinline__ u32 mx(int wid) const { return wid >= 4 ? 0xffffffffu : wid == 0 ? 0u : (0xffffffffu >> (32 - 8 * wid)); }
+    __device__ __forceinline__ u32 my(int wid) const { return wid <= 4 ? 0u : (0xffffffffu >> (32 - 8 * (wid - 4))); }
+    __device__ __forceinline__ u32 before(int wid) const { return __dp4a(x & mx(wid), 0x01010101u, __dp4a(y & my(wid), 0x01010101u, 0u)); }
+    __device__ __forceinline__ bool first(int wid) const { return ((x & mx(wid)) | (y & my(wid))) == 0u; }
+    __device__ __forceinline__ u32 total() const { return __dp4a(x, 0x01010101u, __dp4a(y, 0x01010101u, 0u)); }
+};
+typedef Packed<kPartWarps> Pack;
+__host__ __device__ inline size_t scatter_smem_bytes(int bins) { return (size_t)bins * (2 * sizeof(Pack) + 4); }
+
+__host__ __device__ inline size_t rank_smem_bytes(int bins) { return ((size_t)bins * (2 * sizeof(Pack) + 4) + 127) / 128 * 128; }
+
+// Rank of a record inside its digit for one step of kPartThreads records in BAM order, and the digit's running
+// destination offset: match_any groups the lanes of a warp by digit, the group leaders add their group size into the
+// byte of their warp in a packed per-digit counter (8 warps x 8 bits, two words), and after one barrier every thread
+// reads "records of my digit in earlier warps" out of the lower bytes. One shared-memory atomic per (warp, digit) and
+// two barriers per step (the packed counters are double buffered). Returns the destination index (d < 0: none).
+__device__ __forceinline__ size_t rank_step(Pack *packed, u32 *off, int bins, int buf, int d, int lane, int wid) {
+    Pack *pk = packed + (size_t)buf * bins;
+    const u32 peers = __match_any_sync(kFull, d);
+    const bool leader = d >= 0 && lane == __ffs(peers) - 1;
+    if (leader) Pack::add(&pk[d], wid, (u32)__popc(peers));
+    __syncthreads();
+    Pack v; v.clear(); u32 base = 0;
+    if (d >= 0) { v = pk[d]; base = off[d]; }
+    __syncthreads();
+    if (d < 0) return 0;
+    if (leader && v.first(wid)) { off[d] = base + v.total(); pk[d].clear(); }   // first warp that holds the digit
+    return (size_t)base + v.before(wid) + __popc(peers & ((1u << lane) - 1u));
+}
+
+#ifndef MGATK_SCATTER_CTAS
+#define MGATK_SCATTER_CTAS 2
+#endif
+constexpr int kWarpBufSlack = 64;    // the plane builder may load this far past the last staged byte
+
+struct ScatterArgs {
+    mgatk_batch b;
+    int32_t n_cells;
+    int64_t chunk; int nchunks, shift, bins;
+    const u32 *mat;
+    uint8_t *dst;
+    u64 *error_bits;
+    int words, slot_bytes;            // plane words per read (W), bytes per slot
+    int min_baseq, dist, min_mapq, extent;
+    int wbuf;                         // bytes of one per-warp blob staging buffer (multiple of 16)
+};
+
+__host__ __device__ inline size_t scatter_smem_bytes(int bins, int wbuf, int words, bool compact) {
+    return rank_smem_bytes(bins) + (size_t)kPartWarps * 2 * (wbuf + kWarpBufSlack) + (compact ? 0 : (size_t)kPartThreads * 16 * words);
+}
+
+struct RawRec { int32_t pos, tlen, bc, prev; u32 off; uint16_t flag, lseq, ncig; uint8_t mapq; bool valid; };
+
+__device__ __forceinline__ RawRec load_raw(const mgatk_batch &b, int64_t i, bool valid) {     // loads only; used one or two steps later
+    RawRec r; r.valid = valid;
+    r.pos = 0; r.tlen = 0; r.bc = -1; r.off = 0; r.flag = 0x4; r.lseq = 0; r.ncig = 0; r.mapq = 0; r.prev = 0x80000000;
+    if (valid) {
+        if ((threadIdx.x & 31) == 0 && i > 0) r.prev = b.pos[i - 1];     // sortedness check across the warp border
+        r.pos = b.pos[i]; r.tlen = b.tlen[i]; r.bc = b.bc_idx[i]; r.off = b.blob_off[i];
+        r.flag = b.flag[i]; r.lseq = b.l_seq[i]; r.ncig = b.n_cigar[i]; r.mapq = b.mapq[i];
+    }
+    return r;
+}
+
+// The blobs of a warp's 32 records of one step: when they sit back to back in the caller's blob (they do when the host
+// packs records in file order) and fit the warp's buffer, lane 0 arms the barrier and issues one bulk copy. Returns
+// whether the step is staged; `beg16` = blob offset (16-byte units) of the first byte in the buffer.
+__device__ __forceinline__ bool stage_blobs(const mgatk_batch &b, const RawRec &r, int lane, u32 buf_addr, u32 bar, int wbuf, u32 &beg16) {
+    const u32 sz16 = r.valid ? (u32)((4 * (int)r.ncig + (((int)r.lseq + 1) >> 1) + (int)r.lseq + 15) >> 4) : 0u;
+    const u64 end = (u64)r.off + sz16;
+    const u64 prev_end = __shfl_up_sync(kFull, end, 1);
+    const bool contiguous = !r.valid || lane == 0 || (u64)r.off == prev_end;
+    const u32 valid_mask = __ballot_sync(kFull, r.valid);
+    if (!valid_mask) return false;
+    const int last = 31 - __clz(valid_mask);
+    const u64 range_end = __shfl_sync(kFull, end, last);
+    beg16 = __shfl_sync(kFull, r.off, 0);
+    const u64 bytes = 16 * (range_end - (u64)beg16);
+    const bool ok = __all_sync(kFull, contiguous) && range_end >= (u64)beg16 && bytes > 0 && bytes <= (u64)wbuf && 16 * range_end <= (u64)b.blob_bytes;
+    if (ok && lane == 0) {
+        fence_proxy_async();                                 // the warp's reads of this buffer (two steps ago) come first
+        mbar_expect_tx(bar, (u32)bytes);
+        bulk_load(buf_addr, b.blob + 16 * (size_t)beg16, (u32)bytes, bar);
+    }
+    return ok;
+}
+
+// The slot of one record. `mem` / `cig_addr` reach its blob (staged in shared memory or straight from global memory),
+// `dst` is its place in the partitioned array. kCompact: registers only, one 256-bit store.
+template <bool kCompact, class M>
+__device__ __forceinline__ void build_slot(const ScatterArgs &a, const M &mem, u32 cig_addr, const RawRec &r, int cell, uint8_t *dst,
+                                           QualGe qg, u32 scratch_addr, bool &extent_err) {
+    const int L = r.lseq, ncig = r.ncig;
+    const int32_t t = r.tlen;
+    const u32 tlen_abs = t < 0 ? (u32)(-(int64_t)t) : (u32)t;            // abs(read.template_length), readers.py:124
+    u32 meta = ((r.flag & 0x10) ? SM_STRAND : 0u) | ((r.flag & 0x1) ? SM_PAIRED : 0u) | ((int)r.mapq >= a.min_mapq ? SM_MAPQ_OK : 0u) |
+               (L == 0 ? SM_EMPTY : 0u);
+    const int span = cigar_ref_span(mem, cig_addr, ncig);
+    const bool beyond = L > a.extent || span > a.extent;                  // MGATK_ERR_EXTENT: the slot stays empty
+    if (beyond) extent_err = true;
+    const int q_lo = a.dist > 0 ? a.dist : 0;                             // pileup.py:67-72
+    int q_hi = a.dist > 0 ? L - a.dist : L;
+    if (qg.none) q_hi = q_lo;
+    const u32 w0 = ncig > 0 ? mem.ld32(cig_addr) : 0u;
+    // one aligned block over all of SEQ: reference offset i <-> query base i, the query planes are the slot's planes
+    const bool simple = ncig == 1 && cigar_op_aligned((int)(w0 & 15u)) && (int)(w0 >> 4) >= L;
+    const u32 seq_addr = cig_addr + 4u * (u32)ncig;
+    const u32 tn5off = L > 0 ? (u32)(L - 1) : 0u;
+    if (kCompact) {
+        u32 g[2][3] = {{0u, 0u, 0u}, {0u, 0u, 0u}};
+        const int nq = beyond ? 0 : L > 32 ? 2 : (L > 0 ? 1 : 0);        // L <= 56
+#pragma unroll
+        for (int w = 0; w < 2; w++) if (w < nq) query_mask_group(mem, seq_addr, L, w, q_lo, q_hi, qg, g[w][0], g[w][1], g[w][2]);
+        if (!simple && nq > 0) {
+            QueryPlanes64 q;
+            q.v = ((u64)g[1][0] << 32) | g[0][0]; q.b0 = ((u64)g[1][1] << 32) | g[0][1]; q.b1 = ((u64)g[1][2] << 32) | g[0][2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) ref_group(mem, cig_addr, ncig, q, k, g[k]);
+        }
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"((u32)r.pos), "r"(tlen_abs), "r"(g[0][0]),
+                     "r"((g[1][0] & 0xffffffu) | (meta << 24)), "r"(g[0][1]), "r"((g[1][1] & 0xffffffu) | ((tn5off & 63u) << 24)),
+                     "r"(g[0][2]), "r"(g[1][2] & 0xffffffu) : "memory");
+    } else {
+        const int W = a.words;
+        const bool indirect = L > 32 * W || span > 32 * W;
+        if (indirect) meta |= SM_INDIRECT;
+        uint4 *out = reinterpret_cast<uint4 *>(dst);
+        out[0] = make_uint4((u32)r.pos, tlen_abs, (u32)cell | (meta << 24), tn5off & 0xffffu);
+        const int nq = (L + 31) >> 5;
+        if (indirect || L == 0 || beyond) {
+            out[1] = indirect ? make_uint4(r.off, (u32)L | ((u32)ncig << 16), 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+            for (int k = 1; k < W; k++) out[1 + k] = make_uint4(0u, 0u, 0u, 0u);
+        } else if (simple) {
+            for (int k = 0; k < W; k++) {
+                u32 v = 0u, b0 = 0u, b1 = 0u;
+                if (k < nq) query_mask_group(mem, seq_addr, L, k, q_lo, q_hi, qg, v, b0, b1);
+                out[1 + k] = make_uint4(v, b0, b1, 0u);
+            }
+        } else {
+            const SharedMem smem;
+            for (int w = 0; w < nq; w++) {
+                u32 v, b0, b1;
+                query_mask_group(mem, seq_addr, L, w, q_lo, q_hi, qg, v, b0, b1);
+                smem.st128(scratch_addr + 16u * (u32)w, v, b0, b1, 0u);
+            }
+            const QueryPlanesMem<SharedMem> q{smem, scratch_addr, nq};
+            for (int k = 0; k < W; k++) {
+                u32 o[3];
+                ref_group(mem, cig_addr, ncig, q, k, o);
+                out[1 + k] = make_uint4(o[0], o[1], o[2], 0u);
+            }
+        }
+    }
+}
+
+template <bool kCompact>
+__global__ void __launch_bounds__(kPartThreads, MGATK_SCATTER_CTAS)
+k_scatter_planes(ScatterArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) u64 s_bar[kPartWarps][2];
+    const int bins = a.bins;
+    Pack *packed = reinterpret_cast<Pack *>(smem_raw);                 // [2][bins] per-warp byte counters of the step
+    u32 *off = reinterpret_cast<u32 *>(smem_raw + (size_t)2 * bins * sizeof(Pack));   // [bins] running destination offsets
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const u32 stage_stride = (u32)(a.wbuf + kWarpBufSlack);
+    const u32 wbuf_addr = (u32)__cvta_generic_to_shared(smem_raw + rank_smem_bytes(bins)) + (u32)wid * 2u * stage_stride;
+    const u32 scratch_addr = kCompact ? 0u
+        : (u32)__cvta_generic_to_shared(smem_raw + rank_smem_bytes(bins) + (size_t)kPartWarps * 2 * stage_stride) + (u32)t * 16u * (u32)a.words;
+    const u32 bar_addr = (u32)__cvta_generic_to_shared(&s_bar[wid][0]);
+    const u32 *row = a.mat + (size_t)blockIdx.x * bins;
+    for (int b = t; b < bins; b += kPartThreads) { off[b] = row[b]; packed[b].clear(); packed[bins + b].clear(); }
+    if (lane == 0) { mbar_init(bar_addr, 1); mbar_init(bar_addr + 8, 1); mbar_fence_init(); }
+    const int64_t n = a.b.n_records;
+    int64_t beg = (int64_t)blockIdx.x * a.chunk, end = beg + a.chunk;
+    if (end > n) end = n;
+    const QualGe qg = make_qual_ge(a.min_baseq);
+    RawRec r1 = load_raw(a.b, beg + t, beg + t < end);                                  // two steps of loads in flight
+    RawRec r2 = load_raw(a.b, beg + kPartThreads + t, beg + kPartThreads + t < end);
+    __syncthreads();
+    u32 beg16_0 = 0u, beg16_1 = 0u;                          // blob offset of the first staged byte of either buffer
+    u32 staged = 0u, parity = 0u;                            // bit b: buffer b holds a staged step / parity of its next wait
+    if (stage_blobs(a.b, r1, lane, wbuf_addr, bar_addr, a.wbuf, beg16_0)) staged |= 1u;
+    int buf = 0;
+    bool unsorted = false, extent_err = false;
+    for (int64_t i0 = beg; i0 < end; i0 += kPartThreads, buf ^= 1) {
+        // the next step's blobs start to move now (its fields were loaded one step ago)
+        staged &= ~(2u >> buf);                              // clears the bit of buffer buf ^ 1
+        {
+            u32 nb16 = 0u;
+            if (stage_blobs(a.b, r2, lane, wbuf_addr + (u32)(buf ^ 1) * stage_stride, bar_addr + 8u * (u32)(buf ^ 1), a.wbuf, nb16))
+                staged |= 1u << (buf ^ 1);
+            if (buf) beg16_0 = nb16; else beg16_1 = nb16;
+        }
+        {   // records must come sorted by reference_start (coordinate-sorted BAM): compare with the record before
+            int32_t before = __shfl_up_sync(kFull, r1.valid ? r1.pos : 0x7fffffff, 1);
+            if (lane == 0) before = r1.prev;
+            unsorted |= r1.valid && r1.pos < before;
+        }
+        const RawRec cur = r1;
+        r1 = r2;
+        r2 = load_raw(a.b, i0 + 2 * kPartThreads + t, i0 + 2 * kPartThreads + t < end);
+        // readers.py:96-97 unmapped / secondary / supplementary; :104-111 tag absent or not whitelisted
+        const int cell = (!cur.valid || (cur.flag & 0x904) || cur.bc < 0 || cur.bc >= a.n_cells) ? -1 : cur.bc;
+        const int d = cell >= 0 ? (cell >> a.shift) & (bins - 1) : -1;
+        const size_t dd = rank_step(packed, off, bins, buf, d, lane, wid);
+        const bool have = (staged >> buf) & 1u;
+        if (have) { mbar_wait(bar_addr + 8u * (u32)buf, (parity >> buf) & 1u); parity ^= 1u << buf; }
+        if (d >= 0) {
+            uint8_t *dst = a.dst + dd * (size_t)a.slot_bytes;
+            if (have) {
+                const SharedMem smem;
+                build_slot<kCompact>(a, smem, wbuf_addr + (u32)buf * stage_stride + 16u * (cur.off - (buf ? beg16_1 : beg16_0)), cur, cell, dst, qg, scratch_addr, extent_err);
+            } else {
+                const u64 byte_off = 16ull * cur.off;
+                const u64 left = (u64)a.b.blob_bytes > byte_off ? (u64)a.b.blob_bytes - byte_off : 0ull;
+                const GlobalBlob gb{a.b.blob + byte_off, left > 0xffffffffull ? 0xffffffffu : (u32)left};
+                build_slot<kCompact>(a, gb, 0u, cur, cell, dst, qg, scratch_addr, extent_err);
+            }
+        }
+        __syncwarp();                                        // every lane has read the buffer before lane 0 refills it
+    }
+    if (unsorted) atomicOr(a.error_bits, (u64)ERR_UNSORTED);
+    if (extent_err) atomicOr(a.error_bits, (u64)ERR_EXTENT);
+}
+
+// Second digit pass (more than 2048 cells): finished wide slots move to their rank inside the high digit.
+__global__ void __launch_bounds__(kPartThreads, 4)
+k_scatter_slots(SrcSlots src, int64_t chunk, int nchunks, int shift, int bins, const u32 *__restrict__ mat, uint8_t *__restrict__ dst) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Pack *packed = reinterpret_cast<Pack *>(smem_raw);
+    u32 *off = reinterpret_cast<u32 *>(smem_raw + (size_t)2 * bins * sizeof(Pack));
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const u32 *row = mat + (size_t)blockIdx.x * bins;
+    for (int b = t; b < bins; b += kPartThreads) { off[b] = row[b]; packed[b].clear(); packed[bins + b].clear(); }
+    const int64_t n = src.count();
+    int64_t beg = (int64_t)blockIdx.x * chunk, end = beg + chunk;
+    if (end > n) end = n;
+    const int q = src.slot_bytes >> 4;
+    __syncthreads();
+    int buf = 0;
+    for (int64_t i0 = beg; i0 < end; i0 += kPartThreads, buf ^= 1) {
+        const int64_t i = i0 + t;
+        const uint4 *in = reinterpret_cast<const uint4 *>(src.a + (size_t)i * src.slot_bytes);
+        uint4 head = make_uint4(0u, 0u, 0u, 0u);
+        if (i < end) head = in[0];
+        const int d = i < end ? (int)((head.z & 0xffffffu) >> shift) & (bins - 1) : -1;
+        const size_t dd = rank_step(packed, off, bins, buf, d, lane, wid);
+        if (d >= 0) {
+            uint4 *out = reinterpret_cast<uint4 *>(dst + dd * (size_t)src.slot_bytes);
+            out[0] = head;
+            for (int k = 1; k < q; k++) out[k] = in[k];
+        }
+    }
+}
+
+}  // namespace mgatk

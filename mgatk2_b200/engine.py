@@ -201,10 +201,15 @@ class PileupEngine:
             tensors[name] = src.to(dev, non_blocking=True) if src.numel() else torch.empty(0, dtype=src.dtype, device=dev)
         return DeviceBatch(batch.n_records, int(len(batch.blob)), tensors)
 
-    def alloc_device_outputs(self, n_cells: int, mito_length: int, n_records: int, overflow_capacity: int = 4096):
+    def alloc_device_outputs(self, n_cells: int, mito_length: int, n_records: int, overflow_capacity: int = 4096,
+                             max_read_extent: int | None = None):
+        """Device outputs + workspace for batches of up to `n_records` records. `max_read_extent` selects the slot
+        layout the workspace is sized for (32 bytes per read up to an extent of 56, more beyond); without it the
+        workspace covers any extent (144 bytes per read)."""
         import torch
         dev = torch.device("cuda", self.device)
-        ws_bytes = int(self.lib.mgatk_workspace_bytes(int(n_records), int(n_cells)))
+        extent = 1 << 20 if max_read_extent is None else max(int(max_read_extent), 1)
+        ws_bytes = int(self.lib.mgatk_workspace_bytes(int(n_records), int(n_cells), extent))
         if ws_bytes < 0:
             raise PileupKernelError(8, "n_records / n_cells outside limits")
         return DeviceOutputs(
@@ -250,7 +255,7 @@ class PileupEngine:
         for batch in batches:
             acc.max_read_extent = max(int(batch.max_read_extent()), 1)
             db = self.upload(batch)
-            need = int(self.lib.mgatk_workspace_bytes(int(batch.n_records), int(params.n_cells)))
+            need = int(self.lib.mgatk_workspace_bytes(int(batch.n_records), int(params.n_cells), int(acc.max_read_extent)))
             if need > dout.workspace.numel():
                 raise PileupKernelError(3, "workspace smaller than the largest streamed batch needs")
             self.run_device(db, acc, dout)

@@ -14,7 +14,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("prog", ["bitplane_check", "qmask_check", "round_check", "inflate_check"])
+@pytest.mark.parametrize("prog", ["bitplane_check", "qmask_check", "refplane_check", "round_check", "inflate_check"])
 def test_bitplane_helpers_on_host(prog, tmp_path):
     gxx = shutil.which("g++")
     assert gxx, "g++ is part of the image"

@@ -46,10 +46,11 @@ def test_struct_sizes():
 
 
 def test_no_gpu_calls(lib):
-    assert lib.mgatk_abi_version() == 1
+    assert lib.mgatk_abi_version() == 2
     assert lib.mgatk_status_string(4) == b"records are not sorted by reference_start"
-    assert lib.mgatk_workspace_bytes(1_000_000, 2000) > 22_000_000
-    assert lib.mgatk_workspace_bytes(-1, 5) == -1
+    assert lib.mgatk_workspace_bytes(1_000_000, 2000, 50) > 64_000_000
+    assert lib.mgatk_workspace_bytes(1_000_000, 2000, 150) > 2 * 96 * 1_000_000
+    assert lib.mgatk_workspace_bytes(-1, 5, 50) == -1
     import torch
     if not torch.cuda.is_available():
         h = ctypes.c_void_p()

@@ -212,6 +212,34 @@ def test_staging_paths(engine):
     assert_result_equals_oracle(res, ora)
 
 
+def test_compact_slots_complex_cigars(engine):
+    """Reads of at most 56 reference positions travel as 32-byte slots whose planes are already in reference coordinates:
+    soft clips, insertions (the reference's query-position quirk), deletions, hard clips and padding must land
+    exactly where pileup.py:52-95 puts them, on both strands, with hot spots deeper than a stage of the pileup kernel."""
+    rng = np.random.default_rng(23)
+    recs = []
+    for _ in range(6000):
+        L = int(rng.choice([20, 36, 48]))
+        kind = rng.choice(["simple", "clip", "indel"])
+        pos = int(rng.integers(0, 16569)) if rng.random() < 0.6 else int(rng.integers(3000, 3100))
+        recs.append(_random_read(rng, pos, L, int(rng.integers(0, 3)), kind))
+    for _ in range(300):                                  # H and P operations, reads left of 0 and over the end of chrM
+        L = 30
+        cig = [(5, 3), (0, 10), (6, 2), (1, 2), (0, 8), (2, 4), (0, 10), (5, 1)]
+        recs.append(dict(pos=int(rng.choice([-20, -3, 0, 16540, 16560, 16568])), flag=int(rng.choice([0, 16])), mapq=60,
+                         seq="".join(rng.choice(list("ACGT"), size=L)), cigar=cig, tlen=int(rng.integers(0, 50)), bc_idx=1))
+    recs.sort(key=lambda r: r["pos"])
+    batch = ReadBatch.from_records(recs)
+    assert batch.max_read_extent() <= 56
+    for kw in (dict(), dict(min_distance_from_end=0, dedup_mode=2, max_strand_bias=0.8), dict(min_baseq=30, dedup_mode=1, min_distance_from_end=9)):
+        res, ora = run_both(engine, batch, 3, device_path=bool(kw.get("dedup_mode", 0) == 2), **kw)
+        assert_result_equals_oracle(res, ora)
+    # the same reads with a declared extent beyond 56 take the wide slots: same result
+    from oracle.oracle import make_params as mk, run_oracle
+    p = mk(3, max_read_extent=100)
+    assert_result_equals_oracle(engine.run_host(batch, to_lib_params(p), overflow_capacity=1 << 16), run_oracle(batch, p, n_threads=8))
+
+
 @pytest.mark.parametrize("profile,kw", [("atac50", dict()), ("stress150", dict(max_strand_bias=0.8, min_distance_from_end=10, min_reads_per_cell=300)),
                                         ("atac70", dict(dedup_mode=1, flags=1))])
 def test_streamed_batches_equal_one_batch(engine, profile, kw):
