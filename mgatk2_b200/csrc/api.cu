@@ -20,6 +20,7 @@ namespace {
 constexpr int kMaxChunks = 148 * MGATK_SCATTER_CTAS * (256 / kPartThreads);   // partition CTAs: one wave (bounds the open write heads)
 constexpr int kMaxDigitBits = 11;                    // 2048 bins * 20 B = 40 KB of shared memory per scatter CTA
 constexpr int kMaxStages = 16;
+constexpr int kTotalsMaxPpad = 1 << 16;              // contigs up to this long get their base totals from the pileup kernel itself
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -35,7 +36,7 @@ struct Layout {          // carve-up of the caller's workspace
     SlotFmt fmt;
     int stage_bytes, cap_reads, unit_reads; int64_t max_units;
     size_t slots[2];         // two slot arrays: partition output(s) and the compacted reads to pile up
-    size_t mat, part, cell_start, unit_start, units, units_big, scan_state, scalars, total;
+    size_t mat, part, cell_start, unit_start, units, units_big, scan_state, totals32, scalars, total;
     int64_t dedup_blocks;
 };
 
@@ -65,7 +66,7 @@ bool make_layout(int64_t n, int32_t n_cells, int extent, Layout &L) {
     L.cap_reads = L.stage_bytes / L.fmt.bytes;
     {   // reads per unit: leave room for the reads of the halo and of the chunk the tile border is rounded down to
         const int v = env_int("MGATK_UNIT_READS", 0);
-        L.unit_reads = v > 0 ? (v < 32 ? 32 : v) : (int)(0.8 * L.cap_reads);
+        L.unit_reads = v > 0 ? (v < 32 ? 32 : v) : (int)(0.68 * L.cap_reads);
         if (L.unit_reads < 32) L.unit_reads = 32;
     }
     L.max_units = (int64_t)n_cells + n / L.unit_reads + 1;
@@ -81,6 +82,7 @@ bool make_layout(int64_t n, int32_t n_cells, int extent, Layout &L) {
     L.units_big = o; o += align_up((size_t)L.max_units * sizeof(Unit));
     L.dedup_blocks = (n + kDedupTile - 1) / kDedupTile + 1;
     L.scan_state = o; o += align_up((size_t)L.dedup_blocks * 8);
+    L.totals32 = o; o += align_up((size_t)4 * kTotalsMaxPpad * 4);
     L.scalars = o; o += 256;
     L.total = o;
     return true;
@@ -345,6 +347,11 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     a.extent = p->max_read_extent;
     a.slot_bytes = L.fmt.bytes; a.words = L.fmt.words;
     a.cap_reads = L.cap_reads;
+    // cross-cell base totals: reduced by the counting kernels themselves (32-bit atomics on a [4][ppad] scratch, widened
+    // below) when the contig fits the scratch, else by a pass over the finished planes
+    const bool fused_totals = !accumulate && ppad <= kTotalsMaxPpad && env_int("MGATK_FUSED_TOTALS", 1);
+    a.totals32 = fused_totals ? (u32 *)(ws + L.totals32) : nullptr;
+    if (fused_totals) CU(cudaMemsetAsync(a.totals32, 0, (size_t)4 * ppad * 4, s));
     PileupArgs a2 = a;
     a2.units = (Unit *)(ws + L.units_big); a2.n_units = work_counter + 4; a2.work_counter = work_counter + 5;
     rc = launch_pileup(h, s, compact, a, a2, L.stage_bytes);
@@ -353,12 +360,17 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     if (accumulate) return MGATK_OK;                     // filters, coverage, statistics: mgatk_stream_finish_device
 
     // ---- reference-allele totals, median depth ----
-    dim3 tg((ppad / 2 + 127) / 128, (C + kTotalsCellGroup - 1) / kTotalsCellGroup);
-    k_base_totals<<<tg, 128, 0, s>>>(o->planes, C, P, ppad, (u64 *)o->base_totals);
-    h->launches++;
-    if (o->overflow_capacity > 0) {
-        k_base_totals_overflow<<<8, 256, 0, s>>>(o->overflow, o->stats, o->overflow_capacity, P, (u64 *)o->base_totals);
+    if (fused_totals) {
+        k_totals_widen<<<(P + 255) / 256, 256, 0, s>>>(a.totals32, P, ppad, (u64 *)o->base_totals);
         h->launches++;
+    } else {
+        dim3 tg((ppad / 2 + 127) / 128, (C + kTotalsCellGroup - 1) / kTotalsCellGroup);
+        k_base_totals<<<tg, 128, 0, s>>>(o->planes, C, P, ppad, (u64 *)o->base_totals);
+        h->launches++;
+        if (o->overflow_capacity > 0) {
+            k_base_totals_overflow<<<8, 256, 0, s>>>(o->overflow, o->stats, o->overflow_capacity, P, (u64 *)o->base_totals);
+            h->launches++;
+        }
     }
     k_median<<<C, 256, 0, s>>>(o->planes, P, ppad, o->cell_qc);
     h->launches++;

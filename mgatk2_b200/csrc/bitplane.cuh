@@ -221,6 +221,42 @@ MG_HD void query_mask_group(const M &mem, u32 seq_addr /*4-aligned*/, int L, int
     oV = mV; o0 = m0 & mV; o1 = m1 & mV;
 }
 
+// All query planes of a read of at most 56 bases at once (the compact slot, common.cuh): every word of SEQ and QUAL
+// is loaded once, groups of eight bases outside the window are skipped as a whole, the window itself is one mask at the
+// end. g[w] = { V, B0, B1 } of query bases 32w .. 32w+31.
+template <class M>
+MG_HD void query_planes56(const M &mem, u32 seq_addr /*4-aligned*/, int L, int q_lo, int q_hi, QualGe qg, u32 (&g)[2][3]) {
+    const u32 qual_addr = seq_addr + (u32)((L + 1) >> 1);
+    const u32 qsh = (qual_addr & 3u) * 8u, qa = qual_addr & ~3u;
+    const int hi = q_hi < L ? q_hi : L;                              // window [q_lo, hi), hi <= 56
+    const int lo = q_lo > 0 ? q_lo : 0;
+    const int g_lo = lo >> 3;
+    int g_n = ((hi + 7) >> 3) - g_lo;                                // groups g_lo .. g_lo + g_n - 1 meet the window
+    if (g_n < 0 || hi <= lo) g_n = 0;
+    u32 qw[15];
+#pragma unroll
+    for (int k = 0; k < 15; k++) qw[k] = ((u32)(k - 2 * g_lo) < (u32)(2 * g_n + (g_n > 0))) ? mem.ld32(qa + 4u * (u32)k) : 0u;
+    u32 mV[2] = {0u, 0u}, m0[2] = {0u, 0u}, m1[2] = {0u, 0u};
+#pragma unroll
+    for (int gi = 0; gi < 7; gi++) {
+        if ((u32)(gi - g_lo) < (u32)g_n) {
+            const u32 s = mem.ld32(seq_addr + 4u * (u32)gi);
+            const u32 ok = qual_ok8_top(funnel_r(qw[2 * gi], qw[2 * gi + 1], qsh), funnel_r(qw[2 * gi + 1], qw[2 * gi + 2], qsh), qg);
+            const Planes8 e = seq_planes8_raw(s);
+            const int w = gi >> 2, b = gi & 3;
+            if (b == 0) { mV[w] = insert_top_byte<0>(mV[w], e.v & ok); m0[w] = insert_top_byte<0>(m0[w], e.b0); m1[w] = insert_top_byte<0>(m1[w], e.b1); }
+            else if (b == 1) { mV[w] = insert_top_byte<1>(mV[w], e.v & ok); m0[w] = insert_top_byte<1>(m0[w], e.b0); m1[w] = insert_top_byte<1>(m1[w], e.b1); }
+            else if (b == 2) { mV[w] = insert_top_byte<2>(mV[w], e.v & ok); m0[w] = insert_top_byte<2>(m0[w], e.b0); m1[w] = insert_top_byte<2>(m1[w], e.b1); }
+            else { mV[w] = insert_top_byte<3>(mV[w], e.v & ok); m0[w] = insert_top_byte<3>(m0[w], e.b0); m1[w] = insert_top_byte<3>(m1[w], e.b1); }
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+        const u32 v = mV[w] & bit_range(lo - 32 * w, hi - 32 * w);   // pileup.py:67-78 (also cuts bases >= L)
+        g[w][0] = v; g[w][1] = m0[w] & v; g[w][2] = m1[w] & v;
+    }
+}
+
 // the same -> four words at out + 16w
 template <class M>
 MG_HD void build_query_mask_group(const M &mem, u32 seq_addr /*4-aligned*/, u32 out /*16-aligned*/, int L, int w, int q_lo, int q_hi, QualGe qg) {

@@ -69,6 +69,10 @@ struct SharedMem {                   // by 32-bit shared address
     }
 };
 
+struct SharedMemPure {               // loads the compiler may merge and schedule (no `volatile`): only for data that is not
+    __device__ __forceinline__ u32 ld32(u32 a) const { u32 v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }   // rewritten while in use
+};
+
 struct GlobalBlob {                  // one record's cigar|seq|qual in the caller's blob, by offset; nothing is read beyond `avail`
     const uint8_t *base; u32 avail;
     __device__ __forceinline__ u32 ld32(u32 a) const { return a + 4u <= avail ? __ldg(reinterpret_cast<const u32 *>(base + a)) : 0u; }
@@ -90,6 +94,22 @@ __device__ __forceinline__ bool mbar_try_wait(u32 bar, u32 parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) { while (!mbar_try_wait(bar, parity)) {} }
+// the same with a suspend-time hint (ns): the thread sleeps in hardware instead of burning issue slots on the probe
+__device__ __forceinline__ void mbar_wait_sleepy(u32 bar, u32 parity, u32 hint_ns) {
+    u32 ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+    } while (!ok);
+}
+// wait, then hand out a zero that DEPENDS on the wait: added to a shared address it keeps reordering-free (non-volatile)
+// loads of the data the barrier guards behind the wait
+__device__ __forceinline__ u32 mbar_wait_token(u32 bar, u32 parity) {
+    mbar_wait(bar, parity);
+    u32 z;
+    asm volatile("mov.u32 %0, 0;" : "=r"(z) :: "memory");
+    return z;
+}
 // global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar`
 __device__ __forceinline__ void bulk_load(u32 dst_shared, const void *src, u32 bytes, u32 bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -34,6 +34,16 @@ k_base_totals(const uint16_t *__restrict__ planes, int n_cells, int P, int ppad,
     }
 }
 
+// the totals k_pileup reduced while counting ([4][ppad] u32: a batch holds fewer than 2^31 records) -> int64 [P][4]
+__global__ void k_totals_widen(const u32 *__restrict__ t32, int P, int ppad, u64 *__restrict__ totals) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    ulonglong2 lo, hi;
+    lo.x = t32[p]; lo.y = t32[(size_t)ppad + p]; hi.x = t32[(size_t)2 * ppad + p]; hi.y = t32[(size_t)3 * ppad + p];
+    reinterpret_cast<ulonglong2 *>(totals)[2 * (size_t)p] = lo;
+    reinterpret_cast<ulonglong2 *>(totals)[2 * (size_t)p + 1] = hi;
+}
+
 __global__ void k_base_totals_overflow(const mgatk_overflow *__restrict__ ovf, const mgatk_stats *__restrict__ stats,
                                        int64_t cap, int P, u64 *__restrict__ totals) {
     const int64_t n = min((int64_t)stats->n_overflow, cap);

@@ -223,7 +223,7 @@ __device__ __forceinline__ size_t rank_step(Pack *packed, u32 *off, int bins, in
 }
 
 #ifndef MGATK_SCATTER_CTAS
-#define MGATK_SCATTER_CTAS 2
+#define MGATK_SCATTER_CTAS 3
 #endif
 constexpr int kWarpBufSlack = 64;    // the plane builder may load this far past the last staged byte
 
@@ -240,7 +240,7 @@ struct ScatterArgs {
 };
 
 __host__ __device__ inline size_t scatter_smem_bytes(int bins, int wbuf, int words, bool compact) {
-    return rank_smem_bytes(bins) + (size_t)kPartWarps * 2 * (wbuf + kWarpBufSlack) + (compact ? 0 : (size_t)kPartThreads * 16 * words);
+    return rank_smem_bytes(bins) + (size_t)kPartWarps * (wbuf + kWarpBufSlack) + (compact ? 0 : (size_t)kPartThreads * 16 * words);
 }
 
 struct RawRec { int32_t pos, tlen, bc, prev; u32 off; uint16_t flag, lseq, ncig; uint8_t mapq; bool valid; };
@@ -256,114 +256,131 @@ __device__ __forceinline__ RawRec load_raw(const mgatk_batch &b, int64_t i, bool
     return r;
 }
 
-// The blobs of a warp's 32 records of one step: when they sit back to back in the caller's blob (they do when the host
-// packs records in file order) and fit the warp's buffer, lane 0 arms the barrier and issues one bulk copy. Returns
-// whether the step is staged; `beg16` = blob offset (16-byte units) of the first byte in the buffer.
+// The blobs of a warp's 32 records of one step lie in [min offset, max end) of the caller's blob - back to back when the
+// host packs records in file order. When that range fits the warp's buffer, lane 0 arms the barrier and issues ONE bulk
+// copy of it. Returns whether the step is staged; `beg16` = blob offset (16-byte units) of the first byte in the buffer.
 __device__ __forceinline__ bool stage_blobs(const mgatk_batch &b, const RawRec &r, int lane, u32 buf_addr, u32 bar, int wbuf, u32 &beg16) {
-    const u32 sz16 = r.valid ? (u32)((4 * (int)r.ncig + (((int)r.lseq + 1) >> 1) + (int)r.lseq + 15) >> 4) : 0u;
-    const u64 end = (u64)r.off + sz16;
-    const u64 prev_end = __shfl_up_sync(kFull, end, 1);
-    const bool contiguous = !r.valid || lane == 0 || (u64)r.off == prev_end;
-    const u32 valid_mask = __ballot_sync(kFull, r.valid);
-    if (!valid_mask) return false;
-    const int last = 31 - __clz(valid_mask);
-    const u64 range_end = __shfl_sync(kFull, end, last);
-    beg16 = __shfl_sync(kFull, r.off, 0);
-    const u64 bytes = 16 * (range_end - (u64)beg16);
-    const bool ok = __all_sync(kFull, contiguous) && range_end >= (u64)beg16 && bytes > 0 && bytes <= (u64)wbuf && 16 * range_end <= (u64)b.blob_bytes;
+    const u32 sz16 = (u32)((4 * (int)r.ncig + (((int)r.lseq + 1) >> 1) + (int)r.lseq + 15) >> 4);
+    u32 end = r.off + sz16;
+    if (end < r.off) end = 0xffffffffu;                      // offsets near 2^32: too large for the buffer below
+    const u32 lo = __reduce_min_sync(kFull, r.valid ? r.off : 0xffffffffu), hi = __reduce_max_sync(kFull, r.valid ? end : 0u);
+    beg16 = lo;
+    const bool ok = hi > lo && hi - lo <= (u32)(wbuf >> 4) && 16ull * hi <= (u64)b.blob_bytes;
     if (ok && lane == 0) {
-        fence_proxy_async();                                 // the warp's reads of this buffer (two steps ago) come first
-        mbar_expect_tx(bar, (u32)bytes);
-        bulk_load(buf_addr, b.blob + 16 * (size_t)beg16, (u32)bytes, bar);
+        fence_proxy_async();                                 // the warp's reads of the buffer (the step before) come first
+        mbar_expect_tx(bar, 16u * (hi - lo));
+        bulk_load(buf_addr, b.blob + 16 * (size_t)lo, 16u * (hi - lo), bar);
     }
     return ok;
 }
 
-// The slot of one record. `mem` / `cig_addr` reach its blob (staged in shared memory or straight from global memory),
-// `dst` is its place in the partitioned array. kCompact: registers only, one 256-bit store.
-template <bool kCompact, class M>
-__device__ __forceinline__ void build_slot(const ScatterArgs &a, const M &mem, u32 cig_addr, const RawRec &r, int cell, uint8_t *dst,
-                                           QualGe qg, u32 scratch_addr, bool &extent_err) {
-    const int L = r.lseq, ncig = r.ncig;
+// What a slot carries besides its planes
+struct SlotHead { u32 pos, tlen_abs, meta, tn5off; int L, ncig, span; bool beyond, simple; };
+
+template <class M>
+__device__ __forceinline__ SlotHead slot_head(const ScatterArgs &a, const M &mem, u32 cig_addr, const RawRec &r, bool &extent_err) {
+    SlotHead h;
+    h.L = r.lseq; h.ncig = r.ncig;
     const int32_t t = r.tlen;
-    const u32 tlen_abs = t < 0 ? (u32)(-(int64_t)t) : (u32)t;            // abs(read.template_length), readers.py:124
-    u32 meta = ((r.flag & 0x10) ? SM_STRAND : 0u) | ((r.flag & 0x1) ? SM_PAIRED : 0u) | ((int)r.mapq >= a.min_mapq ? SM_MAPQ_OK : 0u) |
-               (L == 0 ? SM_EMPTY : 0u);
-    const int span = cigar_ref_span(mem, cig_addr, ncig);
-    const bool beyond = L > a.extent || span > a.extent;                  // MGATK_ERR_EXTENT: the slot stays empty
-    if (beyond) extent_err = true;
-    const int q_lo = a.dist > 0 ? a.dist : 0;                             // pileup.py:67-72
-    int q_hi = a.dist > 0 ? L - a.dist : L;
-    if (qg.none) q_hi = q_lo;
-    const u32 w0 = ncig > 0 ? mem.ld32(cig_addr) : 0u;
+    h.pos = (u32)r.pos;
+    h.tlen_abs = t < 0 ? (u32)(-(int64_t)t) : (u32)t;                    // abs(read.template_length), readers.py:124
+    h.meta = ((r.flag & 0x10) ? SM_STRAND : 0u) | ((r.flag & 0x1) ? SM_PAIRED : 0u) | ((int)r.mapq >= a.min_mapq ? SM_MAPQ_OK : 0u) |
+             (h.L == 0 ? SM_EMPTY : 0u);
+    const u32 w0 = h.ncig > 0 ? mem.ld32(cig_addr) : 0u;
     // one aligned block over all of SEQ: reference offset i <-> query base i, the query planes are the slot's planes
-    const bool simple = ncig == 1 && cigar_op_aligned((int)(w0 & 15u)) && (int)(w0 >> 4) >= L;
-    const u32 seq_addr = cig_addr + 4u * (u32)ncig;
-    const u32 tn5off = L > 0 ? (u32)(L - 1) : 0u;
-    if (kCompact) {
-        u32 g[2][3] = {{0u, 0u, 0u}, {0u, 0u, 0u}};
-        const int nq = beyond ? 0 : L > 32 ? 2 : (L > 0 ? 1 : 0);        // L <= 56
+    h.simple = h.ncig == 1 && cigar_op_aligned((int)(w0 & 15u)) && (int)(w0 >> 4) >= h.L;
+    h.span = h.ncig == 1 ? (cigar_op_aligned((int)(w0 & 15u)) || cigar_op_ref_only((int)(w0 & 15u)) ? ((int)(w0 >> 4) < kOpCap ? (int)(w0 >> 4) : kOpCap) : 0)
+                         : cigar_ref_span(mem, cig_addr, h.ncig);
+    h.beyond = h.L > a.extent || h.span > a.extent;                        // MGATK_ERR_EXTENT: the slot stays empty
+    if (h.beyond) extent_err = true;
+    h.tn5off = h.L > 0 ? (u32)(h.L - 1) : 0u;
+    return h;
+}
+
+// planes of a compact slot (at most 56 reference positions) in registers
+template <class M>
+__device__ __forceinline__ void compact_planes(const ScatterArgs &a, const M &mem, u32 cig_addr, const SlotHead &h, QualGe qg, u32 (&g)[2][3]) {
+    const int q_lo = a.dist > 0 ? a.dist : 0;                             // pileup.py:67-72
+    int q_hi = a.dist > 0 ? h.L - a.dist : h.L;
+    if (qg.none) q_hi = q_lo;
+    if (h.beyond || h.L == 0 || !(h.meta & SM_MAPQ_OK)) {                // (a read below min_mapq only takes part in dedup, Q2)
 #pragma unroll
-        for (int w = 0; w < 2; w++) if (w < nq) query_mask_group(mem, seq_addr, L, w, q_lo, q_hi, qg, g[w][0], g[w][1], g[w][2]);
-        if (!simple && nq > 0) {
-            QueryPlanes64 q;
-            q.v = ((u64)g[1][0] << 32) | g[0][0]; q.b0 = ((u64)g[1][1] << 32) | g[0][1]; q.b1 = ((u64)g[1][2] << 32) | g[0][2];
+        for (int w = 0; w < 2; w++) { g[w][0] = 0u; g[w][1] = 0u; g[w][2] = 0u; }
+        return;
+    }
+    query_planes56(mem, cig_addr + 4u * (u32)h.ncig, h.L, q_lo, q_hi, qg, g);
+    if (!h.simple) {
+        QueryPlanes64 q;
+        q.v = ((u64)g[1][0] << 32) | g[0][0]; q.b0 = ((u64)g[1][1] << 32) | g[0][1]; q.b1 = ((u64)g[1][2] << 32) | g[0][2];
 #pragma unroll
-            for (int k = 0; k < 2; k++) ref_group(mem, cig_addr, ncig, q, k, g[k]);
+        for (int k = 0; k < 2; k++) ref_group(mem, cig_addr, h.ncig, q, k, g[k]);
+    }
+}
+
+__device__ __forceinline__ void store_compact(uint8_t *dst, const SlotHead &h, const u32 (&g)[2][3]) {     // one 256-bit store: a whole sector
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(h.pos), "r"(h.tlen_abs), "r"(g[0][0]),
+                 "r"((g[1][0] & 0xffffffu) | (h.meta << 24)), "r"(g[0][1]), "r"((g[1][1] & 0xffffffu) | ((h.tn5off & 63u) << 24)),
+                 "r"(g[0][2]), "r"(g[1][2] & 0xffffffu) : "memory");
+}
+
+// a wide slot, written group by group
+template <class M>
+__device__ __forceinline__ void store_wide(const ScatterArgs &a, const M &mem, u32 cig_addr, const SlotHead &h, const RawRec &r, int cell,
+                                           uint8_t *dst, QualGe qg, u32 scratch_addr) {
+    const int q_lo = a.dist > 0 ? a.dist : 0;
+    int q_hi = a.dist > 0 ? h.L - a.dist : h.L;
+    if (qg.none) q_hi = q_lo;
+    const int W = a.words, L = h.L;
+    const bool indirect = L > 32 * W || h.span > 32 * W;
+    const u32 seq_addr = cig_addr + 4u * (u32)h.ncig;
+    uint4 *out = reinterpret_cast<uint4 *>(dst);
+    out[0] = make_uint4(h.pos, h.tlen_abs, (u32)cell | ((h.meta | (indirect ? SM_INDIRECT : 0u)) << 24), h.tn5off & 0xffffu);
+    const int nq = (L + 31) >> 5;
+    if (indirect || L == 0 || h.beyond) {
+        out[1] = indirect ? make_uint4(r.off, (u32)L | ((u32)h.ncig << 16), 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        for (int k = 1; k < W; k++) out[1 + k] = make_uint4(0u, 0u, 0u, 0u);
+    } else if (h.simple) {
+        for (int k = 0; k < W; k++) {
+            u32 v = 0u, b0 = 0u, b1 = 0u;
+            if (k < nq) query_mask_group(mem, seq_addr, L, k, q_lo, q_hi, qg, v, b0, b1);
+            out[1 + k] = make_uint4(v, b0, b1, 0u);
         }
-        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"((u32)r.pos), "r"(tlen_abs), "r"(g[0][0]),
-                     "r"((g[1][0] & 0xffffffu) | (meta << 24)), "r"(g[0][1]), "r"((g[1][1] & 0xffffffu) | ((tn5off & 63u) << 24)),
-                     "r"(g[0][2]), "r"(g[1][2] & 0xffffffu) : "memory");
     } else {
-        const int W = a.words;
-        const bool indirect = L > 32 * W || span > 32 * W;
-        if (indirect) meta |= SM_INDIRECT;
-        uint4 *out = reinterpret_cast<uint4 *>(dst);
-        out[0] = make_uint4((u32)r.pos, tlen_abs, (u32)cell | (meta << 24), tn5off & 0xffffu);
-        const int nq = (L + 31) >> 5;
-        if (indirect || L == 0 || beyond) {
-            out[1] = indirect ? make_uint4(r.off, (u32)L | ((u32)ncig << 16), 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-            for (int k = 1; k < W; k++) out[1 + k] = make_uint4(0u, 0u, 0u, 0u);
-        } else if (simple) {
-            for (int k = 0; k < W; k++) {
-                u32 v = 0u, b0 = 0u, b1 = 0u;
-                if (k < nq) query_mask_group(mem, seq_addr, L, k, q_lo, q_hi, qg, v, b0, b1);
-                out[1 + k] = make_uint4(v, b0, b1, 0u);
-            }
-        } else {
-            const SharedMem smem;
-            for (int w = 0; w < nq; w++) {
-                u32 v, b0, b1;
-                query_mask_group(mem, seq_addr, L, w, q_lo, q_hi, qg, v, b0, b1);
-                smem.st128(scratch_addr + 16u * (u32)w, v, b0, b1, 0u);
-            }
-            const QueryPlanesMem<SharedMem> q{smem, scratch_addr, nq};
-            for (int k = 0; k < W; k++) {
-                u32 o[3];
-                ref_group(mem, cig_addr, ncig, q, k, o);
-                out[1 + k] = make_uint4(o[0], o[1], o[2], 0u);
-            }
+        const SharedMem smem;
+        for (int w = 0; w < nq; w++) {
+            u32 v, b0, b1;
+            query_mask_group(mem, seq_addr, L, w, q_lo, q_hi, qg, v, b0, b1);
+            smem.st128(scratch_addr + 16u * (u32)w, v, b0, b1, 0u);
+        }
+        const QueryPlanesMem<SharedMem> q{smem, scratch_addr, nq};
+        for (int k = 0; k < W; k++) {
+            u32 o[3];
+            ref_group(mem, cig_addr, h.ncig, q, k, o);
+            out[1 + k] = make_uint4(o[0], o[1], o[2], 0u);
         }
     }
 }
 
+// One step = kPartThreads records in BAM order, one per thread. Per warp: the blobs of the step sit in the warp's
+// staging buffer (bulk copy issued one step earlier); compact slots are built in registers straight away, the buffer is
+// handed back to the TMA unit for the next step, and only then the CTA ranks the step (two barriers) and stores.
 template <bool kCompact>
 __global__ void __launch_bounds__(kPartThreads, MGATK_SCATTER_CTAS)
 k_scatter_planes(ScatterArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ __align__(8) u64 s_bar[kPartWarps][2];
+    __shared__ __align__(8) u64 s_bar[kPartWarps];
     const int bins = a.bins;
     Pack *packed = reinterpret_cast<Pack *>(smem_raw);                 // [2][bins] per-warp byte counters of the step
     u32 *off = reinterpret_cast<u32 *>(smem_raw + (size_t)2 * bins * sizeof(Pack));   // [bins] running destination offsets
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const u32 stage_stride = (u32)(a.wbuf + kWarpBufSlack);
-    const u32 wbuf_addr = (u32)__cvta_generic_to_shared(smem_raw + rank_smem_bytes(bins)) + (u32)wid * 2u * stage_stride;
+    const u32 wbuf_addr = (u32)__cvta_generic_to_shared(smem_raw + rank_smem_bytes(bins)) + (u32)wid * stage_stride;
     const u32 scratch_addr = kCompact ? 0u
-        : (u32)__cvta_generic_to_shared(smem_raw + rank_smem_bytes(bins) + (size_t)kPartWarps * 2 * stage_stride) + (u32)t * 16u * (u32)a.words;
-    const u32 bar_addr = (u32)__cvta_generic_to_shared(&s_bar[wid][0]);
+        : (u32)__cvta_generic_to_shared(smem_raw + rank_smem_bytes(bins) + (size_t)kPartWarps * stage_stride) + (u32)t * 16u * (u32)a.words;
+    const u32 bar_addr = (u32)__cvta_generic_to_shared(&s_bar[wid]);
     const u32 *row = a.mat + (size_t)blockIdx.x * bins;
     for (int b = t; b < bins; b += kPartThreads) { off[b] = row[b]; packed[b].clear(); packed[bins + b].clear(); }
-    if (lane == 0) { mbar_init(bar_addr, 1); mbar_init(bar_addr + 8, 1); mbar_fence_init(); }
+    if (lane == 0) { mbar_init(bar_addr, 1); mbar_fence_init(); }
     const int64_t n = a.b.n_records;
     int64_t beg = (int64_t)blockIdx.x * a.chunk, end = beg + a.chunk;
     if (end > n) end = n;
@@ -371,20 +388,11 @@ k_scatter_planes(ScatterArgs a) {
     RawRec r1 = load_raw(a.b, beg + t, beg + t < end);                                  // two steps of loads in flight
     RawRec r2 = load_raw(a.b, beg + kPartThreads + t, beg + kPartThreads + t < end);
     __syncthreads();
-    u32 beg16_0 = 0u, beg16_1 = 0u;                          // blob offset of the first staged byte of either buffer
-    u32 staged = 0u, parity = 0u;                            // bit b: buffer b holds a staged step / parity of its next wait
-    if (stage_blobs(a.b, r1, lane, wbuf_addr, bar_addr, a.wbuf, beg16_0)) staged |= 1u;
+    u32 beg16 = 0u, parity = 0u;
+    bool have = stage_blobs(a.b, r1, lane, wbuf_addr, bar_addr, a.wbuf, beg16);         // the buffer holds (will hold) the current step
     int buf = 0;
     bool unsorted = false, extent_err = false;
     for (int64_t i0 = beg; i0 < end; i0 += kPartThreads, buf ^= 1) {
-        // the next step's blobs start to move now (its fields were loaded one step ago)
-        staged &= ~(2u >> buf);                              // clears the bit of buffer buf ^ 1
-        {
-            u32 nb16 = 0u;
-            if (stage_blobs(a.b, r2, lane, wbuf_addr + (u32)(buf ^ 1) * stage_stride, bar_addr + 8u * (u32)(buf ^ 1), a.wbuf, nb16))
-                staged |= 1u << (buf ^ 1);
-            if (buf) beg16_0 = nb16; else beg16_1 = nb16;
-        }
         {   // records must come sorted by reference_start (coordinate-sorted BAM): compare with the record before
             int32_t before = __shfl_up_sync(kFull, r1.valid ? r1.pos : 0x7fffffff, 1);
             if (lane == 0) before = r1.prev;
@@ -396,22 +404,48 @@ k_scatter_planes(ScatterArgs a) {
         // readers.py:96-97 unmapped / secondary / supplementary; :104-111 tag absent or not whitelisted
         const int cell = (!cur.valid || (cur.flag & 0x904) || cur.bc < 0 || cur.bc >= a.n_cells) ? -1 : cur.bc;
         const int d = cell >= 0 ? (cell >> a.shift) & (bins - 1) : -1;
-        const size_t dd = rank_step(packed, off, bins, buf, d, lane, wid);
-        const bool have = (staged >> buf) & 1u;
-        if (have) { mbar_wait(bar_addr + 8u * (u32)buf, (parity >> buf) & 1u); parity ^= 1u << buf; }
-        if (d >= 0) {
-            uint8_t *dst = a.dst + dd * (size_t)a.slot_bytes;
+        const u64 byte_off = 16ull * cur.off;
+        const u64 left = (u64)a.b.blob_bytes > byte_off ? (u64)a.b.blob_bytes - byte_off : 0ull;
+        const GlobalBlob gb{a.b.blob + byte_off, left > 0xffffffffull ? 0xffffffffu : (u32)left};    // when the step is not staged
+        if (kCompact) {
+            SlotHead h;
+            u32 g[2][3];
             if (have) {
-                const SharedMem smem;
-                build_slot<kCompact>(a, smem, wbuf_addr + (u32)buf * stage_stride + 16u * (cur.off - (buf ? beg16_1 : beg16_0)), cur, cell, dst, qg, scratch_addr, extent_err);
-            } else {
-                const u64 byte_off = 16ull * cur.off;
-                const u64 left = (u64)a.b.blob_bytes > byte_off ? (u64)a.b.blob_bytes - byte_off : 0ull;
-                const GlobalBlob gb{a.b.blob + byte_off, left > 0xffffffffull ? 0xffffffffu : (u32)left};
-                build_slot<kCompact>(a, gb, 0u, cur, cell, dst, qg, scratch_addr, extent_err);
+                const u32 tok = mbar_wait_token(bar_addr, parity);
+                parity ^= 1u;
+                if (d >= 0) {
+                    const SharedMemPure smem;
+                    const u32 sb = wbuf_addr + 16u * (cur.off - beg16) + tok;
+                    h = slot_head(a, smem, sb, cur, extent_err);
+                    compact_planes(a, smem, sb, h, qg, g);
+                }
+            } else if (d >= 0) {
+                h = slot_head(a, gb, 0u, cur, extent_err);
+                compact_planes(a, gb, 0u, h, qg, g);
             }
+            __syncwarp();                                    // every lane has read the buffer: it goes back to the TMA unit
+            have = stage_blobs(a.b, r1, lane, wbuf_addr, bar_addr, a.wbuf, beg16);
+            const size_t dd = rank_step(packed, off, bins, buf, d, lane, wid);
+            if (d >= 0) store_compact(a.dst + dd * 32, h, g);
+        } else {
+            const size_t dd = rank_step(packed, off, bins, buf, d, lane, wid);
+            u32 tok = 0u;
+            if (have) { tok = mbar_wait_token(bar_addr, parity); parity ^= 1u; }
+            if (d >= 0) {
+                uint8_t *dst = a.dst + dd * (size_t)a.slot_bytes;
+                if (have) {
+                    const SharedMem smem;
+                    const u32 sb = wbuf_addr + 16u * (cur.off - beg16) + tok;
+                    const SlotHead h = slot_head(a, smem, sb, cur, extent_err);
+                    store_wide(a, smem, sb, h, cur, cell, dst, qg, scratch_addr);
+                } else {
+                    const SlotHead h = slot_head(a, gb, 0u, cur, extent_err);
+                    store_wide(a, gb, 0u, h, cur, cell, dst, qg, scratch_addr);
+                }
+            }
+            __syncwarp();
+            have = stage_blobs(a.b, r1, lane, wbuf_addr, bar_addr, a.wbuf, beg16);
         }
-        __syncwarp();                                        // every lane has read the buffer before lane 0 refills it
     }
     if (unsorted) atomicOr(a.error_bits, (u64)ERR_UNSORTED);
     if (extent_err) atomicOr(a.error_bits, (u64)ERR_EXTENT);

@@ -139,6 +139,7 @@ struct PileupArgs {
     int accumulate;                  // streaming: add the counts of this batch to the planes, nothing else (MGATK_FLAG_ACCUMULATE)
     int slot_bytes, words;           // slot layout (common.cuh)
     int cap_reads;                   // slots per stage (main) / per batch (big)
+    u32 *totals32;                   // [4][ppad] cross-cell base totals of this batch (fwd + rev after the filters), or null
     double max_bias;
 };
 
@@ -201,6 +202,14 @@ __device__ __forceinline__ void finish_chunk(const PileupArgs &a, int cell, int 
         }
     }
     const u32 cov = ((cnt[0] + cnt[1]) + (cnt[2] + cnt[3])) + ((cnt[4] + cnt[5]) + (cnt[6] + cnt[7]));  // pileup.py:150
+    if (a.totals32 && cov) {                         // reference-allele vote input (writers.py:220-222): one reduction per base,
+#pragma unroll                                       // lanes = consecutive words of the base's row (exact, before saturation)
+        for (int b = 0; b < 4; b++) {                // predicated RED, no branch
+            const u32 t = cnt[2 * b] + cnt[2 * b + 1];
+            asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %1, 0;\n @q red.global.add.u32 [%0], %1;\n}"
+                         :: "l"(a.totals32 + (size_t)b * ppad + p), "r"(t) : "memory");
+        }
+    }
     if (cov == 0) { if (!a.raw) { cnt[8] = 0; cnt[9] = 0; } }   // pileup.py:152-153: dropped with its Tn5 counts
     else { sum += cov; covered++; maxd = max(maxd, cov); }
     u32 vals[MGATK_N_PLANES];
@@ -396,9 +405,12 @@ __device__ __forceinline__ void unit_statistics(const PileupArgs &a, int cell, i
 }
 
 #ifndef MGATK_PILEUP_CTAS
-#define MGATK_PILEUP_CTAS 3
+#define MGATK_PILEUP_CTAS 4            // 56 registers per thread (20 bytes of spills): measured faster than 3 CTAs of 72 registers
 #endif
-constexpr int kStages = 2;            // units in flight per CTA of the main kernel
+#ifndef MGATK_PILEUP_STAGES
+#define MGATK_PILEUP_STAGES 3
+#endif
+constexpr int kStages = MGATK_PILEUP_STAGES;   // units in flight per CTA of the main kernel: a warp may run this far ahead of the slowest
 
 // ---------------------------------------------------------------------------------------------
 // Main kernel: every unit fits one stage. Warp kWarpsPerCta is the producer: unit index from the global counter, the
@@ -408,7 +420,7 @@ constexpr int kStages = 2;            // units in flight per CTA of the main ker
 // only holds back the refill of its own stage.
 // ---------------------------------------------------------------------------------------------
 template <bool kCompact, int kPpad>
-__global__ void __launch_bounds__(kThreads + 32, MGATK_PILEUP_CTAS)
+__global__ void __launch_bounds__(kThreads + 32, kCompact ? MGATK_PILEUP_CTAS : 3)     // wide slots: the walk over plane groups needs the registers
 k_pileup_main(PileupArgs a, int stage_bytes) {
     extern __shared__ __align__(128) uint8_t dyn[];          // [kStages][stage_bytes]
     __shared__ __align__(8) u64 s_full[kStages], s_empty[kStages];
@@ -426,7 +438,7 @@ k_pileup_main(PileupArgs a, int stage_bytes) {
             const int n_units = *a.n_units;
             for (u32 k = 0;; k++) {
                 const u32 b = k % kStages;
-                if (k >= (u32)kStages) mbar_wait(empty0 + 8u * b, ((k / kStages) - 1u) & 1u);     // all consumer warps left the stage
+                if (k >= (u32)kStages) mbar_wait_sleepy(empty0 + 8u * b, ((k / kStages) - 1u) & 1u, 2000u);     // all consumer warps left the stage
                 Unit un;
                 for (;;) {
                     const int u = atomicAdd(a.work_counter, 1);
@@ -450,7 +462,7 @@ k_pileup_main(PileupArgs a, int stage_bytes) {
     const TransposeConst tc = make_transpose_const(lane);
     for (u32 k = 0;; k++) {
         const u32 b = k % kStages;
-        mbar_wait(full0 + 8u * b, (k / kStages) & 1u);
+        mbar_wait_sleepy(full0 + 8u * b, (k / kStages) & 1u, 500u);
         const Unit un = s_unit[b];
         if (un.cell < 0) break;
         const u32 addr = stage0 + b * (u32)stage_bytes;

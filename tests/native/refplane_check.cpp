@@ -89,6 +89,9 @@ int main() {
         if (small) {
             u32 g[2][3] = {{0, 0, 0}, {0, 0, 0}};
             for (int w = 0; w < nq; w++) query_mask_group(mem, seq, L, w, lo, hi, qg, g[w][0], g[w][1], g[w][2]);
+            u32 g56[2][3];
+            query_planes56(mem, seq, L, lo, hi, qg, g56);           // the all-at-once form gives the same planes
+            if (memcmp(g56, g, sizeof(g))) { printf("query_planes56 mismatch L=%d d=%d minq=%d\n", L, d, minq); bad++; break; }
             QueryPlanes64 q;
             q.v = ((unsigned long long)g[1][0] << 32) | g[0][0]; q.b0 = ((unsigned long long)g[1][1] << 32) | g[0][1];
             q.b1 = ((unsigned long long)g[1][2] << 32) | g[0][2];
