@@ -44,15 +44,26 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true", help="check per-cell QC rows against the oracle at full size")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (the bench line): every rank owns a shard of --cells x --records. strong (side measurement): ONE "
+                         "input of --strong-cells x --strong-records (BASELINE configs[2]) is split by barcode over the ranks")
+    ap.add_argument("--strong-cells", type=int, default=10_000)
+    ap.add_argument("--strong-records", type=int, default=200_000_000)
+    ap.add_argument("--strong-parts", type=int, default=8, help="the strong-scaling input is the union of this many "
+                    "barcode-disjoint parts (seeded per part, so it is the same input whatever the number of ranks)")
     return ap.parse_args()
 
 
 def config_dict(a, n_gpus):
-    return {"workload": f"synthetic 10x-ATAC chrM, BASELINE configs[{CONFIG_INDEX}]: {a.cells} cells x {a.records} "
-                        f"records per GPU, profile {a.profile}, " + {"run": "default run filters (q20 mapq30 d5 bias1.0, "
-                        "alignment_and_fragment_length dedup)", "tenx": "tenx filters (q0 mapq0 d5 alignment_start dedup)",
-                        "stress": "stress filters (q20 mapq30 d10 bias0.8)"}[a.params],
-            "cells_per_gpu": a.cells, "records_per_gpu": a.records, "profile": a.profile,
+    filt = {"run": "default run filters (q20 mapq30 d5 bias1.0, alignment_and_fragment_length dedup)",
+            "tenx": "tenx filters (q0 mapq0 d5 alignment_start dedup)", "stress": "stress filters (q20 mapq30 d10 bias0.8)"}[a.params]
+    if getattr(a, "scaling", "weak") == "strong":
+        wl = (f"synthetic 10x-ATAC chrM, BASELINE configs[2] shape: ONE input of {a.strong_cells} cells x {a.strong_records} records "
+              f"split by barcode over {n_gpus} GPU(s), profile {a.profile}, {filt}")
+    else:
+        wl = (f"synthetic 10x-ATAC chrM, BASELINE configs[{CONFIG_INDEX}]: {a.cells} cells x {a.records} records per GPU, "
+              f"profile {a.profile}, {filt}")
+    return {"workload": wl, "cells_per_gpu": a.cells, "records_per_gpu": a.records, "profile": a.profile,
             "sharding": f"by barcode, {n_gpus} shard(s), no data-path collective",
             "l2": "inputs per step (>2 GB) exceed the 126 MB L2; no explicit flush"}
 
@@ -242,7 +253,26 @@ def run_b200(a):
     from mgatk2_b200.synth import synth_batch
 
     t_gen = time.perf_counter()
-    batch = synth_batch(a.cells, a.records, a.profile, seed=BASE_SEED + CONFIG_INDEX + 1000 * rank)
+    if a.scaling == "strong":
+        # one input, split by barcode: the union of `strong_parts` barcode-disjoint parts; rank r counts parts
+        # r*parts/world .. (r+1)*parts/world - 1 merged back into coordinate order (what routing one BAM by barcode gives)
+        if a.strong_parts % world or a.strong_cells % a.strong_parts or a.strong_records % a.strong_parts:
+            raise SystemExit("--strong-parts must divide --strong-cells and --strong-records and be a multiple of the ranks")
+        from mgatk2_b200.batch import ReadBatch as _RB
+        per, cpp = a.strong_parts // world, a.strong_cells // a.strong_parts
+        parts = []
+        for k in range(per):
+            m = rank * per + k
+            b = synth_batch(cpp, a.strong_records // a.strong_parts, a.profile, seed=BASE_SEED + 7000 + m)
+            b.bc_idx = np.where(b.bc_idx >= 0, b.bc_idx + k * cpp, b.bc_idx).astype(np.int32)
+            parts.append(b)
+        batch = _RB.concat(parts)
+        if per > 1:
+            batch = batch.take(np.argsort(batch.pos, kind="stable"))
+        del parts
+        a.cells, a.records = cpp * per, batch.n_records
+    else:
+        batch = synth_batch(a.cells, a.records, a.profile, seed=BASE_SEED + CONFIG_INDEX + 1000 * rank)
     t_gen = time.perf_counter() - t_gen
     extent = batch.max_read_extent()
     params = default_params(a.cells, extent, a.params)
@@ -294,10 +324,32 @@ def run_b200(a):
     ms_step = float(t.item()) / a.steps
     total_records = a.records * world
     value = total_records / (ms_step * 1e-3)
+    if a.scaling == "strong":          # the one cross-cell quantity of the path: base totals of all shards, one NCCL all-reduce
+        tot = torch.from_numpy(res.base_totals.copy()).cuda()
+        kept_all = torch.tensor([res.stats["filtered_reads"]], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot)
+            dist.all_reduce(kept_all)
+        strong_check = {"filtered_reads_all_ranks": int(kept_all.item()), "base_totals_sum_all_ranks": int(tot.sum().item())}
 
     # ---- e2e: host buffers through the C ABI, every step uploads its inputs and downloads its result ----
     # (1) blocking call per step (mgatk_pileup_host); (2) the same steps through submit / wait with two batches in
     #     flight, which is how a caller with more than one batch drives the library (upload k+1 next to download k).
+    # the box's host -> device ceiling with all ranks copying at once (plain pinned cudaMemcpyAsync, 1 GiB x 8): what the
+    # upload of e2e competes for
+    probe_src = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+    probe_dst = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+    probe_dst.copy_(probe_src, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(8):
+        probe_dst.copy_(probe_src, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    h2d_ceiling_gbs = 8 * (1 << 30) * world / float(dt.item()) / 1e9
+    del probe_src, probe_dst
     hout = eng.alloc_host_outputs(a.cells, 16569)
     hout2 = eng.alloc_host_outputs(a.cells, 16569)
     eng.run_host(pbatch, params, out=hout)      # warm-up: device buffers get allocated here
@@ -383,16 +435,19 @@ def run_b200(a):
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "u32",
         "data": "synthetic", "config": config_dict(a, world), "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": a.e2e_steps,
                 "mode": "mgatk_pileup_host_submit/_wait, two batches in flight, pinned host buffers",
-                "blocking_value": e2e_blocking},
+                "blocking_value": e2e_blocking,
+                "h2d_gbs": h2d * world * e2e_value / total_records / 1e9,
+                "h2d_ceiling_gbs": h2d_ceiling_gbs,
+                "h2d_ceiling_note": "plain pinned 1 GiB host->device copies on all ranks at once; the upload of e2e cannot beat it"},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "counted": {"total_reads": res.stats["total_reads"], "filtered_reads": res.stats["filtered_reads"],
                     "dup_with_length": res.stats["dup_with_length"], "sum_depth": int(res.cell_qc["sum_depth"].sum())},
-        "synth_seconds": t_gen,
+        "synth_seconds": t_gen, **({"strong": strong_check} if a.scaling == "strong" else {}),
     }))
     if world > 1:
         dist.destroy_process_group()

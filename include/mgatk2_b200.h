@@ -206,6 +206,10 @@ int mgatk_stream_finish_device(mgatk_handle *h, const mgatk_params *params, cons
  * (values above 65535 are not representable here; use the fused path for those). */
 int mgatk_filter_strand_bias_device(mgatk_handle *h, uint16_t *planes_dev, int32_t n_cells, int32_t mito_length,
                                     double max_strand_bias, void *stream);
+/* The same rule on 32-bit planes (same shape): exact for any depth. This is what PileupGenerator.filter_strand_bias
+ * is given when a caller hands over the dict generate_pileup() returned (pileup.py:128: plain Python ints there). */
+int mgatk_filter_strand_bias_u32_device(mgatk_handle *h, uint32_t *planes_dev, int32_t n_cells, int32_t mito_length,
+                                        double max_strand_bias, void *stream);
 
 /* Same, but batch and outputs are HOST buffers (pinned for full speed): H2D copy,
  * kernels, D2H copy, synchronise. Device buffers are cached inside the handle. */

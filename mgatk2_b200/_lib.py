@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libmgatk2_b200.so")
 EXPORTS = (
     "mgatk_abi_version", "mgatk_status_string", "mgatk_create", "mgatk_destroy", "mgatk_last_error",
     "mgatk_workspace_bytes", "mgatk_pileup_device", "mgatk_check_stats", "mgatk_pileup_host",
-    "mgatk_filter_strand_bias_device", "mgatk_stream_begin_device", "mgatk_stream_finish_device",
+    "mgatk_filter_strand_bias_device", "mgatk_filter_strand_bias_u32_device", "mgatk_stream_begin_device", "mgatk_stream_finish_device",
     "mgatk_last_launch_count", "mgatk_last_stage_times", "mgatk_pileup_host_submit", "mgatk_pileup_host_wait",
 )
 
@@ -72,6 +72,7 @@ def load():
     lib.mgatk_check_stats.argtypes = [ctypes.c_void_p]
     lib.mgatk_filter_strand_bias_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                                     ctypes.c_double, ctypes.c_void_p]
+    lib.mgatk_filter_strand_bias_u32_device.argtypes = lib.mgatk_filter_strand_bias_device.argtypes
     lib.mgatk_pileup_host.argtypes = [ctypes.c_void_p, ctypes.POINTER(ParamsC), ctypes.POINTER(MgatkBatchC),
                                       ctypes.POINTER(OutputsC)]
     lib.mgatk_pileup_host_submit.argtypes = [ctypes.c_void_p, ctypes.POINTER(ParamsC), ctypes.POINTER(MgatkBatchC),

@@ -186,8 +186,20 @@ def _finish_part(path, config, wl_index, batch, barcodes, qual_missing, first_pa
         bc = table[batch.bc_idx] if batch.n_records else np.zeros(0, np.int32)
     batch.bc_idx = np.ascontiguousarray(bc, dtype=np.int32)
     ok = ((batch.flag & 0x904) == 0) & (batch.bc_idx >= 0)
-    if (qual_missing & ok).any():                                               # readers.py:158
-        raise BAMReadError(str(path), "Read error: record without base qualities")
+    for i in np.nonzero(qual_missing & ok)[0].tolist():
+        # readers.py:146-158: np.array(None) raises when the SimpleRead is built, i.e. only for a record that survived
+        # dedup. The few QUAL-less survivors of stage 1 are checked here the way the reference's sets would see them
+        # (an earlier stage-1 record of the same barcode, start and strand [and |tlen|] makes this one a duplicate).
+        dup = False
+        if not config.dedup.skip:
+            j = i - 1
+            while j >= 0 and batch.pos[j] == batch.pos[i] and not dup:
+                dup = bool(ok[j] and batch.bc_idx[j] == batch.bc_idx[i] and (batch.flag[j] & 0x10) == (batch.flag[i] & 0x10)
+                           and (not config.dedup.use_fragment_length
+                                or abs(int(batch.tlen[j])) == abs(int(batch.tlen[i]))))
+                j -= 1
+        if not dup:
+            raise BAMReadError(str(path), "Read error: record without base qualities")
     return batch
 
 

@@ -364,7 +364,7 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
         k_totals_widen<<<(P + 255) / 256, 256, 0, s>>>(a.totals32, P, ppad, (u64 *)o->base_totals);
         h->launches++;
     } else {
-        dim3 tg((ppad / 2 + 127) / 128, (C + kTotalsCellGroup - 1) / kTotalsCellGroup);
+        dim3 tg((ppad / 2 + 127) / 128, min((C + kTotalsCellGroup - 1) / kTotalsCellGroup, 65535));
         k_base_totals<<<tg, 128, 0, s>>>(o->planes, C, P, ppad, (u64 *)o->base_totals);
         h->launches++;
         if (o->overflow_capacity > 0) {
@@ -372,7 +372,7 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
             h->launches++;
         }
     }
-    k_median<<<C, 256, 0, s>>>(o->planes, P, ppad, o->cell_qc);
+    k_median<<<C, 256, 0, s>>>(o->planes, P, ppad, o->cell_qc, o->overflow_capacity > 0 ? o->overflow : nullptr, o->stats, o->overflow_capacity);
     h->launches++;
     CU(cudaGetLastError());
     mark(h, s, "totals+median");
@@ -386,6 +386,20 @@ int ensure(mgatk_handle *h, DevBuf &b, size_t bytes) {
     size_t want = bytes < 256 ? 256 : bytes;
     CU(cudaMalloc(&b.p, want));
     b.cap = want;
+    return MGATK_OK;
+}
+
+template <class T>
+int filter_planes(mgatk_handle *h, T *planes_dev, int32_t n_cells, int32_t mito_length, double max_strand_bias, void *stream) {
+    if (!h) return MGATK_ERR_BAD_ARG;
+    h->err.clear();
+    if (!planes_dev || n_cells < 0 || mito_length <= 0) return fail(h, MGATK_ERR_BAD_ARG, "bad argument");
+    if (n_cells == 0) return MGATK_OK;
+    CU(cudaSetDevice(h->device));
+    dim3 grid((mito_length + 255) / 256, n_cells < 65535 ? n_cells : 65535);
+    k_filter_planes<T><<<grid, 256, 0, (cudaStream_t)stream>>>(planes_dev, n_cells, mito_length, (int)MGATK_POS_PAD(mito_length), max_strand_bias);
+    h->launches = 1;
+    CU(cudaGetLastError());
     return MGATK_OK;
 }
 
@@ -461,16 +475,12 @@ int mgatk_pileup_device(mgatk_handle *h, const mgatk_params *params, const mgatk
 
 int mgatk_filter_strand_bias_device(mgatk_handle *h, uint16_t *planes_dev, int32_t n_cells, int32_t mito_length,
                                     double max_strand_bias, void *stream) {
-    if (!h) return MGATK_ERR_BAD_ARG;
-    h->err.clear();
-    if (!planes_dev || n_cells < 0 || mito_length <= 0) return fail(h, MGATK_ERR_BAD_ARG, "bad argument");
-    if (n_cells == 0) return MGATK_OK;
-    CU(cudaSetDevice(h->device));
-    dim3 grid((mito_length + 255) / 256, n_cells);
-    k_filter_planes<<<grid, 256, 0, (cudaStream_t)stream>>>(planes_dev, n_cells, mito_length, (int)MGATK_POS_PAD(mito_length), max_strand_bias);
-    h->launches = 1;
-    CU(cudaGetLastError());
-    return MGATK_OK;
+    return filter_planes<uint16_t>(h, planes_dev, n_cells, mito_length, max_strand_bias, stream);
+}
+
+int mgatk_filter_strand_bias_u32_device(mgatk_handle *h, uint32_t *planes_dev, int32_t n_cells, int32_t mito_length,
+                                        double max_strand_bias, void *stream) {
+    return filter_planes<uint32_t>(h, planes_dev, n_cells, mito_length, max_strand_bias, stream);
 }
 
 int mgatk_stream_begin_device(mgatk_handle *h, const mgatk_params *p, const mgatk_outputs *o, void *stream) {
@@ -507,14 +517,14 @@ int mgatk_stream_finish_device(mgatk_handle *h, const mgatk_params *p, const mga
     a.apply_bias = !a.raw && !(p->max_strand_bias >= 1.0);
     k_clear_parked<<<(C + 255) / 256, 256, 0, s>>>(o->cell_qc, C);
     k_stream_finish<<<h->sm_count * 8, 256, 0, s>>>(a, C, p->min_reads_per_cell);
-    dim3 tg((ppad / 2 + 127) / 128, (C + kTotalsCellGroup - 1) / kTotalsCellGroup);
+    dim3 tg((ppad / 2 + 127) / 128, min((C + kTotalsCellGroup - 1) / kTotalsCellGroup, 65535));
     k_base_totals<<<tg, 128, 0, s>>>(o->planes, C, P, ppad, (u64 *)o->base_totals);
     h->launches += 3;
     if (o->overflow_capacity > 0) {
         k_base_totals_overflow<<<8, 256, 0, s>>>(o->overflow, o->stats, o->overflow_capacity, P, (u64 *)o->base_totals);
         h->launches++;
     }
-    k_median<<<C, 256, 0, s>>>(o->planes, P, ppad, o->cell_qc);
+    k_median<<<C, 256, 0, s>>>(o->planes, P, ppad, o->cell_qc, o->overflow_capacity > 0 ? o->overflow : nullptr, o->stats, o->overflow_capacity);
     h->launches++;
     CU(cudaGetLastError());
     return MGATK_OK;

@@ -14,7 +14,8 @@ __global__ void __launch_bounds__(128)
 k_base_totals(const uint16_t *__restrict__ planes, int n_cells, int P, int ppad, u64 *__restrict__ totals) {
     const int pp = blockIdx.x * blockDim.x + threadIdx.x;          // position pair
     if (2 * pp >= ppad) return;
-    const int c0 = blockIdx.y * kTotalsCellGroup, c1 = min(n_cells, c0 + kTotalsCellGroup);
+    for (int c0 = blockIdx.y * kTotalsCellGroup; c0 < n_cells; c0 += gridDim.y * kTotalsCellGroup) {   // (grid.y is capped at 65535)
+    const int c1 = min(n_cells, c0 + kTotalsCellGroup);
     u32 s[4][2] = {};
     for (int c = c0; c < c1; c++) {
         const u32 *row = reinterpret_cast<const u32 *>(planes + (size_t)c * MGATK_N_PLANES * ppad) + pp;
@@ -31,6 +32,7 @@ k_base_totals(const uint16_t *__restrict__ planes, int n_cells, int P, int ppad,
         if (p < P)
 #pragma unroll
             for (int b = 0; b < 4; b++) if (s[b][k]) atomicAdd(&totals[(size_t)p * 4 + b], (u64)s[b][k]);
+    }
     }
 }
 
@@ -56,24 +58,27 @@ __global__ void k_base_totals_overflow(const mgatk_overflow *__restrict__ ovf, c
 // ---------------------------------------------------------------------------------------------
 // PileupGenerator.filter_strand_bias (pileup.py:128-154) as a stand-alone pass over raw planes.
 // ---------------------------------------------------------------------------------------------
+template <class T>                                           // T = uint16_t (saturating coverage) or uint32_t (exact)
 __global__ void __launch_bounds__(256)
-k_filter_planes(uint16_t *__restrict__ planes, int n_cells, int P, int ppad, double max_bias) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
-    if (p >= P || c >= n_cells) return;
-    uint16_t *row = planes + (size_t)c * MGATK_N_PLANES * ppad + p;
-    u32 cov = 0;
+k_filter_planes(T *__restrict__ planes, int n_cells, int P, int ppad, double max_bias) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    for (int c = blockIdx.y; c < n_cells; c += gridDim.y) {  // (grid.y is capped at 65535 blocks)
+        T *row = planes + (size_t)c * MGATK_N_PLANES * ppad + p;
+        u32 cov = 0;
 #pragma unroll
-    for (int b = 0; b < 4; b++) {
-        u32 f = row[(size_t)(2 * b) * ppad], r = row[(size_t)(2 * b + 1) * ppad];
-        const u32 t = f + r;
-        if (t > 0) {
-            const double bias = (double)max(f, r) / (double)t;
-            if (bias > max_bias) { f = 0; r = 0; row[(size_t)(2 * b) * ppad] = 0; row[(size_t)(2 * b + 1) * ppad] = 0; }
+        for (int b = 0; b < 4; b++) {
+            u32 f = row[(size_t)(2 * b) * ppad], r = row[(size_t)(2 * b + 1) * ppad];
+            const u32 t = f + r;
+            if (t > 0) {
+                const double bias = (double)max(f, r) / (double)t;
+                if (bias > max_bias) { f = 0; r = 0; row[(size_t)(2 * b) * ppad] = 0; row[(size_t)(2 * b + 1) * ppad] = 0; }
+            }
+            cov += f + r;
         }
-        cov += f + r;
+        row[(size_t)MGATK_PLANE_COVERAGE * ppad] = sizeof(T) == 2 ? (T)min(cov, 65535u) : (T)cov;
+        if (cov == 0) { row[(size_t)MGATK_PLANE_TN5_FWD * ppad] = 0; row[(size_t)MGATK_PLANE_TN5_REV * ppad] = 0; }
     }
-    row[(size_t)MGATK_PLANE_COVERAGE * ppad] = (uint16_t)min(cov, 65535u);
-    if (cov == 0) { row[(size_t)MGATK_PLANE_TN5_FWD * ppad] = 0; row[(size_t)MGATK_PLANE_TN5_REV * ppad] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -117,44 +122,88 @@ __global__ void k_clear_parked(mgatk_cell_qc *__restrict__ qc, int n_cells) {
 // ---------------------------------------------------------------------------------------------
 // Median depth over covered positions (writers.py:190): the two middle order statistics by a
 // two-level (high byte, low byte) counting select on the coverage plane. One CTA per cell.
+// The plane is saturated at 65535; a cell whose deepest position lies above that (bulk mode, a deep
+// pile) has the exact depths of its saturated positions in the overflow list: an order statistic that
+// falls among them is selected there (radix select over the 32-bit values, one byte per pass), so the
+// medians are exact whatever the depth (np.median of the unsaturated depths in the reference).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 median_scan(const u32 *hist, u32 rem, u32 &bin) {      // first bin with cumulative count > rem; returns rem inside it
+    u32 acc = 0;
+    for (int b = 0; b < 256; b++) { if (rem < acc + hist[b]) { bin = b; return rem - acc; } acc += hist[b]; }
+    bin = 255;
+    return 0;
+}
+
 __global__ void __launch_bounds__(256)
-k_median(const uint16_t *__restrict__ planes, int P, int ppad, mgatk_cell_qc *__restrict__ qc) {
+k_median(const uint16_t *__restrict__ planes, int P, int ppad, mgatk_cell_qc *__restrict__ qc,
+         const mgatk_overflow *__restrict__ ovf, const mgatk_stats *__restrict__ stats, int64_t ovf_cap) {
     __shared__ u32 hist[256];
     __shared__ u32 sel[4];                                   // bin, remainder for lo / hi
+    __shared__ u32 s_list, s_val;
     const int c = blockIdx.x, t = threadIdx.x;
     const uint16_t *cov = planes + ((size_t)c * MGATK_N_PLANES + MGATK_PLANE_COVERAGE) * ppad;
     hist[t] = 0;
+    if (t == 0) s_list = 0;
     __syncthreads();
     for (int p = t; p < P; p += 256) { const u32 v = cov[p]; if (v) atomicAdd(&hist[v >> 8], 1u); }
+    // saturated positions of this cell whose exact depth sits in the overflow list
+    const bool deep = qc[c].max_depth > 65535u && ovf != nullptr;
+    const int64_t n_list = deep ? min((int64_t)stats->n_overflow, ovf_cap) : 0;
+    const u32 want = ((u32)MGATK_PLANE_COVERAGE << 24);
+    if (deep) {
+        u32 mine = 0;
+        for (int64_t e = t; e < n_list; e += 256) mine += ovf[e].cell == c && (ovf[e].plane_pos & 0xff000000u) == want;
+        if (mine) atomicAdd(&s_list, mine);
+    }
     __syncthreads();
     u32 res[2] = {0, 0};
+    u32 k[2] = {0, 0}, n_below = 0;
     if (t == 0) {
         u32 n = 0;
         for (int b = 0; b < 256; b++) n += hist[b];
         sel[0] = sel[2] = 0xffffffffu;
         if (n) {
-            const u32 k[2] = {(n - 1) / 2, n / 2};
-            for (int s = 0; s < 2; s++) {
-                u32 acc = 0;
-                for (int b = 0; b < 256; b++) { if (k[s] < acc + hist[b]) { sel[2 * s] = b; sel[2 * s + 1] = k[s] - acc; break; } acc += hist[b]; }
-            }
+            k[0] = (n - 1) / 2; k[1] = n / 2;
+            for (int s = 0; s < 2; s++) sel[2 * s + 1] = median_scan(hist, k[s], sel[2 * s]);
         }
+        s_val = n;
     }
     __syncthreads();
     if (sel[0] == 0xffffffffu) { if (t == 0) { qc[c].median_lo = 0; qc[c].median_hi = 0; } return; }
+    {
+        const u32 n = s_val;
+        k[0] = (n - 1) / 2; k[1] = n / 2;
+        n_below = n - s_list;                                // values below the listed ones (a true 65535 included)
+    }
     for (int s = 0; s < 2; s++) {
-        const u32 bin = sel[2 * s], rem = sel[2 * s + 1];
-        if (s == 1 && bin == sel[0]) {                       // same high byte: low-byte histogram is still valid
-            if (t == 0) { u32 acc = 0; for (int b = 0; b < 256; b++) { if (rem < acc + hist[b]) { res[1] = (bin << 8) | b; break; } acc += hist[b]; } }
-            break;
+        if (k[s] >= n_below) {                               // the (k - n_below)-th smallest listed depth
+            u32 rem = k[s] - n_below, prefix = 0, mask = 0;
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                __syncthreads();
+                hist[t] = 0;
+                __syncthreads();
+                for (int64_t e = t; e < n_list; e += 256)
+                    if (ovf[e].cell == c && (ovf[e].plane_pos & 0xff000000u) == want && (ovf[e].value & mask) == prefix)
+                        atomicAdd(&hist[(ovf[e].value >> shift) & 255u], 1u);
+                __syncthreads();
+                if (t == 0) { u32 bin; const u32 r = median_scan(hist, rem, bin); sel[0] = bin; sel[1] = r; }
+                __syncthreads();
+                prefix |= sel[0] << shift; mask |= 255u << shift; rem = sel[1];
+            }
+            res[s] = prefix;
+            continue;
         }
+        const u32 bin = sel[2 * s], rem = sel[2 * s + 1];
+        if (!(s == 1 && bin == sel[0])) {                    // (same high byte as the lower median: its low-byte histogram is still valid)
+            __syncthreads();
+            hist[t] = 0;
+            __syncthreads();
+            for (int p = t; p < P; p += 256) { const u32 v = cov[p]; if (v && (v >> 8) == bin) atomicAdd(&hist[v & 255], 1u); }
+            __syncthreads();
+        }
+        if (t == 0) { u32 b; median_scan(hist, rem, b); s_val = (bin << 8) | b; }
         __syncthreads();
-        hist[t] = 0;
-        __syncthreads();
-        for (int p = t; p < P; p += 256) { const u32 v = cov[p]; if (v && (v >> 8) == bin) atomicAdd(&hist[v & 255], 1u); }
-        __syncthreads();
-        if (t == 0) { u32 acc = 0; for (int b = 0; b < 256; b++) { if (rem < acc + hist[b]) { res[s] = (bin << 8) | b; break; } acc += hist[b]; } }
+        res[s] = s_val;
     }
     if (t == 0) { qc[c].median_lo = res[0]; qc[c].median_hi = res[1]; }
 }

@@ -44,6 +44,7 @@ class PileupResult:
     min_reads_per_cell: int = 1
     stage_ms: dict = field(default_factory=dict)
     launches: int = 0
+    columns: np.ndarray | None = None      # whitelist index of every row of `planes` / `cell_qc` (None: row = whitelist index)
 
     def plane(self, k: int, exact: bool = True) -> np.ndarray:
         """Plane k as uint32 [n_cells, P]; exact=True patches saturated entries from the overflow list."""
@@ -239,35 +240,58 @@ class PileupEngine:
         return OutputsC(dout.planes.data_ptr(), dout.cell_qc.data_ptr(), dout.stats.data_ptr(), dout.base_totals.data_ptr(),
                         dout.overflow.data_ptr() if dout.overflow_capacity else None, dout.overflow_capacity)
 
-    def run_stream(self, batches, params: ParamsC, dout: "DeviceOutputs") -> PileupResult:
-        """Batches cut on reference_start borders (`ReadBatch.split_on_start_borders`), in file order: every batch adds its
-        raw counts to the resident planes (MGATK_FLAG_ACCUMULATE), the finish pass applies the cell gate, the strand-bias
-        filter, coverage / Tn5 gating and the depth statistics. Equals the one-batch result while no entry passes 65535."""
+    def stream_begin(self, params: ParamsC, dout: "DeviceOutputs") -> None:
+        """Zero the resident outputs of a stream of batches (mgatk_stream_begin_device)."""
         import torch
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         oc = self._outputs_c(dout)
         rc = self.lib.mgatk_stream_begin_device(self.handle, ctypes.byref(params), ctypes.byref(oc), stream)
         if rc:
             self._raise(rc)
+        dout.stream_launches = 0
+
+    def stream_add(self, batch: ReadBatch, params: ParamsC, dout: "DeviceOutputs") -> None:
+        """One batch of a stream (cut on reference_start borders, file order): upload, stages 1-6 with
+        MGATK_FLAG_ACCUMULATE - the batch's raw counts are added to the resident planes."""
+        import torch
+        if batch.n_records == 0:
+            return
         acc = ParamsC.from_buffer_copy(params)
         acc.flags = int(params.flags) | _lib.FLAG_ACCUMULATE
-        launches = 0
-        for batch in batches:
-            acc.max_read_extent = max(int(batch.max_read_extent()), 1)
-            db = self.upload(batch)
-            need = int(self.lib.mgatk_workspace_bytes(int(batch.n_records), int(params.n_cells), int(acc.max_read_extent)))
-            if need > dout.workspace.numel():
-                raise PileupKernelError(3, "workspace smaller than the largest streamed batch needs")
-            self.run_device(db, acc, dout)
-            launches += self.launch_count()
-            torch.cuda.synchronize(self.device)          # the batch's device buffers are released before the next upload
+        acc.max_read_extent = max(int(batch.max_read_extent()), 1)
+        need = int(self.lib.mgatk_workspace_bytes(int(batch.n_records), int(params.n_cells), int(acc.max_read_extent)))
+        if need < 0:
+            raise PileupKernelError(8, "n_records / n_cells outside limits")
+        if need > dout.workspace.numel():                # a later part may be larger (or longer reads) than the first
+            dout.workspace = None
+            dout.workspace = torch.empty(need, dtype=torch.uint8, device=torch.device("cuda", self.device))
+        db = self.upload(batch)
+        self.run_device(db, acc, dout)
+        dout.stream_launches = getattr(dout, "stream_launches", 0) + self.launch_count()
+        torch.cuda.synchronize(self.device)              # the batch's device buffers are released before the next upload
+
+    def stream_finish(self, params: ParamsC, dout: "DeviceOutputs") -> PileupResult:
+        """What needs the totals of all batches (mgatk_stream_finish_device): cell gate, strand-bias filter, coverage /
+        Tn5 gating, depth statistics, base totals, medians; then the download."""
+        import torch
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        oc = self._outputs_c(dout)
         rc = self.lib.mgatk_stream_finish_device(self.handle, ctypes.byref(params), ctypes.byref(oc), stream)
         if rc:
             self._raise(rc)
-        launches += self.launch_count()
+        launches = getattr(dout, "stream_launches", 0) + self.launch_count()
         res = self.download(dout, params)
         res.launches = launches
         return res
+
+    def run_stream(self, batches, params: ParamsC, dout: "DeviceOutputs") -> PileupResult:
+        """Batches cut on reference_start borders (`ReadBatch.split_on_start_borders`), in file order: every batch adds its
+        raw counts to the resident planes (MGATK_FLAG_ACCUMULATE), the finish pass applies the cell gate, the strand-bias
+        filter, coverage / Tn5 gating and the depth statistics. Equals the one-batch result while no entry passes 65535."""
+        self.stream_begin(params, dout)
+        for batch in batches:
+            self.stream_add(batch, params, dout)
+        return self.stream_finish(params, dout)
 
     def download(self, dout: "DeviceOutputs", params: ParamsC) -> PileupResult:
         """Synchronise and bring a device result back as a PileupResult (checks the device error bits)."""

@@ -10,13 +10,15 @@ from . import _lib
 from .batch import ReadBatch
 from .engine import PLANE_NAMES, PileupEngine, PileupResult
 
-_ENGINES: dict[int, PileupEngine] = {}
+_ENGINES: dict[tuple, PileupEngine] = {}
 
 
-def get_engine(device: int = 0) -> PileupEngine:
-    if device not in _ENGINES:
-        _ENGINES[device] = PileupEngine(device)
-    return _ENGINES[device]
+def get_engine(device: int = 0, instance: int = 0) -> PileupEngine:
+    """One engine (= one C-ABI handle) per device; `instance` separates the handles when a device is listed more than
+    once (two host threads must not share a handle)."""
+    if (device, instance) not in _ENGINES:
+        _ENGINES[(device, instance)] = PileupEngine(device)
+    return _ENGINES[(device, instance)]
 
 
 def reads_to_batch(reads, bc_idx: int = 0) -> ReadBatch:
@@ -34,13 +36,8 @@ def reads_to_batch(reads, bc_idx: int = 0) -> ReadBatch:
     return ReadBatch.from_records(recs)
 
 
-def cell_pileup_dict(res: PileupResult, cell: int, raw: bool = False) -> dict[int, dict[str, int]]:
-    """The per-cell pileup dict of pileup.py:100-124 (keys 0-based positions) from the dense planes."""
-    P = res.mito_length
-    planes = np.stack([res.plane(k)[cell] for k in range(11)])            # exact (overflow list applied), [11, P]
-    keep = planes[10] > 0
-    if raw:
-        keep |= (planes[8] > 0) | (planes[9] > 0)
+def planes_to_dict(planes: np.ndarray, keep: np.ndarray) -> dict[int, dict[str, int]]:
+    """Rows of [11, P] exact planes -> the per-position dicts of pileup.py:100-124 for the positions in `keep`."""
     out = {}
     for pos in np.nonzero(keep)[0].tolist():
         v = planes[:, pos]
@@ -52,6 +49,15 @@ def cell_pileup_dict(res: PileupResult, cell: int, raw: bool = False) -> dict[in
             d[f"{base}_rev"] = r
         out[pos] = d
     return out
+
+
+def cell_pileup_dict(res: PileupResult, cell: int, raw: bool = False) -> dict[int, dict[str, int]]:
+    """The per-cell pileup dict of pileup.py:100-124 (keys 0-based positions) from the dense planes."""
+    planes = np.stack([res.plane(k)[cell] for k in range(11)])            # exact (overflow list applied), [11, P]
+    keep = planes[10] > 0
+    if raw:
+        keep |= (planes[8] > 0) | (planes[9] > 0)
+    return planes_to_dict(planes, keep)
 
 
 class PileupGenerator:
@@ -77,7 +83,8 @@ class PileupGenerator:
         return cell_pileup_dict(self._run(batch, _lib.FLAG_RAW_PILEUP), 0, raw=True)
 
     def filter_strand_bias(self, pileup: dict[int, dict[str, int]]) -> dict[int, dict[str, int]]:
-        """pileup.py:128-154 on the device (mgatk_filter_strand_bias_device) for a dict generate_pileup returned."""
+        """pileup.py:128-154 on the device for a dict generate_pileup returned: the dict's plain integers go into
+        32-bit planes (`mgatk_filter_strand_bias_u32_device`), so any depth takes the same device path."""
         import ctypes
 
         import torch
@@ -86,38 +93,18 @@ class PileupGenerator:
         eng = get_engine(self.device)
         P = int(self.config.mito_length)
         ppad = (P + 63) // 64 * 64
-        host = np.zeros((1, 11, ppad), np.uint16)
-        big = {}
+        host = np.zeros((1, 11, ppad), np.uint32)
         for pos, d in pileup.items():
-            vals = [d["A_fwd"], d["A_rev"], d["C_fwd"], d["C_rev"], d["G_fwd"], d["G_rev"], d["T_fwd"], d["T_rev"],
-                    d["tn5_cuts_fwd"], d["tn5_cuts_rev"], d["depth"]]
-            if max(vals) > 65535:
-                big[pos] = d
-                continue
-            host[0, :, pos] = vals
-        dev = torch.from_numpy(host).cuda(self.device)
-        rc = eng.lib.mgatk_filter_strand_bias_device(eng.handle, dev.data_ptr(), 1, P,
-                                                     float(self.config.quality.max_strand_bias),
-                                                     ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+            host[0, :, pos] = [d["A_fwd"], d["A_rev"], d["C_fwd"], d["C_rev"], d["G_fwd"], d["G_rev"], d["T_fwd"], d["T_rev"],
+                               d["tn5_cuts_fwd"], d["tn5_cuts_rev"], d["depth"]]
+        dev = torch.from_numpy(host.view(np.int32)).cuda(self.device)
+        rc = eng.lib.mgatk_filter_strand_bias_u32_device(eng.handle, dev.data_ptr(), 1, P,
+                                                         float(self.config.quality.max_strand_bias),
+                                                         ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         if rc:
             eng._raise(rc)
-        planes = dev.cpu().numpy()
-        res = PileupResult(planes, np.zeros(1, dtype=[("n_reads", "<u4")]), {}, np.zeros((P, 4), np.int64),
-                           np.zeros(0, dtype=[("cell", "<i4"), ("plane_pos", "<u4"), ("value", "<u4")]), P)
-        out = cell_pileup_dict(res, 0)
-        if big:                                   # counts beyond uint16 (never seen in practice): same rule, exact ints
-            mb = float(self.config.quality.max_strand_bias)
-            for pos, d in big.items():
-                d = dict(d)
-                for base in self.bases:
-                    f, r = d[f"{base}_fwd"], d[f"{base}_rev"]
-                    if f + r > 0 and max(f, r) / (f + r) > mb:
-                        d[base] = d[f"{base}_fwd"] = d[f"{base}_rev"] = 0
-                d["depth"] = sum(d[b] for b in self.bases)
-                if d["depth"] > 0:
-                    out[pos] = d
-            out = dict(sorted(out.items()))
-        return out
+        planes = dev.cpu().numpy().view(np.uint32)
+        return planes_to_dict(planes[0, :, :P], planes[0, 10, :P] > 0)
 
 
 __all__ = ["PileupGenerator", "cell_pileup_dict", "reads_to_batch", "get_engine", "PLANE_NAMES"]

@@ -37,7 +37,7 @@ class MtDNAPipeline:
     def __init__(self, bam_path: str, barcodes: list, output_dir, config: PipelineConfig | None = None,
                  output_format: str = "standard", barcode_metadata=None, sample_name: str = "mgatk2",
                  report_title: str | None = None, report_subtitle: str | None = None, working_directory: str | None = None,
-                 device: int = 0):
+                 device: int = 0, devices: list | None = None, max_batch_records: int | None = None):
         self.bam_path = Path(bam_path)
         self.barcodes = set(barcodes)
         self.barcode_list = list(barcodes)
@@ -46,7 +46,9 @@ class MtDNAPipeline:
         self.output_format = output_format.lower()
         self.barcode_metadata = barcode_metadata
         self.sample_name = sample_name
-        self.device = device
+        self.devices = list(devices) if devices else [device]      # GPUs of this box; the cells are split between them
+        self.device = self.devices[0]
+        self.max_batch_records = max_batch_records                  # larger contigs are streamed in parts (dispatch.py)
         if not self.bam_path.exists():
             raise InvalidInputError(f"BAM file not found: {bam_path}")
         if self.output_format == "hdf5":
@@ -73,7 +75,8 @@ class MtDNAPipeline:
         from .writers import DenseTextWriter
         start = time.time()
         logger.info("Collecting reads from BAM by barcode...")
-        reader = BAMReader(str(self.bam_path), self.config, self.barcodes, barcode_list=self.barcode_list, device=self.device)
+        reader = BAMReader(str(self.bam_path), self.config, self.barcodes, barcode_list=self.barcode_list,
+                           devices=self.devices, max_batch_records=self.max_batch_records)
         reads_by_barcode, stats = reader.collect_reads_by_barcode()
         if not reads_by_barcode:
             logger.error("No reads found for any barcodes!")
@@ -108,7 +111,7 @@ class MtDNAPipeline:
 
 def run_pipeline(bam_path: str, output_dir: str, barcode_file: str | None = None, min_barcode_reads: int = 10,
                  barcode_tag: str = "CB", mito_chr: str = "chrM", output_format: str = "standard", device: int = 0,
-                 **config_kwargs) -> dict:
+                 devices: list | None = None, max_batch_records: int | None = None, **config_kwargs) -> dict:
     """core.pipeline.run_pipeline (pipeline.py:184-270): whitelist from file / singlecell.csv / the BAM itself, then
     `MtDNAPipeline.run()`. `config_kwargs` are `PipelineConfig` keywords (min_baseq, min_mapq, max_strand_bias,
     skip_deduplication, use_fragment_length_dedup, min_reads_per_cell, ...)."""
@@ -116,4 +119,5 @@ def run_pipeline(bam_path: str, output_dir: str, barcode_file: str | None = None
                                        min_barcode_reads=min_barcode_reads)
     config = PipelineConfig(barcode_tag=barcode_tag, mito_chr=mito_chr, **config_kwargs)
     return MtDNAPipeline(bam_path, barcodes, Path(output_dir), config, output_format=output_format,
-                         barcode_metadata=metadata, device=device).run()
+                         barcode_metadata=metadata, device=device, devices=devices,
+                         max_batch_records=max_batch_records).run()

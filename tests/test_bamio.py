@@ -102,6 +102,16 @@ def test_errors(tmp_path):
     write_bam(q, b, ["A-1"])
     with pytest.raises(BAMReadError):
         read_bam_chrM(q, cfg, {"A-1": 0})
+    # ... but a QUAL-less record that dedup drops never becomes a SimpleRead: the reference accepts the file (readers.py:146-158)
+    good_first = dict(pos=10, flag=0, mapq=60, seq="ACGT" * 5, qual=[30] * 20, cigar=[(0, 20)], tlen=77, bc_idx=0)
+    b2 = ReadBatch.from_records([good_first, dict(good_first, qual=[255] * 20)])
+    q2 = str(tmp_path / "noqual_dup.bam")
+    write_bam(q2, b2, ["A-1"])
+    got, _ = read_bam_chrM(q2, cfg, {"A-1": 0})
+    assert got.n_records == 2
+    cfg_nodedup = PipelineConfig(skip_deduplication=True)
+    with pytest.raises(BAMReadError):
+        read_bam_chrM(q2, cfg_nodedup, {"A-1": 0})
 
 
 def test_many_distinct_barcodes_first_appearance_order(tmp_path):

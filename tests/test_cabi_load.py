@@ -19,7 +19,7 @@ def lib():
 
 def test_exports_match_header(lib):
     header = open(os.path.join(ROOT, "include", "mgatk2_b200.h")).read()
-    declared = set(re.findall(r"\b(mgatk_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(mgatk_[a-z0-9_]+)\s*\(", header))
     declared -= {"mgatk_status"}
     from mgatk2_b200 import _lib
     assert declared == set(_lib.EXPORTS)

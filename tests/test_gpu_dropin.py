@@ -141,3 +141,99 @@ def test_pipeline_from_bam_to_text_outputs(golden_dir, tmp_path):
     # whitelist discovered from the BAM itself (pipeline.py:214-224): at least the cells with >= 10 countable reads
     res2 = run_pipeline(bam, str(tmp_path / "run2"), barcode_file=None, min_barcode_reads=10)
     assert res2["cells_passed_qc"] > 0
+
+
+def _reader_result(batch, barcodes, params, **kw):
+    from mgatk2_b200 import BAMReader
+    reader = BAMReader("in-memory.bam", make_config(params), set(barcodes), barcode_list=barcodes, batch=batch, **kw)
+    rbb, stats = reader.collect_reads_by_barcode()
+    return reader, rbb, stats
+
+
+def _same_cells(rbb_a, rbb_b):
+    """Same barcodes in the same order with the same planes / QC rows, whatever the column layout of either result."""
+    assert list(rbb_a) == list(rbb_b)
+    ra, rb = rbb_a.result, rbb_b.result
+    ia = np.array([rbb_a[b].index for b in rbb_a], np.int64)
+    ib = np.array([rbb_b[b].index for b in rbb_b], np.int64)
+    for k in range(11):
+        np.testing.assert_array_equal(ra.plane(k)[ia], rb.plane(k)[ib], err_msg=f"plane {k}")
+    np.testing.assert_array_equal(ra.cell_qc[ia], rb.cell_qc[ib])
+    np.testing.assert_array_equal(ra.base_totals, rb.base_totals)
+
+
+def test_columns_only_for_observed_barcodes(golden_dir):
+    """A whitelist far longer than the barcodes on the contig (10x lists have 737 k entries): planes are allocated for
+    the observed ones only, results unchanged (the reference only does set membership, readers.py:104-111)."""
+    d, batch, barcodes, params = load_golden(f"{golden_dir}/synth_run_default.npz")
+    _, rbb_small, stats_small = _reader_result(batch, barcodes, params)
+    pad = [f"PAD{i:07d}-1" for i in range(300_000)]
+    long_list = pad[:150_000] + barcodes + pad[150_000:]
+    import copy
+    shifted = copy.copy(batch)
+    shifted.bc_idx = np.where(batch.bc_idx >= 0, batch.bc_idx + 150_000, batch.bc_idx).astype(np.int32)
+    _, rbb_long, stats_long = _reader_result(shifted, long_list, params)
+    assert stats_small == stats_long
+    assert len(rbb_long.result.planes) <= len(barcodes)
+    assert [long_list[c] for c in rbb_long.result.columns] == [b for b in barcodes if b in set(long_list[c] for c in rbb_long.result.columns)]
+    _same_cells(rbb_small, rbb_long)
+
+
+@pytest.mark.parametrize("name", ["synth_run_default", "synth_stress150"])
+def test_streamed_through_the_seam(golden_dir, name):
+    """A contig longer than `max_batch_records` goes through the seam in parts (device-resident accumulation, prefetch
+    thread) and gives what one batch gives."""
+    d, batch, barcodes, params = load_golden(f"{golden_dir}/{name}.npz")
+    r1, rbb_one, stats_one = _reader_result(batch, barcodes, params)
+    r2, rbb_str, stats_str = _reader_result(batch, barcodes, params, max_batch_records=max(batch.n_records // 7, 1))
+    assert not r1.streamed and r2.streamed
+    assert stats_one == stats_str
+    _same_cells(rbb_one, rbb_str)
+
+
+def test_two_handles_split_the_cells(golden_dir, tmp_path):
+    """`devices=[...]`: the columns are cut into one range per entry, each counted through its own handle on its own host
+    thread, written into one result. With one GPU in the box the same device is listed twice (two handles); one batch and
+    streamed; the text outputs still equal the reference's byte for byte."""
+    import torch
+    from mgatk2_b200 import MtDNAPipeline
+    from mgatk2_b200.bamio import write_bam
+    d, batch, barcodes, params = load_golden(f"{golden_dir}/synth_run_default.npz")
+    devs = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    _, rbb_one, stats_one = _reader_result(batch, barcodes, params)
+    _, rbb_two, stats_two = _reader_result(batch, barcodes, params, devices=devs)
+    assert stats_one == stats_two
+    _same_cells(rbb_one, rbb_two)
+    _, rbb_two_s, stats_two_s = _reader_result(batch, barcodes, params, devices=devs, max_batch_records=max(batch.n_records // 5, 1))
+    assert stats_one == stats_two_s
+    _same_cells(rbb_one, rbb_two_s)
+    bam = str(tmp_path / "possorted_bam.bam")
+    write_bam(bam, batch, barcodes, write_index=False)
+    out = tmp_path / "run"
+    MtDNAPipeline(bam, barcodes, out, make_config(params), devices=devs).run()
+    for base in ("A", "C", "G", "T", "coverage"):
+        assert gzip.open(out / "output" / f"output.{base}.txt.gz").read() == d[f"txt_{base}"].tobytes(), base
+    assert (out / "output" / "chrM_refAllele.txt").read_bytes() == d["txt_refAllele"].tobytes()
+    assert (out / "qc" / "cell_stats.csv").read_bytes() == d["txt_cell_stats"].tobytes()
+
+
+def test_filter_strand_bias_above_uint16():
+    """PileupGenerator.filter_strand_bias on a dict with counts beyond 65535 (bulk depths): same device path as any other
+    dict (32-bit planes), same rule as pileup.py:128-154 - IEEE double, strict >, coverage from what is left, positions
+    without coverage dropped with their Tn5 counts."""
+    from mgatk2_b200 import PileupGenerator, PipelineConfig
+    cfg = PipelineConfig(max_strand_bias=0.8)
+
+    def entry(a=(0, 0), c=(0, 0), g=(0, 0), t=(0, 0), tn5=(0, 0)):
+        d = {"tn5_cuts_fwd": tn5[0], "tn5_cuts_rev": tn5[1]}
+        for base, (f, r) in zip("ACGT", (a, c, g, t)):
+            d[base], d[f"{base}_fwd"], d[f"{base}_rev"] = f + r, f, r
+        d["depth"] = sum(d[b] for b in "ACGT")
+        return d
+    raw = {10: entry(a=(400_000, 100_000), c=(70_000, 3), tn5=(5, 6)),          # A: bias 0.8 exactly, kept; C: dropped
+           11: entry(g=(100_001, 25_000), tn5=(9, 9)),                          # 0.80000... > 0.8: dropped, position vanishes
+           12: entry(t=(3, 3))}
+    out = PileupGenerator(cfg).filter_strand_bias(raw)
+    assert sorted(out) == [10, 12]
+    assert out[10]["A_fwd"] == 400_000 and out[10]["A"] == 500_000 and out[10]["C"] == 0 and out[10]["depth"] == 500_000
+    assert (out[10]["tn5_cuts_fwd"], out[10]["tn5_cuts_rev"]) == (5, 6) and out[12]["depth"] == 6

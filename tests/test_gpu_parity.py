@@ -1,4 +1,6 @@
 """Parity of the CUDA path (through the C-ABI) with the oracle and the reference-generated goldens."""
+import os
+
 import numpy as np
 import pytest
 
@@ -108,6 +110,30 @@ def test_saturation_and_overflow_list(engine):
     assert res.stats["n_overflow"] > 0 and res.planes.max() == 65535
     assert_result_equals_oracle(res, ora)
     assert res.coverage()[0, 5000] == n and res.tn5()[0, 5000, 0] == n
+
+
+def test_median_straddles_the_saturation_border(engine):
+    """Median depth (writers.py:190) of a cell whose middle order statistics sit on either side of 65535, and of one
+    where both lie above it: the device takes them from the exact depths (overflow list), not from the saturated plane."""
+    one = ReadBatch.from_records([dict(pos=0, flag=0, mapq=60, seq="ACGTACGTAC" * 2, cigar=[(0, 20)], tlen=0, bc_idx=0)])
+    short = ReadBatch.from_records([dict(pos=0, flag=0, mapq=60, seq="ACGTACGTAC", cigar=[(0, 10)], tlen=0, bc_idx=0)])
+
+    def pile(pos, n, cell, proto, L):
+        return dict(pos=np.full(n, pos, np.int32), tlen=np.arange(n, dtype=np.int32), flag=np.zeros(n, np.uint16),
+                    mapq=np.full(n, 60, np.uint8), bc_idx=np.full(n, cell, np.int32), l_seq=np.full(n, L, np.uint16),
+                    n_cigar=np.ones(n, np.uint16), blob_off=np.full(n, proto, np.uint32))
+    blob = np.concatenate([one.blob, short.blob])                      # two prototype blobs: 20 bases at unit 0, 10 bases after it
+    off_short = len(one.blob) // 16
+    piles = [pile(100, 10, 0, 0, 20), pile(200, 7, 0, off_short, 10), pile(5000, 70_000, 0, 0, 20), pile(5010, 66_000, 0, 0, 20),
+             pile(300, 3, 1, 0, 20), pile(7000, 80_000, 1, 0, 20), pile(7020, 90_000, 1, 0, 20), pile(7040, 100_000, 1, 0, 20)]
+    cat = {k: np.concatenate([p[k] for p in piles]) for k in piles[0]}
+    order = np.argsort(cat["pos"], kind="stable")
+    batch = ReadBatch(blob=blob, **{k: v[order] for k, v in cat.items()})
+    res, ora = run_both(engine, batch, 3, min_distance_from_end=0)
+    assert_result_equals_oracle(res, ora)
+    assert (int(ora.cell_qc["median_lo"][0]), int(ora.cell_qc["median_hi"][0])) == (10, 66_000)     # 30 shallow, 30 deep positions
+    assert (int(res.cell_qc["median_lo"][1]), int(res.cell_qc["median_hi"][1])) == (80_000, 90_000)    # both above the border
+    assert res.cell_qc["median_lo"][2] == 0
 
 
 def test_edge_cases(engine):
@@ -321,3 +347,40 @@ def test_submit_wait_two_batches_in_flight(engine):
     assert_result_equals_oracle(engine.wait_host(t_ok), oracles[1])
     # and the blocking call still works afterwards
     assert_result_equals_oracle(engine.run_host(cases[2][0], lps[2], out=outs[2]), oracles[2])
+
+
+def test_run_sharded_single_rank(engine):
+    """multi.run_sharded (the torchrun form of one input on N GPUs) at world size 1 against the oracle: routing,
+    renumbering and recombination are the ones the N-rank run uses (tools/check_multi_gpu.py is the same check under
+    torchrun; the 2-rank variant below runs when the box has two GPUs)."""
+    from mgatk2_b200._lib import ParamsC
+    from mgatk2_b200.multi import run_sharded
+    from mgatk2_b200.synth import synth_batch
+    from oracle.oracle import make_params, run_oracle
+    n_cells = 120
+    batch = synth_batch(n_cells, 150_000, "atac50", seed=321)
+    p = make_params(n_cells, max_read_extent=batch.max_read_extent(), max_strand_bias=0.9)
+    lp = ParamsC(*[getattr(p, f) for f, _ in p._fields_])
+    res, cols, combined = run_sharded(batch, lp, engine, 0, 1)
+    ora = run_oracle(batch, p, n_threads=4)
+    np.testing.assert_array_equal(res.counts(), ora.counts[cols])
+    np.testing.assert_array_equal(res.coverage(), ora.coverage[cols])
+    for f in ("n_reads", "n_paired", "sum_depth", "covered", "max_depth", "median_lo", "median_hi"):
+        np.testing.assert_array_equal(combined["cell_qc"][f], ora.cell_qc[f])
+    np.testing.assert_array_equal(combined["base_totals"], ora.base_totals)
+    assert all(combined["stats"][k] == ora.stats[k] for k in ("total_reads", "filtered_reads", "dup_with_length", "dup_position_only"))
+
+
+def test_run_sharded_two_ranks_when_two_gpus():
+    """The same check under torchrun with two ranks (NCCL all-reduce of the base totals); skipped on a one-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29571", os.path.join(root, "tools", "check_multi_gpu.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("parity OK") == 2

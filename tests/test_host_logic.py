@@ -97,3 +97,37 @@ def test_two_rank_gloo_recombination(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
+
+
+def test_column_plan_and_routing():
+    """dispatch.py on the CPU: columns only for observed barcodes, contiguous device ranges balanced by record count,
+    routing keeps file order and renumbers bc_idx per device; every usable record lands on exactly one device."""
+    from mgatk2_b200 import dispatch
+    from mgatk2_b200.synth import synth_batch
+    n_wl = 500
+    batch = synth_batch(40, 6000, "atac50", seed=3)
+    batch.bc_idx = np.where(batch.bc_idx >= 0, batch.bc_idx * 7 + 11, batch.bc_idx).astype(np.int32)   # spread over the list
+    ok = dispatch.usable(batch, n_wl)
+    counts = np.bincount(batch.bc_idx[ok], minlength=n_wl)
+    for n_dev in (1, 2, 3, 8):
+        plan = dispatch.plan_columns(n_wl, counts, n_dev)
+        assert plan.columns.tolist() == np.nonzero(counts)[0].tolist()
+        assert plan.cuts[0] == 0 and plan.cuts[-1] == plan.n_columns and len(plan.cuts) == n_dev + 1
+        assert all(a <= b for a, b in zip(plan.cuts[:-1], plan.cuts[1:]))
+        loads = [int(counts[plan.columns[a:b]].sum()) for a, b in zip(plan.cuts[:-1], plan.cuts[1:])]
+        assert max(loads) <= counts.sum() / n_dev + counts.max()
+        subs, unowned = dispatch.route(batch, plan, n_wl)
+        if n_dev == 1:
+            assert unowned == 0 and subs[0].n_records == batch.n_records
+            np.testing.assert_array_equal(subs[0].bc_idx >= 0, ok)
+            continue
+        assert unowned == int((~ok).sum()) and sum(s.n_records for s in subs) == int(ok.sum())
+        for d, s in enumerate(subs):
+            glob = plan.columns[s.bc_idx + plan.cuts[d]]
+            want = np.nonzero(ok & (plan.device_of(plan.local_of[np.clip(batch.bc_idx, 0, n_wl - 1)]) == d))[0]
+            np.testing.assert_array_equal(glob, batch.bc_idx[want])
+            np.testing.assert_array_equal(s.pos, batch.pos[want])
+            assert s.is_sorted()
+    # nothing observed / whitelist columns for a stream whose barcodes are not known in advance
+    assert dispatch.plan_columns(n_wl, np.zeros(n_wl, np.int64), 4).n_columns == 0
+    assert dispatch.plan_columns(7, None, 2).columns.tolist() == list(range(7))
