@@ -4,8 +4,9 @@ in and the reference's text outputs come out with the counting on the GPU:
     BAMReader.collect_reads_by_barcode()  ->  CellProcessor.process_cells_progressive()  ->  writer.finalize()
 
 Same constructor keywords, same return value of `run()`, same files (`output/output.{A,C,G,T,coverage}.txt.gz`,
-`output/output.depthTable.txt`, `output/<mito>_refAllele.txt`, `qc/cell_stats.csv`, `qc/summary.txt`). The HDF5 layout
-needs h5py, which this image lacks: `output_format="hdf5"` raises `ProcessingError` instead of silently writing text.
+`output/output.depthTable.txt`, `output/<mito>_refAllele.txt`, `qc/cell_stats.csv`, `qc/summary.txt`), or with
+`output_format="hdf5"` the reference's default `output/counts.h5` + `output/metadata.h5` (written by `h5lite`; the HTML
+report that follows them in the reference is out of scope).
 No BAM index is required (the native reader scans without one; the reference would call `pysam.index`)."""
 from __future__ import annotations
 
@@ -16,7 +17,7 @@ from pathlib import Path
 
 from .barcodes import load_barcodes
 from .config import PipelineConfig
-from .exceptions import InvalidInputError, ProcessingError
+from .exceptions import InvalidInputError
 
 logger = logging.getLogger(__name__)
 VERSION = "mgatk2_b200 round 1"
@@ -51,13 +52,6 @@ class MtDNAPipeline:
         self.max_batch_records = max_batch_records                  # larger contigs are streamed in parts (dispatch.py)
         if not self.bam_path.exists():
             raise InvalidInputError(f"BAM file not found: {bam_path}")
-        if self.output_format == "hdf5":
-            try:
-                import h5py  # noqa: F401
-            except ImportError as e:
-                raise ProcessingError("output_format='hdf5' needs h5py (counts.h5 / metadata.h5); use the text layout "
-                                      "or mgatk2_b200.writers.hdf5_datasets() for the arrays") from e
-            raise ProcessingError("HDF5 writer not built in this round; use the text layout")
         from .bamio import BamFile, pick_mito_contig
         with BamFile(str(self.bam_path)) as bam:                          # pipeline.py:62-76
             if self.config.mito_chr not in bam.references:
@@ -72,7 +66,7 @@ class MtDNAPipeline:
     def run(self) -> dict:
         from .processors import CellProcessor
         from .readers import BAMReader
-        from .writers import DenseTextWriter
+        from .writers import DenseHDF5Writer, DenseTextWriter
         start = time.time()
         logger.info("Collecting reads from BAM by barcode...")
         reader = BAMReader(str(self.bam_path), self.config, self.barcodes, barcode_list=self.barcode_list,
@@ -83,7 +77,10 @@ class MtDNAPipeline:
             return {}
         n_cells_input = len(reads_by_barcode)
         t_write = time.time()
-        writer = DenseTextWriter(self.output_dir, self.config, self.barcode_list)
+        if self.output_format == "hdf5":                                  # pipeline.py:88-94, the default of `mgatk2 run`
+            writer = DenseHDF5Writer(self.output_dir, self.config, self.barcode_list, barcode_metadata=self.barcode_metadata)
+        else:
+            writer = DenseTextWriter(self.output_dir, self.config, self.barcode_list)
         cell_results = CellProcessor(self.config, self.output_dir).process_cells_progressive(reads_by_barcode, writer)
         if not cell_results:
             logger.error("No cells passed quality filters")

@@ -237,3 +237,40 @@ def test_filter_strand_bias_above_uint16():
     assert sorted(out) == [10, 12]
     assert out[10]["A_fwd"] == 400_000 and out[10]["A"] == 500_000 and out[10]["C"] == 0 and out[10]["depth"] == 500_000
     assert (out[10]["tn5_cuts_fwd"], out[10]["tn5_cuts_rev"]) == (5, 6) and out[12]["depth"] == 6
+
+
+def test_pipeline_writes_the_default_hdf5_layout(golden_dir, tmp_path):
+    """MtDNAPipeline(output_format="hdf5") - the default of `mgatk2 run` (cli/options.py:14-78): counts.h5 / metadata.h5
+    hold what the unmodified reference computed for the same records (golden: its per-cell pileups), laid out and typed as
+    IncrementalHDF5Writer does (writers.py:60-134,187-229)."""
+    from mgatk2_b200 import MtDNAPipeline
+    from mgatk2_b200.bamio import write_bam
+    from mgatk2_b200.h5lite import H5Reader
+    d, batch, barcodes, params = load_golden(f"{golden_dir}/synth_run_default.npz")
+    bam = str(tmp_path / "possorted_bam.bam")
+    write_bam(bam, batch, barcodes, write_index=False)
+    out = tmp_path / "run"
+    res = MtDNAPipeline(bam, barcodes, out, make_config(params), output_format="hdf5").run()
+    alive = d["exp_alive"].astype(bool)
+    assert res["cells_passed_qc"] == int(alive.sum())
+    c = H5Reader(out / "output" / "counts.h5")
+    assert c.attrs == {"n_cells": len(barcodes), "n_positions": 16569, "mito_chr": "chrM"}
+    assert c.objects["barcode"].read().tolist() == [b.encode() for b in barcodes]
+    for bi, base in enumerate("ACGT"):
+        for si, strand in enumerate(("fwd", "rev")):
+            want = np.minimum(d["exp_counts"][:, :, bi, si], 65535).astype(np.uint16) * alive[:, None]
+            np.testing.assert_array_equal(c.objects[f"{base}_{strand}"].read(), want.T, err_msg=f"{base}_{strand}")
+    for si, strand in enumerate(("fwd", "rev")):
+        want = np.minimum(d["exp_tn5"][:, :, si], 65535).astype(np.uint16) * alive[:, None]
+        np.testing.assert_array_equal(c.objects[f"tn5_cuts_{strand}"].read(), want.T)
+    m = H5Reader(out / "output" / "metadata.h5")
+    cov = d["exp_coverage"] * alive[:, None]
+    np.testing.assert_array_equal(m.objects["coverage"].read(), np.minimum(cov, 65535).astype(np.uint16).T)
+    dep = [cov[k][cov[k] > 0] for k in range(len(barcodes))]
+    np.testing.assert_array_equal(m.objects["mean_depth"].read(), np.array([x.mean() if len(x) else 0 for x in dep], np.float32))
+    np.testing.assert_array_equal(m.objects["median_depth"].read(), np.array([np.median(x) if len(x) else 0 for x in dep], np.float32))
+    np.testing.assert_array_equal(m.objects["max_depth"].read(), np.array([min(x.max(), 65535) if len(x) else 0 for x in dep], np.uint16))
+    np.testing.assert_array_equal(m.objects["total_bases"].read(), np.array([x.sum() if len(x) else 0 for x in dep], np.float32))
+    np.testing.assert_array_equal(m.objects["genome_coverage"].read(), np.array([len(x) / 16569 * 100 for x in dep], np.float32))
+    assert m.objects["reference"].read().tobytes() == b"".join(l.split(b"\t")[1] for l in d["txt_refAllele"].tobytes().splitlines()[1:])
+    assert (out / "qc" / "cell_stats.csv").read_bytes() == d["txt_cell_stats"].tobytes()
