@@ -401,7 +401,7 @@ def run_b200(a):
     # stages 1-6. The dominant kernel is reported next to it against ITS OWN algorithmic bytes (what that launch must
     # read and write given its place in the pipeline), never against the whole job's.
     bytes_alg = algorithmic_bytes(batch, a.cells)
-    slot_bytes = 32 if extent <= 56 and a.cells <= 2048 else 16 + 16 * min(8, max(2, (extent + 31) // 32))
+    slot_bytes = 32 if extent <= 56 else (16 + 16 * min(8, max(2, (extent + 31) // 32)) + 31) // 32 * 32
     in_bytes = bytes_alg - a.cells * 16569 * 22 - a.cells * 32
     out_bytes = a.cells * 16569 * 22 + a.cells * 32
     stage1, kept = int(res.stats["stage1_reads"]), int(res.stats["filtered_reads"])

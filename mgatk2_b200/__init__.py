@@ -12,7 +12,8 @@ from .exceptions import (BAMReadError, InvalidInputError, MgatkError, NoBarcodeT
 __all__ = ["ReadBatch", "PipelineConfig", "QualityThresholds", "DeduplicationConfig", "PerformanceConfig",
            "MgatkError", "InvalidInputError", "ProcessingError", "BAMReadError", "NoBarcodeTagsError",
            "PileupKernelError", "BAMReader", "CellProcessor", "process_barcode_worker", "PileupGenerator",
-           "PileupEngine", "MtDNAPipeline", "run_pipeline", "load_singlecell_csv", "extract_barcodes_from_bam"]
+           "PileupEngine", "MtDNAPipeline", "run_pipeline", "load_singlecell_csv", "extract_barcodes_from_bam",
+           "DenseTextWriter", "DenseHDF5Writer", "report_inputs"]
 
 
 def __getattr__(name):        # heavy pieces (ctypes library, torch) load on first use
@@ -31,6 +32,12 @@ def __getattr__(name):        # heavy pieces (ctypes library, torch) load on fir
     if name in ("load_singlecell_csv", "extract_barcodes_from_bam"):
         from . import barcodes
         return getattr(barcodes, name)
+    if name in ("DenseTextWriter", "DenseHDF5Writer"):
+        from . import writers
+        return getattr(writers, name)
+    if name == "report_inputs":
+        from .report import report_inputs
+        return report_inputs
     if name == "PileupEngine":
         from .engine import PileupEngine
         return PileupEngine

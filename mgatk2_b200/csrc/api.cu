@@ -36,7 +36,7 @@ struct Layout {          // carve-up of the caller's workspace
     SlotFmt fmt;
     int stage_bytes, cap_reads, unit_reads; int64_t max_units;
     size_t slots[2];         // two slot arrays: partition output(s) and the compacted reads to pile up
-    size_t mat, part, cell_start, unit_start, units, units_big, scan_state, totals32, scalars, total;
+    size_t mat, part, cell_start, cell_first, unit_start, units, units_big, scan_state, totals32, scalars, total;
     int64_t dedup_blocks;
 };
 
@@ -61,7 +61,7 @@ bool make_layout(int64_t n, int32_t n_cells, int extent, Layout &L) {
     L.passes = bits <= kMaxDigitBits ? 1 : 2;
     if (L.passes == 1) { L.bits[0] = bits; L.shift[0] = 0; L.bits[1] = 0; L.shift[1] = 0; }
     else { L.bits[0] = (bits + 1) / 2; L.shift[0] = 0; L.bits[1] = bits - L.bits[0]; L.shift[1] = L.bits[0]; }
-    L.fmt = slot_format(extent, L.passes);
+    L.fmt = slot_format(extent);
     L.stage_bytes = stage_bytes_for(L.fmt);
     L.cap_reads = L.stage_bytes / L.fmt.bytes;
     {   // reads per unit: leave room for the reads of the halo and of the chunk the tile border is rounded down to
@@ -77,6 +77,7 @@ bool make_layout(int64_t n, int32_t n_cells, int extent, Layout &L) {
     L.mat = o; o += align_up((size_t)L.nchunks * max_bins * 4);
     L.part = o; o += align_up((size_t)L.ngroups * max_bins * 4);
     L.cell_start = o; o += align_up(((size_t)n_cells + 1) * 4);
+    L.cell_first = o; o += align_up(((size_t)n_cells + 2) * 4);        // two-digit partition of compact slots: first slot of every cell
     L.unit_start = o; o += align_up(((size_t)n_cells + 1) * 4);
     L.units = o; o += align_up((size_t)L.max_units * sizeof(Unit));
     L.units_big = o; o += align_up((size_t)L.max_units * sizeof(Unit));
@@ -296,10 +297,11 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     sa.words = L.fmt.words; sa.slot_bytes = L.fmt.bytes;
     sa.min_baseq = p->min_baseq; sa.dist = p->min_distance_from_end; sa.min_mapq = p->min_mapq; sa.extent = p->max_read_extent;
     sa.wbuf = warp_buffer_for(b);
+    sa.hi_shift = L.passes == 2 ? L.bits[0] : 31;
     if ((rc = compact ? launch_scatter<true>(h, s, sa) : launch_scatter<false>(h, s, sa))) return rc;
     uint8_t *grouped = slots_a, *piled = slots_b;
     if (L.passes == 2) {
-        SrcSlots ss; ss.a = slots_a; ss.m = m_ptr; ss.slot_bytes = L.fmt.bytes;
+        SrcSlots ss; ss.a = slots_a; ss.m = m_ptr; ss.slot_bytes = L.fmt.bytes; ss.compact = compact; ss.hi_shift = L.bits[0];
         if ((rc = histogram_and_scan(h, s, ss, L, 1, ws, nullptr))) return rc;
         const int bins = 1 << L.bits[1];
         k_scatter_slots<<<L.nchunks, kPartThreads, rank_smem_bytes(bins), s>>>(ss, L.chunk, L.nchunks, L.shift[1], bins, (const u32 *)(ws + L.mat), slots_b);
@@ -317,6 +319,15 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     DedupArgs da;
     da.slots = grouped; da.out = piled; da.slot_bytes = L.fmt.bytes; da.m_ptr = m_ptr;
     da.cell_first = (const u32 *)(ws + L.mat); da.n_first = 1 << L.bits[0];      // row 0 of the scanned histogram (one pass)
+    if (compact && L.passes == 2) {                      // no such row after two digit passes: count the slots per cell
+        u32 *cf = (u32 *)(ws + L.cell_first);
+        CU(cudaMemsetAsync(cf, 0, ((size_t)C + 1) * 4, s));
+        const int smem_cells = C < 12288 ? C : 12288;
+        k_cell_counts<<<h->sm_count * 2, 1024, (size_t)smem_cells * 4, s>>>(su, smem_cells, cf);
+        k_scan_cells<<<1, 1024, 0, s>>>(cf, C);
+        h->launches += 2;
+        da.cell_first = cf; da.n_first = C;
+    }
     da.dedup_mode = p->dedup_mode; da.qc = o->cell_qc; da.stats = o->stats;
     da.ticket = ticket; da.scan_state = (u64 *)(ws + L.scan_state); da.n_proc_out = n_proc;
     if (compact) k_dedup<true><<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(da);
@@ -328,7 +339,8 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     int32_t *unit_start = (int32_t *)(ws + L.unit_start);
     Unit *units = (Unit *)(ws + L.units);
     k_plan_scan<<<1, 1024, 0, s>>>(o->cell_qc, C, min_reads, L.unit_reads, ppad, cell_start, unit_start, n_units);
-    k_plan_units<<<(unsigned)((L.max_units + 255) / 256), 256, 0, s>>>(cell_start, o->cell_qc, piled, L.fmt.bytes, unit_start, C,
+    const SlotList sl{piled, L.fmt.bytes};
+    k_plan_units<<<(unsigned)((L.max_units + 255) / 256), 256, 0, s>>>(cell_start, o->cell_qc, sl, unit_start, C,
                                                                       min_reads, L.unit_reads, ppad, p->max_read_extent, units,
                                                                       L.cap_reads, (Unit *)(ws + L.units_big), work_counter + 4);
     h->launches += 2;

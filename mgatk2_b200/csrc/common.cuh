@@ -22,10 +22,12 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 // (bit i <=> reference_start + i): V = "counts here" (aligned, A/C/G/T, base quality, distance-from-end window,
 // pileup.py:52-86), B0 / B1 = the two bits of the base code under V. Nothing downstream touches SEQ, QUAL or CIGAR.
 //
-//   compact (max_read_extent <= 56, one partition pass), 32 bytes = one sector:
-//       w0 pos   w1 |tlen|   w2 V[0:32)   w3 V[32:56) | meta << 24   w4 B0[0:32)   w5 B0[32:56) | tn5off << 24
-//       w6 B1[0:32)   w7 B1[32:56)
-//   wide (W = ceil(extent / 32) words per plane, at most 8), 16 + 16 W bytes:
+//   compact (max_read_extent <= 56), 32 bytes = one sector:
+//       w0 pos   w1 |tlen|   w2 V[0:32)   w3 V[32:56) | meta << 24 | hi[8:11) << 29   w4 B0[0:32)
+//       w5 B0[32:56) | tn5off << 24   w6 B1[0:32)   w7 B1[32:56) | hi[0:8) << 24
+//       hi = high digit of the cell index, carried from the first to the second pass of a two-digit partition (more than
+//       2048 cells); after the partition a compact slot's cell follows from its place (table of first slots per cell)
+//   wide (W = ceil(extent / 32) words per plane, at most 8), 16 + 16 W bytes rounded up to whole sectors:
 //       w0 pos   w1 |tlen|   w2 cell | meta << 24   w3 tn5off   then W groups { V, B0, B1, 0 } of 32 offsets each
 //       an INDIRECT read (longer than 32 W) keeps { blob_off, l_seq | n_cigar << 16 } in its first group instead and
 //       is counted base by base from the caller's blob.
@@ -37,19 +39,19 @@ constexpr int kMaxPlaneWords = 8;
 
 struct SlotFmt { int compact, words, bytes; };
 
-__host__ __device__ inline SlotFmt slot_format(int extent, int partition_passes) {
+__host__ __device__ inline SlotFmt slot_format(int extent) {
     SlotFmt f;
-    f.compact = extent <= kCompactExtent && partition_passes == 1;
+    f.compact = extent <= kCompactExtent;
     int w = (extent + 31) / 32;
     f.words = f.compact ? 2 : (w < 2 ? 2 : w > kMaxPlaneWords ? kMaxPlaneWords : w);
-    f.bytes = f.compact ? 32 : 16 + 16 * f.words;
+    f.bytes = f.compact ? 32 : (16 + 16 * f.words + 31) / 32 * 32;      // whole 32-byte sectors: scattered slot stores never straddle one
     return f;
 }
 
 // first 16 bytes of a slot = everything dedup and planning need
 template <bool kCompact> struct SlotKey;
 template <> struct SlotKey<true> {
-    __device__ __forceinline__ static u32 meta(const uint4 &k) { return k.w >> 24; }
+    __device__ __forceinline__ static u32 meta(const uint4 &k) { return (k.w >> 24) & 31u; }
 };
 template <> struct SlotKey<false> {
     __device__ __forceinline__ static u32 meta(const uint4 &k) { return k.z >> 24; }

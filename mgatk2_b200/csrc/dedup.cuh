@@ -211,8 +211,9 @@ k_dedup(DedupArgs a) {
     for (int k = 0; k < kDedupRounds; k++)
         if ((pm[k] >> lane) & 1u) {
             const int64_t i = tile0 + k * kDedupThreads + threadIdx.x;
+            const size_t rank = (size_t)(prefix + s_warp[k][wid] + __popc(pm[k] & ((1u << lane) - 1u)));
             const uint4 *in = reinterpret_cast<const uint4 *>(a.slots + (size_t)i * sb);
-            uint8_t *dst = a.out + (size_t)(prefix + s_warp[k][wid] + __popc(pm[k] & ((1u << lane) - 1u))) * sb;
+            uint8_t *dst = a.out + rank * sb;
             if (kCompact) {                                  // one 256-bit store per slot (a whole sector)
                 const uint4 lo = in[0], hi = in[1];
                 asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),

@@ -145,7 +145,23 @@ k_median(const uint16_t *__restrict__ planes, int P, int ppad, mgatk_cell_qc *__
     hist[t] = 0;
     if (t == 0) s_list = 0;
     __syncthreads();
-    for (int p = t; p < P; p += 256) { const u32 v = cov[p]; if (v) atomicAdd(&hist[v >> 8], 1u); }
+    {   // eight positions per load (rows are 128-byte aligned, the padding beyond P is zero); depths below 256 - nearly
+        // all of them - are counted in a register instead of hammering one shared counter
+        u32 low = 0;
+        const uint4 *row = reinterpret_cast<const uint4 *>(cov);
+        for (int q = t; q < ppad / 8; q += 256) {
+            const uint4 w = __ldg(row + q);
+            const u32 x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const u32 a = x[k] & 0xffffu, b = x[k] >> 16;
+                if (a) { if (a < 256u) low++; else atomicAdd(&hist[a >> 8], 1u); }
+                if (b) { if (b < 256u) low++; else atomicAdd(&hist[b >> 8], 1u); }
+            }
+        }
+        low = __reduce_add_sync(kFull, low);
+        if ((t & 31) == 0 && low) atomicAdd(&hist[0], low);
+    }
     // saturated positions of this cell whose exact depth sits in the overflow list
     const bool deep = qc[c].max_depth > 65535u && ovf != nullptr;
     const int64_t n_list = deep ? min((int64_t)stats->n_overflow, ovf_cap) : 0;
@@ -198,7 +214,17 @@ k_median(const uint16_t *__restrict__ planes, int P, int ppad, mgatk_cell_qc *__
             __syncthreads();
             hist[t] = 0;
             __syncthreads();
-            for (int p = t; p < P; p += 256) { const u32 v = cov[p]; if (v && (v >> 8) == bin) atomicAdd(&hist[v & 255], 1u); }
+            const uint4 *row = reinterpret_cast<const uint4 *>(cov);
+            for (int q = t; q < ppad / 8; q += 256) {
+                const uint4 w = __ldg(row + q);
+                const u32 x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const u32 a = x[k] & 0xffffu, b = x[k] >> 16;
+                    if (a && (a >> 8) == bin) atomicAdd(&hist[a & 255u], 1u);
+                    if (b && (b >> 8) == bin) atomicAdd(&hist[b & 255u], 1u);
+                }
+            }
             __syncthreads();
         }
         if (t == 0) { u32 b; median_scan(hist, rem, b); s_val = (bin << 8) | b; }

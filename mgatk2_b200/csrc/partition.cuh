@@ -39,15 +39,18 @@ struct SrcUser {          // pass 0: reads the caller's SoA batch and applies th
     }
 };
 
-struct SrcSlots {         // pass 1 of a two-digit partition: wide slots, already filtered, count on the device
+struct SrcSlots {         // second pass of a two-digit partition: finished slots, already filtered, count on the device
     const uint8_t *a;
     const int64_t *m;
     int slot_bytes;
+    int compact, hi_shift;    // compact slots carry only the high digit of their cell (common.cuh), `hi_shift` = bits of the low one
     static constexpr int vec4 = 0;
     __device__ __forceinline__ void cell4(int64_t, int (&)[4]) const {}
     __device__ __forceinline__ int64_t count() const { return *m; }
     __device__ __forceinline__ int cell(int64_t i) const {
-        return (int)(reinterpret_cast<const u32 *>(a + (size_t)i * slot_bytes)[2] & 0xffffffu);
+        const u32 *w = reinterpret_cast<const u32 *>(a + (size_t)i * slot_bytes);
+        if (compact) return (int)(((w[7] >> 24) | ((w[3] >> 29) << 8)) << hi_shift);
+        return (int)(w[2] & 0xffffffu);
     }
 };
 
@@ -175,6 +178,53 @@ __global__ void k_scan_apply(u32 *__restrict__ mat, int nchunks, int bins, const
     for (int k = 0; k < kScanGroup; k++) if (w0 + k < nchunks) { mat[(size_t)(w0 + k) * bins + b] = run; run += v[k]; }
 }
 
+// Slots per cell and their exclusive scan: where every cell starts in the partitioned array. A one-pass partition has this
+// for free (row 0 of its scanned histogram); compact slots of a two-digit partition carry no cell index, so their
+// consumer (k_dedup) needs the table. Cells below `smem_cells` are counted in shared memory first.
+__global__ void __launch_bounds__(1024)
+k_cell_counts(SrcUser src, int smem_cells, u32 *__restrict__ counts) {
+    extern __shared__ u32 smem[];
+    for (int c = threadIdx.x; c < smem_cells; c += blockDim.x) smem[c] = 0;
+    __syncthreads();
+    const int64_t n = src.count();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = src.cell(i);
+        if (c >= 0) atomicAdd(c < smem_cells ? &smem[c] : &counts[c], 1u);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < smem_cells; c += blockDim.x) if (smem[c]) atomicAdd(&counts[c], smem[c]);
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_cells(u32 *__restrict__ counts, int n) {              // in place, exclusive; counts[n] = total
+    __shared__ u32 warp_sums[32];
+    __shared__ u32 carry_s;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += 1024) {
+        const int c = c0 + t;
+        const u32 mine = c < n ? counts[c] : 0u;
+        u32 inc = mine;
+        for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const u32 v = warp_sums[lane];
+            u32 sc = v;
+            for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(kFull, sc, o); if (lane >= o) sc += x; }
+            warp_sums[lane] = sc - v;
+        }
+        __syncthreads();
+        const u32 carry = carry_s;
+        if (c < n) counts[c] = carry + warp_sums[wid] + inc - mine;
+        __syncthreads();
+        if (t == 1023) carry_s = carry + warp_sums[31] + inc;
+        __syncthreads();
+    }
+    if (t == 0) counts[n] = carry_s;
+}
+
 constexpr int kPartWarps = kPartThreads / 32;
 static_assert(kPartWarps == 8 || kPartWarps == 4, "the packed per-digit counter holds one byte per warp");
 
@@ -237,6 +287,7 @@ struct ScatterArgs {
     int words, slot_bytes;            // plane words per read (W), bytes per slot
     int min_baseq, dist, min_mapq, extent;
     int wbuf;                         // bytes of one per-warp blob staging buffer (multiple of 16)
+    int hi_shift;                     // two-digit partition: bits of the first digit (compact slots carry cell >> hi_shift); else 31
 };
 
 __host__ __device__ inline size_t scatter_smem_bytes(int bins, int wbuf, int words, bool compact) {
@@ -317,13 +368,25 @@ __device__ __forceinline__ void compact_planes(const ScatterArgs &a, const M &me
     }
 }
 
-__device__ __forceinline__ void store_compact(uint8_t *dst, const SlotHead &h, const u32 (&g)[2][3]) {     // one 256-bit store: a whole sector
+__device__ __forceinline__ void store_compact(uint8_t *dst, const SlotHead &h, const u32 (&g)[2][3], u32 hi) {     // one 256-bit store: a whole sector
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(h.pos), "r"(h.tlen_abs), "r"(g[0][0]),
-                 "r"((g[1][0] & 0xffffffu) | (h.meta << 24)), "r"(g[0][1]), "r"((g[1][1] & 0xffffffu) | ((h.tn5off & 63u) << 24)),
-                 "r"(g[0][2]), "r"(g[1][2] & 0xffffffu) : "memory");
+                 "r"((g[1][0] & 0xffffffu) | (h.meta << 24) | ((hi >> 8) << 29)), "r"(g[0][1]),
+                 "r"((g[1][1] & 0xffffffu) | ((h.tn5off & 63u) << 24)), "r"(g[0][2]), "r"((g[1][2] & 0xffffffu) | ((hi & 255u) << 24)) : "memory");
 }
 
-// a wide slot, written group by group
+// 16-byte pieces of a wide slot leave in pairs: one 256-bit store per 32-byte sector of the slot
+struct SectorWriter {
+    uint8_t *dst; uint4 held; bool have;
+    __device__ __forceinline__ void put(const uint4 &v) {
+        if (!have) { held = v; have = true; return; }
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(held.x), "r"(held.y), "r"(held.z), "r"(held.w),
+                     "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        dst += 32; have = false;
+    }
+    __device__ __forceinline__ void finish() { if (have) put(make_uint4(0u, 0u, 0u, 0u)); }
+};
+
+// a wide slot, written sector by sector
 template <class M>
 __device__ __forceinline__ void store_wide(const ScatterArgs &a, const M &mem, u32 cig_addr, const SlotHead &h, const RawRec &r, int cell,
                                            uint8_t *dst, QualGe qg, u32 scratch_addr) {
@@ -333,17 +396,17 @@ __device__ __forceinline__ void store_wide(const ScatterArgs &a, const M &mem, u
     const int W = a.words, L = h.L;
     const bool indirect = L > 32 * W || h.span > 32 * W;
     const u32 seq_addr = cig_addr + 4u * (u32)h.ncig;
-    uint4 *out = reinterpret_cast<uint4 *>(dst);
-    out[0] = make_uint4(h.pos, h.tlen_abs, (u32)cell | ((h.meta | (indirect ? SM_INDIRECT : 0u)) << 24), h.tn5off & 0xffffu);
+    SectorWriter out{dst, make_uint4(0u, 0u, 0u, 0u), false};
+    out.put(make_uint4(h.pos, h.tlen_abs, (u32)cell | ((h.meta | (indirect ? SM_INDIRECT : 0u)) << 24), h.tn5off & 0xffffu));
     const int nq = (L + 31) >> 5;
-    if (indirect || L == 0 || h.beyond) {
-        out[1] = indirect ? make_uint4(r.off, (u32)L | ((u32)h.ncig << 16), 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-        for (int k = 1; k < W; k++) out[1 + k] = make_uint4(0u, 0u, 0u, 0u);
+    if (indirect || L == 0 || h.beyond || !(h.meta & SM_MAPQ_OK)) {      // (a read below min_mapq only takes part in dedup, Q2)
+        out.put(indirect ? make_uint4(r.off, (u32)L | ((u32)h.ncig << 16), 0u, 0u) : make_uint4(0u, 0u, 0u, 0u));
+        for (int k = 1; k < W; k++) out.put(make_uint4(0u, 0u, 0u, 0u));
     } else if (h.simple) {
         for (int k = 0; k < W; k++) {
             u32 v = 0u, b0 = 0u, b1 = 0u;
             if (k < nq) query_mask_group(mem, seq_addr, L, k, q_lo, q_hi, qg, v, b0, b1);
-            out[1 + k] = make_uint4(v, b0, b1, 0u);
+            out.put(make_uint4(v, b0, b1, 0u));
         }
     } else {
         const SharedMem smem;
@@ -356,9 +419,10 @@ __device__ __forceinline__ void store_wide(const ScatterArgs &a, const M &mem, u
         for (int k = 0; k < W; k++) {
             u32 o[3];
             ref_group(mem, cig_addr, h.ncig, q, k, o);
-            out[1 + k] = make_uint4(o[0], o[1], o[2], 0u);
+            out.put(make_uint4(o[0], o[1], o[2], 0u));
         }
     }
+    out.finish();
 }
 
 // One step = kPartThreads records in BAM order, one per thread. Per warp: the blobs of the step sit in the warp's
@@ -426,7 +490,7 @@ k_scatter_planes(ScatterArgs a) {
             __syncwarp();                                    // every lane has read the buffer: it goes back to the TMA unit
             have = stage_blobs(a.b, r1, lane, wbuf_addr, bar_addr, a.wbuf, beg16);
             const size_t dd = rank_step(packed, off, bins, buf, d, lane, wid);
-            if (d >= 0) store_compact(a.dst + dd * 32, h, g);
+            if (d >= 0) store_compact(a.dst + dd * 32, h, g, (u32)cell >> a.hi_shift);
         } else {
             const size_t dd = rank_step(packed, off, bins, buf, d, lane, wid);
             u32 tok = 0u;
@@ -471,12 +535,17 @@ k_scatter_slots(SrcSlots src, int64_t chunk, int nchunks, int shift, int bins, c
         const uint4 *in = reinterpret_cast<const uint4 *>(src.a + (size_t)i * src.slot_bytes);
         uint4 head = make_uint4(0u, 0u, 0u, 0u);
         if (i < end) head = in[0];
-        const int d = i < end ? (int)((head.z & 0xffffffu) >> shift) & (bins - 1) : -1;
+        const int d = i < end ? (src.cell(i) >> shift) & (bins - 1) : -1;
         const size_t dd = rank_step(packed, off, bins, buf, d, lane, wid);
-        if (d >= 0) {
-            uint4 *out = reinterpret_cast<uint4 *>(dst + dd * (size_t)src.slot_bytes);
-            out[0] = head;
-            for (int k = 1; k < q; k++) out[k] = in[k];
+        if (d >= 0) {                                        // whole sectors: 256-bit stores
+            uint8_t *out = dst + dd * (size_t)src.slot_bytes;
+            uint4 lo = head;
+            for (int k = 1; k < q; k += 2) {
+                const uint4 hi = in[k];
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out + 16 * (k - 1)), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+                             "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+                if (k + 1 < q) lo = in[k + 1];
+            }
         }
     }
 }

@@ -31,9 +31,14 @@ constexpr int kAccWords = 10 * 32;   // deep units: counts of one chunk, [8 base
 
 struct Unit { int32_t cell, t0, t1, rbeg, rend; };
 
-__device__ __forceinline__ int slot_pos(const uint8_t *slots, int slot_bytes, int64_t i) {
-    return *reinterpret_cast<const int32_t *>(slots + (size_t)i * slot_bytes);
-}
+// The reads to pile up (k_dedup's compacted array), cell-major, sorted by start inside a cell.
+// (Listing the survivors by place instead of copying them - k_dedup writes 4 bytes per read, the pileup producer gathers
+// the 32-byte slots with one bulk copy each - was measured: dedup 0.314 -> 0.268 ms, pileup 0.56 -> 1.08 ms. Rejected.)
+struct SlotList {
+    const uint8_t *slots; int slot_bytes;
+    __device__ __forceinline__ const uint8_t *at(int64_t i) const { return slots + (size_t)i * slot_bytes; }
+    __device__ __forceinline__ int pos(int64_t i) const { return *reinterpret_cast<const int32_t *>(at(i)); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Work planning: a unit is (cell, position tile). Tile borders sit at every `unit_reads`-th read of
@@ -91,9 +96,10 @@ k_plan_scan(const mgatk_cell_qc *__restrict__ qc, int n_cells, int min_reads,
 }
 
 __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk_cell_qc *__restrict__ qc,
-                             const uint8_t *__restrict__ slots, int slot_bytes, const int32_t *__restrict__ unit_start, int n_cells,
+                             SlotList sl, const int32_t *__restrict__ unit_start, int n_cells,
                              int min_reads, int unit_reads, int ppad, int halo, Unit *__restrict__ units,
                              int cap_reads, Unit *__restrict__ units_big, int32_t *__restrict__ n_big_units) {
+    // (one warp per unit with 32 probes per search step was measured slower: 0.060 against 0.041 ms for plan on C2)
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= unit_start[n_cells]) return;
     int lo = 0, hi = n_cells;                              // last cell with unit_start[c] <= u
@@ -107,17 +113,17 @@ __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk
     Unit un;
     un.cell = c;
     un.t0 = 0; un.t1 = ppad;
-    if (k > 0) un.t0 = min(max(slot_pos(slots, slot_bytes, cs + min(k * per, cnt - 1)), 0), ppad) & ~31;
-    if (k + 1 < nt) un.t1 = min(max(slot_pos(slots, slot_bytes, cs + min((k + 1) * per, cnt - 1)), 0), ppad) & ~31;
+    if (k > 0) un.t0 = min(max(sl.pos(cs + min(k * per, cnt - 1)), 0), ppad) & ~31;
+    if (k + 1 < nt) un.t1 = min(max(sl.pos(cs + min((k + 1) * per, cnt - 1)), 0), ppad) & ~31;
     if (un.t1 < un.t0) un.t1 = un.t0;
     if (cnt == 0) { un.rbeg = un.rend = 0; }
     else {
         const int first = un.t0 - halo + 1;                // reads starting before cannot reach t0
         int a = cs, b = un.t0 == 0 ? cs : ce;              // the leftmost tile also takes the reads left of 0
-        while (a < b) { int mid = (a + b) >> 1; if (slot_pos(slots, slot_bytes, mid) < first) a = mid + 1; else b = mid; }
+        while (a < b) { int mid = (a + b) >> 1; if (sl.pos(mid) < first) a = mid + 1; else b = mid; }
         un.rbeg = a;
         b = ce;
-        while (a < b) { int mid = (a + b) >> 1; if (slot_pos(slots, slot_bytes, mid) < un.t1) a = mid + 1; else b = mid; }
+        while (a < b) { int mid = (a + b) >> 1; if (sl.pos(mid) < un.t1) a = mid + 1; else b = mid; }
         un.rend = a;
     }
     // a tile with more reads than a stage of the main kernel holds (a hot spot, a deep pile) goes to the list of
@@ -285,7 +291,7 @@ template <> struct SlotView<true> {
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(s + 16u));
     }
     __device__ __forceinline__ int pos() const { return (int)w[0]; }
-    __device__ __forceinline__ u32 meta() const { return w[3] >> 24; }
+    __device__ __forceinline__ u32 meta() const { return (w[3] >> 24) & 31u; }
     __device__ __forceinline__ int tn5off() const { return (int)((w[5] >> 24) & 63u); }
     __device__ __forceinline__ static u32 win(u32 lo, u32 hi24, int sh) {     // bits [sh, sh + 32) of a 56-bit plane, sh in (-32, 56]
         const u32 hi = hi24 & 0xffffffu;
@@ -434,12 +440,12 @@ k_pileup_main(PileupArgs a, int stage_bytes) {
     }
     __syncthreads();
     if (wid == kWarpsPerCta) {                               // ---- producer ----
-        if (lane == 0) {
-            const int n_units = *a.n_units;
-            for (u32 k = 0;; k++) {
-                const u32 b = k % kStages;
+        const int n_units = *a.n_units;
+        for (u32 k = 0;; k++) {
+            const u32 b = k % kStages;
+            Unit un;
+            if (lane == 0) {
                 if (k >= (u32)kStages) mbar_wait_sleepy(empty0 + 8u * b, ((k / kStages) - 1u) & 1u, 2000u);     // all consumer warps left the stage
-                Unit un;
                 for (;;) {
                     const int u = atomicAdd(a.work_counter, 1);
                     if (u >= n_units) { un.cell = -1; un.t0 = un.t1 = un.rbeg = un.rend = 0; break; }
@@ -447,14 +453,19 @@ k_pileup_main(PileupArgs a, int stage_bytes) {
                     if (un.t1 - un.t0 >= 32) break;          // an empty tile (its reads belong to the tile before, or to k_pileup_big)
                 }
                 s_unit[b] = un;
-                const u32 bytes = un.cell >= 0 ? (u32)(un.rend - un.rbeg) * (u32)a.slot_bytes : 0u;
-                if (bytes) {
-                    fence_proxy_async();
-                    mbar_expect_tx(full0 + 8u * b, bytes);
-                    bulk_load(stage0 + b * (u32)stage_bytes, a.slots + (size_t)un.rbeg * a.slot_bytes, bytes, full0 + 8u * b);
-                } else mbar_arrive(full0 + 8u * b);
-                if (un.cell < 0) break;
             }
+            un.cell = __shfl_sync(kFull, un.cell, 0); un.rbeg = __shfl_sync(kFull, un.rbeg, 0); un.rend = __shfl_sync(kFull, un.rend, 0);
+            const int n = un.cell >= 0 ? un.rend - un.rbeg : 0;
+            const u32 bytes = (u32)n * (u32)a.slot_bytes;
+            const u32 dst = stage0 + b * (u32)stage_bytes, bar = full0 + 8u * b;
+            if (lane == 0) {
+                if (bytes) {                                 // the unit's slots are one contiguous range: one bulk copy
+                    fence_proxy_async();
+                    mbar_expect_tx(bar, bytes);
+                    bulk_load(dst, a.slots + (size_t)un.rbeg * a.slot_bytes, bytes, bar);
+                } else mbar_arrive(bar);
+            }
+            if (un.cell < 0) break;
         }
         return;
     }
@@ -483,11 +494,11 @@ k_pileup_main(PileupArgs a, int stage_bytes) {
 
 // Number of slots among n (sorted by start, from `base`) whose start is below `key`: every thread of the CTA counts a
 // strided share, one shared-memory counter collects the warp sums.
-__device__ __forceinline__ int block_count_below(const uint8_t *base, int slot_bytes, int n, int key, int *s_count) {
+__device__ __forceinline__ int block_count_below(const SlotList &sl, int64_t first, int n, int key, int *s_count) {
     if (threadIdx.x == 0) *s_count = 0;
     __syncthreads();
     int c = 0;
-    for (int i = threadIdx.x; i < n; i += kThreads) c += slot_pos(base, slot_bytes, i) < key;
+    for (int i = threadIdx.x; i < n; i += kThreads) c += sl.pos(first + i) < key;
     c = __reduce_add_sync(kFull, c);
     if (lane_id() == 0 && c) atomicAdd(s_count, c);
     __syncthreads();
@@ -514,6 +525,7 @@ k_pileup_big(PileupArgs a) {
     const int n_units = *a.n_units;
     const TransposeConst tc = make_transpose_const(lane);
     const int q16 = a.slot_bytes >> 4;
+    const SlotList sl{a.slots, a.slot_bytes};
     for (;;) {
         __syncthreads();                                     // previous unit fully consumed (also covers the s_acc init)
         if (threadIdx.x == 0) s_unit = atomicAdd(a.work_counter, 1);
@@ -530,13 +542,13 @@ k_pileup_big(PileupArgs a) {
                 if (sub_t0 >= un0.t1) break;
                 if (sub_t0 > un0.t0) {
                     __syncthreads();                         // the previous sub-tile is consumed
-                    sub_r += block_count_below(a.slots + (size_t)sub_r * a.slot_bytes, a.slot_bytes, un0.rend - sub_r, sub_t0 - a.extent + 1, &s_count);
+                    sub_r += block_count_below(sl, sub_r, un0.rend - sub_r, sub_t0 - a.extent + 1, &s_count);
                 }
                 un.t0 = sub_t0; un.rbeg = sub_r;
                 if (un0.rend - sub_r > a.cap_reads) {
-                    const int cut = min(max(slot_pos(a.slots, a.slot_bytes, (int64_t)sub_r + a.cap_reads), 0), un0.t1) & ~31;   // first read that finds no slot
+                    const int cut = min(max(sl.pos((int64_t)sub_r + a.cap_reads), 0), un0.t1) & ~31;   // first read that finds no slot
                     un.t1 = cut > sub_t0 ? cut : min(sub_t0 + 32 * kSplitChunks, un0.t1);
-                    un.rend = sub_r + block_count_below(a.slots + (size_t)sub_r * a.slot_bytes, a.slot_bytes, un0.rend - sub_r, un.t1, &s_count);
+                    un.rend = sub_r + block_count_below(sl, sub_r, un0.rend - sub_r, un.t1, &s_count);
                 }
                 sub_t0 = un.t1;
             }
@@ -553,9 +565,11 @@ k_pileup_big(PileupArgs a) {
                 const int nb = min(a.cap_reads, n_reads - rb);                    // reads of this batch
                 __syncthreads();                             // the previous batch / sub-tile is consumed
                 {
-                    const uint4 *g = reinterpret_cast<const uint4 *>(a.slots + (size_t)(un.rbeg + rb) * a.slot_bytes);
                     uint4 *s = reinterpret_cast<uint4 *>(dyn);
-                    for (int e = threadIdx.x; e < nb * q16; e += kThreads) s[e] = g[e];
+                    for (int e = threadIdx.x; e < nb * q16; e += kThreads) {
+                        const int j = e / q16, w = e - j * q16;
+                        s[e] = reinterpret_cast<const uint4 *>(sl.at((int64_t)un.rbeg + rb + j))[w];
+                    }
                 }
                 __syncthreads();
                 for (int item = wid; item < n_chunks * nparts; item += kWarpsPerCta) {
