@@ -136,7 +136,7 @@ class ReadBatch:
             if cuts[-1] < i < n:
                 cuts.append(i)
         cuts.append(n)
-        return [self.take(np.arange(a, b)) for a, b in zip(cuts[:-1], cuts[1:])]
+        return [self.slice(a, b) for a, b in zip(cuts[:-1], cuts[1:])]      # views when the blobs lie in record order
 
     def slice(self, a: int, b: int) -> "ReadBatch":
         """Records [a, b) of a batch whose blobs lie in record order (every ingest batch): views, no gather."""

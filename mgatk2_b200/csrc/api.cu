@@ -118,6 +118,10 @@ struct mgatk_handle {
     DevBuf ws;
     uint32_t serial = 0;
     cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    // streaming (mgatk_stream_begin_device .. _finish_device): carry planes for cells with entries beyond 65535
+    DevBuf deep_planes, deep_map;
+    int deep_cap = 0; int32_t deep_cells = 0; int deep_ppad = 0;
+    const void *deep_owner = nullptr;                    // the planes of the stream the carry planes belong to
     // side stream of the overflow-list kernel (runs next to the main pileup kernel): fork / join events
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -183,9 +187,10 @@ int warp_buffer_for(const mgatk_batch *b) {
 
 template <bool kCompact>
 int launch_scatter(mgatk_handle *h, cudaStream_t s, const ScatterArgs &a) {
-    const size_t smem = scatter_smem_bytes(a.bins, a.wbuf, a.words, kCompact);
-    CU(cudaFuncSetAttribute(k_scatter_planes<kCompact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_scatter_planes<kCompact><<<a.nchunks, kPartThreads, smem, s>>>(a);
+    constexpr int kT = kCompact ? kPartThreads : kWideThreads;
+    const size_t smem = scatter_smem_bytes<kT>(a.bins, a.wbuf, a.words, kCompact);
+    CU(cudaFuncSetAttribute(k_scatter_planes<kCompact, kT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_scatter_planes<kCompact, kT><<<a.nchunks, kT, smem, s>>>(a);
     h->launches += 1;
     CU(cudaGetLastError());
     return MGATK_OK;
@@ -359,6 +364,11 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     a.extent = p->max_read_extent;
     a.slot_bytes = L.fmt.bytes; a.words = L.fmt.words;
     a.cap_reads = L.cap_reads;
+    a.deep_map = nullptr; a.deep_planes = nullptr; a.deep_count = nullptr; a.deep_cap = 0;
+    if (accumulate && h->deep_owner == (const void *)o->planes && h->deep_cells == C && h->deep_ppad == ppad) {
+        a.deep_map = (int32_t *)h->deep_map.p + 1; a.deep_count = (int32_t *)h->deep_map.p;
+        a.deep_planes = (u32 *)h->deep_planes.p; a.deep_cap = h->deep_cap;
+    }
     // cross-cell base totals: reduced by the counting kernels themselves (32-bit atomics on a [4][ppad] scratch, widened
     // below) when the contig fits the scratch, else by a pass over the finished planes
     const bool fused_totals = !accumulate && ppad <= kTotalsMaxPpad && env_int("MGATK_FUSED_TOTALS", 1);
@@ -462,6 +472,8 @@ int mgatk_destroy(mgatk_handle *h) {
         if (sl.in_done) { cudaEventDestroy(sl.in_done); cudaEventDestroy(sl.compute_done); cudaEventDestroy(sl.out_done); }
     }
     if (h->ws.p) cudaFree(h->ws.p);
+    if (h->deep_planes.p) cudaFree(h->deep_planes.p);
+    if (h->deep_map.p) cudaFree(h->deep_map.p);
     if (h->s_h2d) { cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h); }
     if (h->events_ready) for (int i = 0; i <= kMaxStages; i++) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -505,6 +517,15 @@ int mgatk_stream_begin_device(mgatk_handle *h, const mgatk_params *p, const mgat
     const size_t C = (size_t)p->n_cells, P = (size_t)p->mito_length, ppad = (size_t)MGATK_POS_PAD(P);
     if (C) CU(cudaMemsetAsync(o->planes, 0, C * MGATK_N_PLANES * ppad * 2, s));
     if (C) CU(cudaMemsetAsync(o->cell_qc, 0, C * sizeof(mgatk_cell_qc), s));
+    if (C) {    // carry planes for up to kDeepSets cells whose entries pass 65535 while the batches add up (bulk mode, deep piles)
+        int rc;
+        const int cap = (int)(C < (size_t)env_int("MGATK_DEEP_SETS", 64) ? C : (size_t)env_int("MGATK_DEEP_SETS", 64));
+        if ((rc = ensure(h, h->deep_map, (C + 1) * 4)) || (rc = ensure(h, h->deep_planes, (size_t)cap * 10 * ppad * 4))) return rc;
+        CU(cudaMemsetAsync(h->deep_map.p, 0xff, (C + 1) * 4, s));
+        CU(cudaMemsetAsync(h->deep_map.p, 0, 4, s));                             // word 0: sets handed out
+        CU(cudaMemsetAsync(h->deep_planes.p, 0, (size_t)cap * 10 * ppad * 4, s));
+        h->deep_cap = cap; h->deep_cells = (int32_t)C; h->deep_ppad = (int)ppad; h->deep_owner = o->planes;
+    }
     CU(cudaMemsetAsync(o->stats, 0, sizeof(mgatk_stats), s));
     CU(cudaMemsetAsync(o->base_totals, 0, P * 4 * sizeof(int64_t), s));
     return MGATK_OK;
@@ -527,6 +548,10 @@ int mgatk_stream_finish_device(mgatk_handle *h, const mgatk_params *p, const mga
     a.P = P; a.ppad = ppad; a.max_bias = p->max_strand_bias;
     a.raw = (p->flags & MGATK_FLAG_RAW_PILEUP) ? 1 : 0;
     a.apply_bias = !a.raw && !(p->max_strand_bias >= 1.0);
+    if (h->deep_owner == (const void *)o->planes && h->deep_cells == C && h->deep_ppad == ppad) {
+        a.deep_map = (int32_t *)h->deep_map.p + 1; a.deep_count = (int32_t *)h->deep_map.p;
+        a.deep_planes = (u32 *)h->deep_planes.p; a.deep_cap = h->deep_cap;
+    }
     k_clear_parked<<<(C + 255) / 256, 256, 0, s>>>(o->cell_qc, C);
     k_stream_finish<<<h->sm_count * 8, 256, 0, s>>>(a, C, p->min_reads_per_cell);
     dim3 tg((ppad / 2 + 127) / 128, min((C + kTotalsCellGroup - 1) / kTotalsCellGroup, 65535));

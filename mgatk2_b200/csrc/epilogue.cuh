@@ -96,8 +96,12 @@ k_stream_finish(PileupArgs a, int n_cells, int min_reads) {
         const bool dead = cell_dead(a.qc[cell], min_reads);
         const uint16_t *in = a.planes + (size_t)cell * MGATK_N_PLANES * a.ppad + 32 * ch + lane;
         u32 cnt[10];
+        const int set = a.deep_map ? a.deep_map[cell] : -1;                       // carry planes of a deep cell: 65536-wraps per entry
 #pragma unroll
-        for (int k = 0; k < 10; k++) cnt[k] = dead ? 0u : (u32)in[(size_t)k * a.ppad];
+        for (int k = 0; k < 10; k++) {
+            cnt[k] = dead ? 0u : (u32)in[(size_t)k * a.ppad];
+            if (set >= 0 && !dead) cnt[k] += a.deep_planes[((size_t)set * 10 + k) * a.ppad + 32 * ch + lane] << 16;
+        }
         u64 sum = 0; u32 covered = 0, maxd = 0;
         finish_chunk<0>(a, cell, 32 * ch, lane, cnt, sum, covered, maxd);
         if (__any_sync(kFull, covered != 0)) {

@@ -249,15 +249,16 @@ template <> struct Packed<8> {
     __device__ __forceinline__ u32 total() const { return __dp4a(x, 0x01010101u, __dp4a(y, 0x01010101u, 0u)); }
 };
 typedef Packed<kPartWarps> Pack;
-__host__ __device__ inline size_t scatter_smem_bytes(int bins) { return (size_t)bins * (2 * sizeof(Pack) + 4); }
-
-__host__ __device__ inline size_t rank_smem_bytes(int bins) { return ((size_t)bins * (2 * sizeof(Pack) + 4) + 127) / 128 * 128; }
+template <int kWarps>
+__host__ __device__ inline size_t rank_smem_bytes_t(int bins) { return ((size_t)bins * (2 * sizeof(Packed<kWarps>) + 4) + 127) / 128 * 128; }
+__host__ __device__ inline size_t rank_smem_bytes(int bins) { return rank_smem_bytes_t<kPartWarps>(bins); }
 
 // Rank of a record inside its digit for one step of kPartThreads records in BAM order, and the digit's running
 // destination offset: match_any groups the lanes of a warp by digit, the group leaders add their group size into the
 // byte of their warp in a packed per-digit counter (8 warps x 8 bits, two words), and after one barrier every thread
 // reads "records of my digit in earlier warps" out of the lower bytes. One shared-memory atomic per (warp, digit) and
 // two barriers per step (the packed counters are double buffered). Returns the destination index (d < 0: none).
+template <class Pack>
 __device__ __forceinline__ size_t rank_step(Pack *packed, u32 *off, int bins, int buf, int d, int lane, int wid) {
     Pack *pk = packed + (size_t)buf * bins;
     const u32 peers = __match_any_sync(kFull, d);
@@ -290,8 +291,15 @@ struct ScatterArgs {
     int hi_shift;                     // two-digit partition: bits of the first digit (compact slots carry cell >> hi_shift); else 31
 };
 
+// Wide slots (reads beyond 56 positions) run 128-thread CTAs: their staging buffers (32 blobs of a few hundred bytes per
+// warp) and plane scratch would otherwise leave one 256-thread CTA per SM (stress shape: partition 1.95 -> 1.55 ms).
+#ifndef MGATK_WIDE_THREADS
+#define MGATK_WIDE_THREADS 128
+#endif
+constexpr int kWideThreads = MGATK_WIDE_THREADS;
+template <int kT>
 __host__ __device__ inline size_t scatter_smem_bytes(int bins, int wbuf, int words, bool compact) {
-    return rank_smem_bytes(bins) + (size_t)kPartWarps * (wbuf + kWarpBufSlack) + (compact ? 0 : (size_t)kPartThreads * 16 * words);
+    return rank_smem_bytes_t<kT / 32>(bins) + (size_t)(kT / 32) * (wbuf + kWarpBufSlack) + (compact ? 0 : (size_t)kT * 16 * words);
 }
 
 struct RawRec { int32_t pos, tlen, bc, prev; u32 off; uint16_t flag, lseq, ncig; uint8_t mapq; bool valid; };
@@ -428,9 +436,11 @@ __device__ __forceinline__ void store_wide(const ScatterArgs &a, const M &mem, u
 // One step = kPartThreads records in BAM order, one per thread. Per warp: the blobs of the step sit in the warp's
 // staging buffer (bulk copy issued one step earlier); compact slots are built in registers straight away, the buffer is
 // handed back to the TMA unit for the next step, and only then the CTA ranks the step (two barriers) and stores.
-template <bool kCompact>
+template <bool kCompact, int kPartThreads>
 __global__ void __launch_bounds__(kPartThreads, MGATK_SCATTER_CTAS)
 k_scatter_planes(ScatterArgs a) {
+    constexpr int kPartWarps = kPartThreads / 32;
+    typedef Packed<kPartWarps> Pack;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) u64 s_bar[kPartWarps];
     const int bins = a.bins;
@@ -438,9 +448,9 @@ k_scatter_planes(ScatterArgs a) {
     u32 *off = reinterpret_cast<u32 *>(smem_raw + (size_t)2 * bins * sizeof(Pack));   // [bins] running destination offsets
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const u32 stage_stride = (u32)(a.wbuf + kWarpBufSlack);
-    const u32 wbuf_addr = (u32)__cvta_generic_to_shared(smem_raw + rank_smem_bytes(bins)) + (u32)wid * stage_stride;
+    const u32 wbuf_addr = (u32)__cvta_generic_to_shared(smem_raw + rank_smem_bytes_t<kPartWarps>(bins)) + (u32)wid * stage_stride;
     const u32 scratch_addr = kCompact ? 0u
-        : (u32)__cvta_generic_to_shared(smem_raw + rank_smem_bytes(bins) + (size_t)kPartWarps * stage_stride) + (u32)t * 16u * (u32)a.words;
+        : (u32)__cvta_generic_to_shared(smem_raw + rank_smem_bytes_t<kPartWarps>(bins) + (size_t)kPartWarps * stage_stride) + (u32)t * 16u * (u32)a.words;
     const u32 bar_addr = (u32)__cvta_generic_to_shared(&s_bar[wid]);
     const u32 *row = a.mat + (size_t)blockIdx.x * bins;
     for (int b = t; b < bins; b += kPartThreads) { off[b] = row[b]; packed[b].clear(); packed[bins + b].clear(); }

@@ -146,6 +146,9 @@ struct PileupArgs {
     int slot_bytes, words;           // slot layout (common.cuh)
     int cap_reads;                   // slots per stage (main) / per batch (big)
     u32 *totals32;                   // [4][ppad] cross-cell base totals of this batch (fwd + rev after the filters), or null
+    // streaming: cells with an entry beyond 65535 get a set of 32-bit carry planes (count of 65536-wraps per entry of the
+    // ten counted planes), so accumulation stays exact for any depth; deep_map[cell] = set index, -1 none yet
+    int32_t *deep_map; u32 *deep_planes; int32_t *deep_count; int deep_cap;
     double max_bias;
 };
 
@@ -172,6 +175,25 @@ __device__ __forceinline__ u32 warp_transpose(u32 x, const TransposeConst &tc) {
     return x;
 }
 
+// The carry planes of a cell (streaming): looked up, or claimed by lane 0 when the cell has none yet. Warp-uniform call.
+__device__ __forceinline__ int deep_set_of(const PileupArgs &a, int cell, int lane) {
+    int set = -1;
+    if (a.deep_map && lane == 0) {
+        volatile int32_t *m = a.deep_map + cell;
+        int s = *m;
+        if (s == -1 && atomicCAS(a.deep_map + cell, -1, -2) == -1) {             // ours to claim
+            const int k = atomicAdd(a.deep_count, 1);
+            s = k < a.deep_cap ? k : -3;                                          // -3: every set is taken
+            __threadfence();
+            atomicExch(a.deep_map + cell, s);
+        } else {
+            while ((s = *m) == -2 || s == -1) {}                                  // another warp is claiming it
+        }
+        set = s >= 0 ? s : -1;
+    }
+    return __shfl_sync(kFull, set, 0);
+}
+
 // The counts of a chunk are final: strand-bias filter, coverage, Tn5 gating (pileup.py:128-154), depth
 // statistics, saturation (writers.py:205-218) and the one write of the 11 planes.
 template <int kPpad>
@@ -185,16 +207,26 @@ __device__ __forceinline__ void finish_chunk(const PileupArgs &a, int cell, int 
     }
     if (a.accumulate) {                              // streamed batches: raw counts add up in the planes; filters, coverage
         uint16_t *acc = a.planes + (size_t)cell * MGATK_N_PLANES * ppad + p;      // and statistics come in k_stream_finish
+        u32 v[10], wraps = 0u;
+#pragma unroll
+        for (int pl = 0; pl < 10; pl++) {
+            v[pl] = cnt[pl] ? (u32)acc[(size_t)pl * ppad] + cnt[pl] : 0u;
+            wraps |= v[pl] >> 16;
+        }
+        int set = -1;
+        if (__any_sync(kFull, wraps != 0u)) set = deep_set_of(a, cell, lane);      // an entry passes 65535: the cell's carry planes
         bool sat = false;
 #pragma unroll
         for (int pl = 0; pl < 10; pl++) {
             if (cnt[pl]) {
-                u32 v = (u32)acc[(size_t)pl * ppad] + cnt[pl];
-                if (v > 65535u) { v = 65535u; sat = true; }
-                acc[(size_t)pl * ppad] = (uint16_t)v;
+                if (v[pl] > 65535u) {
+                    if (set >= 0) { atomicAdd(a.deep_planes + ((size_t)set * 10 + pl) * ppad + p, v[pl] >> 16); v[pl] &= 0xffffu; }
+                    else { v[pl] = 65535u; sat = true; }
+                }
+                acc[(size_t)pl * ppad] = (uint16_t)v[pl];
             }
         }
-        if (sat) atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_SATURATED);
+        if (sat) atomicOr((u64 *)&a.stats->error_bits, (u64)ERR_SATURATED);      // no carry planes (left): refused, not saturated
         return;
     }
     if (a.apply_bias) {

@@ -286,17 +286,31 @@ def test_streamed_batches_equal_one_batch(engine, profile, kw):
     dout = engine.alloc_device_outputs(n_cells, lp.mito_length, max(b.n_records for b in parts), overflow_capacity=1 << 16)
     res = engine.run_stream(parts, lp, dout)
     assert_result_equals_oracle(res, ora)
-    # one position piled beyond 65535 cannot be streamed exactly: refused, not silently saturated
-    n = 70_000
-    one = ReadBatch.from_records([dict(pos=5000, flag=0, mapq=60, seq="ACGTACGTAC" * 2, cigar=[(0, 20)], tlen=0, bc_idx=0)])
-    deep = ReadBatch(pos=np.full(n, 5000, np.int32), tlen=np.arange(n, dtype=np.int32), flag=np.zeros(n, np.uint16),
-                     mapq=np.full(n, 60, np.uint8), bc_idx=np.zeros(n, np.int32), l_seq=np.full(n, 20, np.uint16),
-                     n_cigar=np.ones(n, np.uint16), blob_off=np.zeros(n, np.uint32), blob=one.blob)
-    lp2 = to_lib_params(make_params(deep, 1))
-    dout2 = engine.alloc_device_outputs(1, lp2.mito_length, n)
-    with pytest.raises(PileupKernelError) as e:
-        engine.run_stream([deep], lp2, dout2)
-    assert e.value.status == 9
+    # entries that pass 65535 while the batches add up (bulk depths): the cell gets carry planes and the result stays exact -
+    # one pile in one batch, and two piles in two batches that only overlap to more than 65535 together
+    from oracle.oracle import run_oracle
+    one = ReadBatch.from_records([dict(pos=0, flag=0, mapq=60, seq="ACGTACGTAC" * 2, cigar=[(0, 20)], tlen=0, bc_idx=0)])
+
+    def pile(pos, n, cell):
+        return ReadBatch(pos=np.full(n, pos, np.int32), tlen=np.arange(n, dtype=np.int32), flag=np.zeros(n, np.uint16),
+                         mapq=np.full(n, 60, np.uint8), bc_idx=np.full(n, cell, np.int32), l_seq=np.full(n, 20, np.uint16),
+                         n_cigar=np.ones(n, np.uint16), blob_off=np.zeros(n, np.uint32), blob=one.blob)
+    for parts2, cells in (([pile(5000, 70_000, 0)], 1), ([pile(5000, 40_000, 1), pile(5010, 45_000, 1), pile(9000, 66_000, 2)], 3)):
+        whole = ReadBatch.concat(parts2)
+        p2 = make_params(whole, cells, min_distance_from_end=0)
+        lp2 = to_lib_params(p2)
+        dout2 = engine.alloc_device_outputs(cells, lp2.mito_length, max(b.n_records for b in parts2), overflow_capacity=1 << 16)
+        res2 = engine.run_stream(parts2, lp2, dout2)
+        assert res2.stats["n_overflow"] > 0
+        assert_result_equals_oracle(res2, run_oracle(whole, p2, n_threads=4))
+    # without carry planes left the batch is refused, not silently saturated
+    os.environ["MGATK_DEEP_SETS"] = "0"
+    try:
+        with pytest.raises(PileupKernelError) as e:
+            engine.run_stream([pile(5000, 70_000, 0)], lp2, dout2)
+        assert e.value.status == 9
+    finally:
+        del os.environ["MGATK_DEEP_SETS"]
 
 
 def test_submit_wait_two_batches_in_flight(engine):

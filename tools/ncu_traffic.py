@@ -12,6 +12,7 @@ step) is the measured step. Kernels are grouped into the stages bench.py times (
 import argparse
 import csv
 import json
+import re
 
 STAGE_OF = (("k_hist", "filter+planes+partition"), ("k_scan", "filter+planes+partition"), ("k_scatter", "filter+planes+partition"),
             ("k_publish_m", "filter+planes+partition"), ("k_init", "filter+planes+partition"), ("k_dedup", "dedup"), ("k_plan", "plan"),
@@ -34,7 +35,8 @@ def main():
         if len(r) <= col["Metric Value"]:
             continue
         lid = int(r[col["ID"]])
-        name = r[col["Kernel Name"]].split("(")[0].split("::")[-1]
+        full = r[col["Kernel Name"]].split("(")[0].replace("<unnamed>::", "")
+        name = re.sub(r"<.*", "", full).split("::")[-1] + ("<compact>" if "<1" in full or "<(bool)1" in full else "")
         v = float(r[col["Metric Value"]].replace(",", ""))
         unit = r[col["Metric Unit"]]
         scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
