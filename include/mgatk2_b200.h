@@ -48,7 +48,7 @@ typedef enum mgatk_status {
     MGATK_ERR_OVERFLOW_CAP = 6,  /* more >65535 entries than overflow_capacity      */
     MGATK_ERR_NO_DEVICE = 7,     /* no usable CUDA device                           */
     MGATK_ERR_RANGE = 8,         /* n_cells / n_records / blob outside limits       */
-    MGATK_ERR_STREAM_SATURATED = 9 /* a streamed plane entry passed 65535 (use one batch) */
+    MGATK_ERR_STREAM_SATURATED = 9 /* streaming: more cells with entries beyond 65535 than carry-plane sets */
 } mgatk_status;
 
 /* ---- dedup strategies (reference src/cli/utils.py:164-169) ---------------- */
@@ -104,8 +104,10 @@ typedef struct mgatk_params {
  *     mgatk_pileup_device(..., flags | MGATK_FLAG_ACCUMULATE)   once per batch, in file order
  *     mgatk_stream_finish_device(...)                           cell gate, strand-bias filter, coverage, Tn5 gating,
  *                                                               depth statistics, base totals, medians
- * The result equals the one-batch result bit for bit as long as no plane entry passes 65535 while accumulating
- * (MGATK_ERR_STREAM_SATURATED otherwise: such inputs need the one-batch path and its overflow list). */
+ * The result equals the one-batch result bit for bit, whatever the depth: a cell whose plane entry passes 65535 while the
+ * batches add up (bulk mode, deep piles) gets a set of 32-bit carry planes inside the handle (64 sets, allocated by
+ * mgatk_stream_begin_device; one stream per handle at a time), folded back in by mgatk_stream_finish_device.
+ * MGATK_ERR_STREAM_SATURATED only when every set is taken. */
 #define MGATK_FLAG_ACCUMULATE 2
 
 /* ---- one batch of records, structure-of-arrays, BAM (coordinate) order ---- */
@@ -203,7 +205,7 @@ int mgatk_stream_finish_device(mgatk_handle *h, const mgatk_params *params, cons
 
 /* PileupGenerator.filter_strand_bias (pileup.py:128-154) on raw planes, in place:
  * planes_dev is [n_cells][MGATK_N_PLANES][MGATK_POS_PAD(P)] as written with MGATK_FLAG_RAW_PILEUP
- * (values above 65535 are not representable here; use the fused path for those). */
+ * (values above 65535 are not representable here; use the 32-bit variant below for those). */
 int mgatk_filter_strand_bias_device(mgatk_handle *h, uint16_t *planes_dev, int32_t n_cells, int32_t mito_length,
                                     double max_strand_bias, void *stream);
 /* The same rule on 32-bit planes (same shape): exact for any depth. This is what PileupGenerator.filter_strand_bias

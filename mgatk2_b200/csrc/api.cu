@@ -140,6 +140,7 @@ int fail(mgatk_handle *h, int code, const std::string &msg) { if (h) h->err = ms
 
 __global__ void k_init(mgatk_stats *stats, int64_t n_records, int32_t *work_counter, u32 *ticket, int accumulate) {
     work_counter[4] = 0; work_counter[5] = 0;            // overflow list: length, work counter (scalars + 32, + 36)
+    work_counter[6] = 0;                                 // long-run flag of k_find_long_runs (scalars + 40)
     if (accumulate) stats->total_reads += (uint64_t)n_records;    // streamed batch: the counters keep running
     else {
         stats->total_reads = (uint64_t)n_records;        // readers.py:93 counts every fetched record
@@ -185,12 +186,12 @@ int warp_buffer_for(const mgatk_batch *b) {
     return (int)((w + 127) / 128 * 128);
 }
 
-template <bool kCompact>
+template <bool kCompact, int kGroups>
 int launch_scatter(mgatk_handle *h, cudaStream_t s, const ScatterArgs &a) {
     constexpr int kT = kCompact ? kPartThreads : kWideThreads;
     const size_t smem = scatter_smem_bytes<kT>(a.bins, a.wbuf, a.words, kCompact);
-    CU(cudaFuncSetAttribute(k_scatter_planes<kCompact, kT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_scatter_planes<kCompact, kT><<<a.nchunks, kT, smem, s>>>(a);
+    CU(cudaFuncSetAttribute(k_scatter_planes<kCompact, kT, kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_scatter_planes<kCompact, kT, kGroups><<<a.nchunks, kT, smem, s>>>(a);
     h->launches += 1;
     CU(cudaGetLastError());
     return MGATK_OK;
@@ -303,7 +304,14 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     sa.min_baseq = p->min_baseq; sa.dist = p->min_distance_from_end; sa.min_mapq = p->min_mapq; sa.extent = p->max_read_extent;
     sa.wbuf = warp_buffer_for(b);
     sa.hi_shift = L.passes == 2 ? L.bits[0] : 31;
-    if ((rc = compact ? launch_scatter<true>(h, s, sa) : launch_scatter<false>(h, s, sa))) return rc;
+    {   // the longest window of the batch ends at max_read_extent - min_distance_from_end (pileup.py:67-72)
+        const int reach = p->max_read_extent - (p->min_distance_from_end > 0 ? p->min_distance_from_end : 0);
+        if (!compact) rc = launch_scatter<false, 7>(h, s, sa);
+        else if (reach <= 40) rc = launch_scatter<true, 5>(h, s, sa);
+        else if (reach <= 48) rc = launch_scatter<true, 6>(h, s, sa);
+        else rc = launch_scatter<true, 7>(h, s, sa);
+        if (rc) return rc;
+    }
     uint8_t *grouped = slots_a, *piled = slots_b;
     if (L.passes == 2) {
         SrcSlots ss; ss.a = slots_a; ss.m = m_ptr; ss.slot_bytes = L.fmt.bytes; ss.compact = compact; ss.hi_shift = L.bits[0];
@@ -335,9 +343,22 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     }
     da.dedup_mode = p->dedup_mode; da.qc = o->cell_qc; da.stats = o->stats;
     da.ticket = ticket; da.scan_state = (u64 *)(ws + L.scan_state); da.n_proc_out = n_proc;
-    if (compact) k_dedup<true><<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(da);
-    else k_dedup<false><<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(da);
-    h->launches += 1;
+    {   // very long (cell, start) runs switch k_dedup to its warp-cooperative look-back (scalars + 40: the flag)
+        u32 *flag = (u32 *)(ws + L.scalars + 40);
+        da.long_runs = flag;
+        const unsigned blocks = (unsigned)((b->n_records / kLongRun + 255) / 256 + 1);
+        if (compact) k_find_long_runs<true><<<blocks, 256, 0, s>>>(grouped, L.fmt.bytes, m_ptr, da.cell_first, da.n_first, flag);
+        else k_find_long_runs<false><<<blocks, 256, 0, s>>>(grouped, L.fmt.bytes, m_ptr, da.cell_first, da.n_first, flag);
+        h->launches += 1;
+    }
+    if (compact) {
+        k_dedup<true, false><<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(da);
+        k_dedup<true, true><<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(da);
+    } else {
+        k_dedup<false, false><<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(da);
+        k_dedup<false, true><<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(da);
+    }
+    h->launches += 2;
     mark(h, s, "dedup");
 
     // ---- units ----
@@ -442,7 +463,7 @@ const char *mgatk_status_string(int status) {
         case MGATK_ERR_OVERFLOW_CAP: return "overflow list capacity exceeded";
         case MGATK_ERR_NO_DEVICE: return "no usable CUDA device";
         case MGATK_ERR_RANGE: return "size outside supported range";
-        case MGATK_ERR_STREAM_SATURATED: return "a streamed plane entry passed 65535 (use one batch)";
+        case MGATK_ERR_STREAM_SATURATED: return "streaming: more cells with entries beyond 65535 than carry-plane sets";
         default: return "unknown status";
     }
 }

@@ -257,6 +257,39 @@ MG_HD void query_planes56(const M &mem, u32 seq_addr /*4-aligned*/, int L, int q
     }
 }
 
+// The same without any per-group condition: all seven groups of eight bases are computed whatever the window (what lies
+// outside it is cut by the mask at the end), so the builder is straight-line code. Loads reach up to 64 bytes past the
+// start of QUAL + 56, i.e. at most 48 bytes beyond a record's blob: the caller's staging memory must allow that.
+// kGroups = groups of eight bases to compute: 7 covers any compact read; fewer when the caller knows that no window of the
+// batch reaches further (window end <= 8 kGroups for every read).
+template <int kGroups, class M>
+MG_HD void query_planes56_straight(const M &mem, u32 seq_addr /*4-aligned*/, int L, int q_lo, int q_hi, QualGe qg, u32 (&g)[2][3]) {
+    const u32 qual_addr = seq_addr + (u32)((L + 1) >> 1);
+    const u32 qsh = (qual_addr & 3u) * 8u, qa = qual_addr & ~3u;
+    const int hi = q_hi < L ? q_hi : L;
+    const int lo = q_lo > 0 ? q_lo : 0;
+    u32 qw[2 * kGroups + 1];
+#pragma unroll
+    for (int k = 0; k < 2 * kGroups + 1; k++) qw[k] = mem.ld32(qa + 4u * (u32)k);
+    u32 mV[2] = {0u, 0u}, m0[2] = {0u, 0u}, m1[2] = {0u, 0u};
+#pragma unroll
+    for (int gi = 0; gi < kGroups; gi++) {
+        const u32 s = mem.ld32(seq_addr + 4u * (u32)gi);
+        const u32 ok = qual_ok8_top(funnel_r(qw[2 * gi], qw[2 * gi + 1], qsh), funnel_r(qw[2 * gi + 1], qw[2 * gi + 2], qsh), qg);
+        const Planes8 e = seq_planes8_raw(s);
+        const int w = gi >> 2, b = gi & 3;
+        if (b == 0) { mV[w] = insert_top_byte<0>(mV[w], e.v & ok); m0[w] = insert_top_byte<0>(m0[w], e.b0); m1[w] = insert_top_byte<0>(m1[w], e.b1); }
+        else if (b == 1) { mV[w] = insert_top_byte<1>(mV[w], e.v & ok); m0[w] = insert_top_byte<1>(m0[w], e.b0); m1[w] = insert_top_byte<1>(m1[w], e.b1); }
+        else if (b == 2) { mV[w] = insert_top_byte<2>(mV[w], e.v & ok); m0[w] = insert_top_byte<2>(m0[w], e.b0); m1[w] = insert_top_byte<2>(m1[w], e.b1); }
+        else { mV[w] = insert_top_byte<3>(mV[w], e.v & ok); m0[w] = insert_top_byte<3>(m0[w], e.b0); m1[w] = insert_top_byte<3>(m1[w], e.b1); }
+    }
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+        const u32 v = hi > lo ? mV[w] & bit_range(lo - 32 * w, hi - 32 * w) : 0u;
+        g[w][0] = v; g[w][1] = m0[w] & v; g[w][2] = m1[w] & v;
+    }
+}
+
 // the same -> four words at out + 16w
 template <class M>
 MG_HD void build_query_mask_group(const M &mem, u32 seq_addr /*4-aligned*/, u32 out /*16-aligned*/, int L, int w, int q_lo, int q_hi, QualGe qg) {

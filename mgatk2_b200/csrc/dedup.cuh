@@ -21,6 +21,8 @@ namespace mgatk {
 constexpr int kDedupThreads = MGATK_DEDUP_THREADS;
 constexpr int kDedupRounds = MGATK_DEDUP_ROUNDS;             // records per thread
 constexpr int kDedupTile = kDedupThreads * kDedupRounds;
+constexpr int kDedupPrivateSteps = 64;                      // long-run mode: look-back steps a record takes on its own before the warp helps
+constexpr int kLongRun = 2048;                              // a (cell, start) run of at least twice this many slots is always noticed
 constexpr int kDedupCells = 64;                             // consecutive cells of a tile counted in shared memory
 constexpr u64 kScanAggregate = 1ull << 62, kScanPrefix = 2ull << 62, kScanValue = (1ull << 62) - 1;
 
@@ -31,11 +33,70 @@ struct DedupArgs {
     int dedup_mode;
     mgatk_cell_qc *qc; mgatk_stats *stats;
     u32 *ticket; u64 *scan_state; int64_t *n_proc_out;
+    const u32 *long_runs;                    // set by k_find_long_runs: some (cell, start) run is longer than kLongRun slots
 };
 
+// The rest of the look-backs of a warp's records (`resume` >= 0: where a record's own scan stopped), one pending record
+// after the other, 32 predecessors per step. Returns for the calling lane: bit 0 = an earlier record of the run has the
+// same strand, bit 1 = ... and the same template length.
+// Does the partitioned array hold a very long (cell, start) run? Every kLongRun-th slot is compared with the one kLongRun
+// before it: a run of 2 kLongRun slots or more cannot hide. Sets *flag (cleared by the caller).
 template <bool kCompact>
-__global__ void __launch_bounds__(kDedupThreads, 1536 / kDedupThreads)
+__global__ void k_find_long_runs(const uint8_t *__restrict__ slots, int slot_bytes, const int64_t *__restrict__ m_ptr,
+                                 const u32 *__restrict__ cell_first, int n_first, u32 *__restrict__ flag) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1) * kLongRun;
+    if (i >= *m_ptr) return;
+    const uint4 a = *reinterpret_cast<const uint4 *>(slots + (size_t)i * slot_bytes);
+    const uint4 b = *reinterpret_cast<const uint4 *>(slots + (size_t)(i - kLongRun) * slot_bytes);
+    if (a.x != b.x) return;
+    if (kCompact) {                                          // same cell: the cell of slot i starts at or before i - kLongRun
+        int lo = 0, hi = n_first;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int64_t)__ldg(cell_first + mid) <= i) lo = mid; else hi = mid; }
+        if ((int64_t)__ldg(cell_first + lo) > i - kLongRun) return;
+    } else if (SlotKey<false>::cell(a) != SlotKey<false>::cell(b)) return;
+    *flag = 1u;
+}
+
+template <bool kCompact>
+__device__ __noinline__ u32 warp_lookback(const uint8_t *slots, size_t sb, u32 pos, u32 tlen, u32 strand, int cell, int64_t first, int64_t resume, int lane) {
+    u32 mine = 0u;
+    for (u32 pend = __ballot_sync(kFull, resume >= 0); pend; pend &= pend - 1) {
+        const int L = __ffs(pend) - 1;
+        const u32 kx = __shfl_sync(kFull, pos, L), ky = __shfl_sync(kFull, tlen, L), kstrand = __shfl_sync(kFull, strand, L);
+        const int kcell = __shfl_sync(kFull, cell, L);
+        const int64_t kfirst = __shfl_sync(kFull, first, L);
+        bool any_pos = false, any_len = false;
+        for (int64_t base = __shfl_sync(kFull, resume, L);; base -= 32) {
+            const int64_t j = base - lane;
+            bool stop = true, sp = false, sl = false;
+            if (j >= kfirst) {
+                const uint4 o = *reinterpret_cast<const uint4 *>(slots + (size_t)j * sb);
+                stop = o.x != kx || (!kCompact && SlotKey<false>::cell(o) != kcell);
+                sp = !stop && (SlotKey<kCompact>::meta(o) & SM_STRAND) == kstrand;
+                sl = sp && o.y == ky;
+            }
+            const u32 ms = __ballot_sync(kFull, stop), mp = __ballot_sync(kFull, sp), ml = __ballot_sync(kFull, sl);
+            const u32 before = ms ? ((1u << (__ffs(ms) - 1)) - 1u) : kFull;      // the run ends at the first stop
+            any_pos |= (mp & before) != 0u;
+            any_len |= (ml & before) != 0u;
+            if (ms || any_len) break;
+        }
+        if (lane == L) mine = (any_pos ? 1u : 0u) | (any_len ? 2u : 0u);
+    }
+    return mine;
+}
+
+#ifndef MGATK_DEDUP_CTAS
+#define MGATK_DEDUP_CTAS (1536 / MGATK_DEDUP_THREADS)
+#endif
+// kGuard: the instance for batches with a very long (cell, start) run (bounded private look-back, then the whole warp).
+// Both instances are launched; the one whose turn it is not leaves at once (the choice is made on the device by
+// k_find_long_runs, no host round trip). Compiled into one kernel behind a run-time flag the guard costs the common path
+// 0.035 ms on C2 (dedup 0.315 -> 0.350: its registers), as two instances about 0.01 ms (an empty launch).
+template <bool kCompact, bool kGuard>
+__global__ void __launch_bounds__(kDedupThreads, MGATK_DEDUP_CTAS)
 k_dedup(DedupArgs a) {
+    if ((*a.long_runs != 0u) != kGuard) return;
     __shared__ u32 s_cnt[4];
     __shared__ u32 s_warp[kDedupRounds][kDedupThreads / 32];
     __shared__ u32 s_blk;
@@ -67,6 +128,7 @@ k_dedup(DedupArgs a) {
         __syncthreads();
     }
     const int lane = lane_id(), wid = threadIdx.x >> 5;
+    constexpr bool guard = kGuard;
     u32 pm[kDedupRounds];
     u32 n_keep = 0, n_len = 0, n_pos = 0, n_empty = 0;
 #pragma unroll
@@ -81,8 +143,11 @@ k_dedup(DedupArgs a) {
         prev.x = __shfl_up_sync(kFull, me.x, 1); prev.y = __shfl_up_sync(kFull, me.y, 1);
         prev.z = __shfl_up_sync(kFull, me.z, 1); prev.w = __shfl_up_sync(kFull, me.w, 1);
         if (lane == 0 && i > 0 && i < m) prev = *reinterpret_cast<const uint4 *>(a.slots + (size_t)(i - 1) * sb);
+        int64_t first = 0;                                   // first slot of this record's cell
+        u32 meta = 0u;
+        bool len_dup = false, pos_dup = false;
+        int64_t resume = -1;                                 // >= 0: the look-back of this record goes on there, by the whole warp
         if (i < m) {
-            int64_t first = 0;                               // first slot of this record's cell
             if (kCompact) {
                 int e = 0;
                 while (e < kDedupCells && (int64_t)s_first[e + 1] <= i) e++;
@@ -93,22 +158,45 @@ k_dedup(DedupArgs a) {
                     cell = lo; first = __ldg(a.cell_first + lo);
                 }
             } else cell = SlotKey<false>::cell(me);
-            const u32 meta = SlotKey<kCompact>::meta(me);
+            meta = SlotKey<kCompact>::meta(me);
             const u32 strand = meta & SM_STRAND;
             paired = meta & SM_PAIRED;
-            bool len_dup = false, pos_dup = false;
             if (a.dedup_mode != MGATK_DEDUP_NONE) {
                 uint4 o = prev;
-                for (int64_t j = i - 1; j >= first; ) {
-                    if (o.x != me.x) break;                                  // another start
-                    if (!kCompact && SlotKey<false>::cell(o) != cell) break;
-                    if ((SlotKey<kCompact>::meta(o) & SM_STRAND) == strand) {
-                        pos_dup = true;
-                        if (o.y == me.y) { len_dup = true; break; }
+                if (!guard) {                                // the common case: every record walks its own (short) run
+                    for (int64_t j = i - 1; j >= first; ) {
+                        if (o.x != me.x) break;                                  // another start
+                        if (!kCompact && SlotKey<false>::cell(o) != cell) break;
+                        if ((SlotKey<kCompact>::meta(o) & SM_STRAND) == strand) {
+                            pos_dup = true;
+                            if (o.y == me.y) { len_dup = true; break; }
+                        }
+                        if (--j >= first) o = *reinterpret_cast<const uint4 *>(a.slots + (size_t)j * sb);
                     }
-                    if (--j >= first) o = *reinterpret_cast<const uint4 *>(a.slots + (size_t)j * sb);
+                } else {                                     // the batch holds a very long run: bounded private scan, then the warp
+                    for (int64_t j = i - 1; j >= first; ) {
+                        if (o.x != me.x) break;
+                        if (!kCompact && SlotKey<false>::cell(o) != cell) break;
+                        if ((SlotKey<kCompact>::meta(o) & SM_STRAND) == strand) {
+                            pos_dup = true;
+                            if (o.y == me.y) { len_dup = true; break; }
+                        }
+                        if (--j < first) break;
+                        if (j < i - kDedupPrivateSteps) { resume = j; break; }
+                        o = *reinterpret_cast<const uint4 *>(a.slots + (size_t)j * sb);
+                    }
                 }
             }
+        }
+        // Long runs (a hot spot: very many reads of one cell at one start with distinct template lengths): the rest of a
+        // record's look-back is walked by the whole warp, 32 predecessors per step - K / 32 steps instead of K for a run of K
+        // (K^2 / 2 key loads per run otherwise). Only when k_find_long_runs saw such a run: the guard costs the common path
+        // 0.04 ms on C2 when compiled in unconditionally.
+        if (guard && __any_sync(kFull, resume >= 0)) {
+            const u32 found = warp_lookback<kCompact>(a.slots, sb, me.x, me.y, meta & SM_STRAND, cell, first, resume, lane);
+            pos_dup |= (found & 1u) != 0u; len_dup |= (found & 2u) != 0u;
+        }
+        if (i < m) {
             keep = a.dedup_mode == MGATK_DEDUP_FRAGMENT_LENGTH ? !len_dup : a.dedup_mode == MGATK_DEDUP_POSITION_ONLY ? !pos_dup : true;
             // pileup.py:33-34 mapq gate (after dedup, Q2). An empty SEQ makes the reference raise
             // (readers.py:157); such survivors are reported in stats.n_empty_seq and not piled up.

@@ -331,8 +331,23 @@ template <> struct SlotView<true> {
         if (sh >= 0) return funnel_r(lo, hi, (u32)sh);
         return lo << (-sh);
     }
+    // the same for the three planes at once and without branches (every lane of a round has its own offset, so the
+    // three cases of win() would all be walked by every warp): the window is a funnel shift of two of the words
+    // (0, lo, hi, 0), picked by where it starts
     __device__ __forceinline__ void window(const PileupArgs &, u32, int sh, u32 &v, u32 &b0, u32 &b1) const {
+#ifdef MGATK_BRANCHY_WINDOW
         v = win(w[2], w[3], sh); b0 = win(w[4], w[5], sh); b1 = win(w[6], w[7], sh);
+#else
+        const u32 t = (u32)(sh + 32), s = t & 31u;           // sh in (-32, 56]: t in [1, 88]
+        const bool below = t < 32u, above = t >= 64u;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const u32 lo = w[2 + 2 * k], hi = w[3 + 2 * k] & 0xffffffu;
+            const u32 a = below ? 0u : (above ? hi : lo), b = below ? lo : (above ? 0u : hi);
+            const u32 r = funnel_r(a, b, s);
+            if (k == 0) v = r; else if (k == 1) b0 = r; else b1 = r;
+        }
+#endif
     }
 };
 template <> struct SlotView<false> {

@@ -287,7 +287,8 @@ class PileupEngine:
     def run_stream(self, batches, params: ParamsC, dout: "DeviceOutputs") -> PileupResult:
         """Batches cut on reference_start borders (`ReadBatch.split_on_start_borders`), in file order: every batch adds its
         raw counts to the resident planes (MGATK_FLAG_ACCUMULATE), the finish pass applies the cell gate, the strand-bias
-        filter, coverage / Tn5 gating and the depth statistics. Equals the one-batch result while no entry passes 65535."""
+        filter, coverage / Tn5 gating and the depth statistics. Equals the one-batch result for any depth (cells whose
+        entries pass 65535 on the way get 32-bit carry planes inside the handle)."""
         self.stream_begin(params, dout)
         for batch in batches:
             self.stream_add(batch, params, dout)

@@ -92,6 +92,10 @@ int main() {
             u32 g56[2][3];
             query_planes56(mem, seq, L, lo, hi, qg, g56);           // the all-at-once form gives the same planes
             if (memcmp(g56, g, sizeof(g))) { printf("query_planes56 mismatch L=%d d=%d minq=%d\n", L, d, minq); bad++; break; }
+            query_planes56_straight<7>(mem, seq, L, lo, hi, qg, g56);  // and so does the form without per-group conditions
+            if (memcmp(g56, g, sizeof(g))) { printf("query_planes56_straight mismatch L=%d d=%d minq=%d\n", L, d, minq); bad++; break; }
+            if (hi <= 40) { query_planes56_straight<5>(mem, seq, L, lo, hi, qg, g56); if (memcmp(g56, g, sizeof(g))) { printf("straight<5> mismatch\n"); bad++; break; } }
+            if (hi <= 48) { query_planes56_straight<6>(mem, seq, L, lo, hi, qg, g56); if (memcmp(g56, g, sizeof(g))) { printf("straight<6> mismatch\n"); bad++; break; } }
             QueryPlanes64 q;
             q.v = ((unsigned long long)g[1][0] << 32) | g[0][0]; q.b0 = ((unsigned long long)g[1][1] << 32) | g[0][1];
             q.b1 = ((unsigned long long)g[1][2] << 32) | g[0][2];

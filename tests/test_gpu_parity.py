@@ -136,6 +136,45 @@ def test_median_straddles_the_saturation_border(engine):
     assert res.cell_qc["median_lo"][2] == 0
 
 
+@pytest.mark.parametrize("dedup_mode", [0, 1, 2])
+def test_long_start_runs_in_dedup(engine, dedup_mode):
+    """Thousands of reads of one cell at one start (a hot spot): a record's look-back is finished by the whole warp after
+    its first 16 private steps. Duplicates at every distance, both strands, template lengths from small and large sets, runs
+    that end at a cell border or at another start; both duplicate counters against the oracle in all three modes."""
+    rng = np.random.default_rng(12)
+    one = ReadBatch.from_records([dict(pos=0, flag=0, mapq=60, seq="ACGTACGTAC" * 2, cigar=[(0, 20)], tlen=0, bc_idx=0)])
+    runs = [(100, 0, 3000, 40), (100, 1, 700, 5000), (101, 1, 40, 3), (4000, 0, 9000, 100000), (4000, 2, 17, 2), (4001, 2, 5000, 7)]
+    cols = {k: [] for k in ("pos", "bc", "tlen", "flag")}
+    for pos, cell, n, n_tlen in runs:
+        cols["pos"].append(np.full(n, pos)); cols["bc"].append(np.full(n, cell))
+        cols["tlen"].append(rng.integers(1, n_tlen + 1, n) * rng.choice([-1, 1], n))
+        cols["flag"].append(rng.choice([99, 147, 83, 163, 0, 16], n))
+    cat = {k: np.concatenate(v) for k, v in cols.items()}
+    order = np.argsort(cat["pos"], kind="stable")
+    n = len(order)
+    batch = ReadBatch(pos=cat["pos"][order].astype(np.int32), tlen=cat["tlen"][order].astype(np.int32),
+                      flag=cat["flag"][order].astype(np.uint16), mapq=np.full(n, 60, np.uint8), bc_idx=cat["bc"][order].astype(np.int32),
+                      l_seq=np.full(n, 20, np.uint16), n_cigar=np.ones(n, np.uint16), blob_off=np.zeros(n, np.uint32), blob=one.blob)
+    res, ora = run_both(engine, batch, 3, dedup_mode=dedup_mode)
+    if dedup_mode != 2:                                      # (no counters without dedup, readers.py:118)
+        assert ora.stats["dup_with_length"] > 1000 and ora.stats["dup_position_only"] > ora.stats["dup_with_length"]
+    assert_result_equals_oracle(res, ora)
+
+
+def test_record_count_with_chunks_past_the_end(engine):
+    """1 818 625 records: the partition's 444 chunks of 4 352 records overshoot the batch by 26 chunks and the count is
+    1 modulo 4. Those empty chunks must count nothing (a negative length rounded down to a multiple of four once made each
+    of them count the last record again: 9 phantom slots in a 2 000 477-record batch, found by the streamed stress run)."""
+    n = 1_818_625
+    batch = synth_batch(50, n, "atac50", seed=31)
+    assert batch.n_records == n
+    batch.flag[-1] = 99
+    batch.bc_idx[-1] = 0                                     # the last record passes stage 1
+    res, ora = run_both(engine, batch, 50, device_path=True)
+    assert res.stats["stage1_reads"] == ora.stats["stage1_reads"]
+    assert_result_equals_oracle(res, ora)
+
+
 def test_edge_cases(engine):
     from mgatk2_b200.exceptions import PileupKernelError
     empty = ReadBatch.from_records([])
