@@ -84,17 +84,21 @@ MG_HD u32 qual_ok8_top(u32 q0, u32 q1, QualGe g) {
 // outside v), b1 = code has bit 2 or 3 (G, T; scrap outside v).
 struct Planes8 { u32 v, b0, b1; };
 
-MG_HD u32 pack_nibble_flags_raw(u32 e) {                // flags at bits 4n (n = 0..7, nothing else set) -> bits 24..31; lower bits are scrap
-    const u32 y = (e | (e >> 3)) & 0x03030303u;         // byte k: bits 0,1 = nibbles 2k, 2k+1
+// `e` holds one flag per base at the low bit of its nibble (bits 4n, nothing else set), in BAM order: byte k carries
+// base 2k in its HIGH nibble and base 2k + 1 in its low one. Returns the eight flags as the top byte (bit 24 + i = base i;
+// lower bits are scrap). The two flags of a byte first meet in its bits 0, 1 (high nibble >> 4, low nibble << 1 - an
+// add on the FMA pipe, the sets are disjoint), then one multiplication lines the four pairs up in the top byte. Working
+// on the bytes as stored spares swapping the nibbles of every SEQ word first.
+MG_HD u32 pack_nibble_flags_raw(u32 e) {
+    const u32 y = ((e >> 4) + e * 2u) & 0x03030303u;    // byte k: bit 0 = base 2k, bit 1 = base 2k + 1
     return y * 0x01041040u;
 }
 
 MG_HD Planes8 seq_planes8_raw(u32 s) {                  // top byte = flags, lower bits scrap (AND with a top-byte mask)
-    const u32 t0 = ((s & 0x0f0f0f0fu) << 4) | ((s >> 4) & 0x0f0f0f0fu);   // nibble n now holds base n
-    const u32 t1 = t0 >> 1, t2 = t0 >> 2, t3 = t0 >> 3;
+    const u32 t1 = s >> 1, t2 = s >> 2, t3 = s >> 3;     // bit 4n of tK = bit K of nibble n
     const u32 k = 0x11111111u;
-    const u32 one3 = (t0 ^ t1 ^ t2) & ~(t0 & t1 & t2);   // exactly one of the low three code bits
-    const u32 none3 = ~(t0 | t1 | t2);
+    const u32 one3 = (s ^ t1 ^ t2) & ~(s & t1 & t2);     // exactly one of the low three code bits
+    const u32 none3 = ~(s | t1 | t2);
     Planes8 r;
     r.v = pack_nibble_flags_raw(((one3 & ~t3) | (none3 & t3)) & k);       // one-hot code
     r.b0 = pack_nibble_flags_raw((t1 | t3) & k);
