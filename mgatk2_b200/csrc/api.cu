@@ -201,7 +201,7 @@ constexpr int kChrMPpad = (int)MGATK_POS_PAD(16569);    // the plane pitch of ch
 
 template <bool kCompact, int kPpad>
 int launch_pileup_t(mgatk_handle *h, cudaStream_t s, const PileupArgs &a, const PileupArgs &a_big, int stage_bytes) {
-    const size_t smem_main = (size_t)kStages * stage_bytes, smem_big = (size_t)stage_bytes;
+    const size_t smem_main = (size_t)PileupStages<kCompact>::value * stage_bytes, smem_big = (size_t)stage_bytes;
     CU(cudaFuncSetAttribute(k_pileup_main<kCompact, kPpad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_main));
     CU(cudaFuncSetAttribute(k_pileup_big<kCompact, kPpad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
     int per_sm = 0, per_sm_big = 0;

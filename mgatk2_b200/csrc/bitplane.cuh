@@ -225,6 +225,31 @@ MG_HD void query_mask_group(const M &mem, u32 seq_addr /*4-aligned*/, int L, int
     oV = mV; o0 = m0 & mV; o1 = m1 & mV;
 }
 
+// query_mask_group without its per-subgroup conditions: the four words of SEQ and the nine of QUAL of the 32 bases are
+// always loaded and turned into flags, the window is one mask at the end (straight-line code; loads reach up to 44 bytes
+// past the end of QUAL). Same result.
+template <class M>
+MG_HD void query_mask_group_straight(const M &mem, u32 seq_addr /*4-aligned*/, int L, int w, int q_lo, int q_hi, QualGe qg, u32 &oV, u32 &o0, u32 &o1) {
+    const u32 qual_addr = seq_addr + (u32)((L + 1) >> 1) + 32u * (u32)w;
+    const u32 qsh = (qual_addr & 3u) * 8u, qa = qual_addr & ~3u;
+    u32 qw[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) qw[k] = mem.ld32(qa + 4u * (u32)k);
+    u32 mV = 0, m0 = 0, m1 = 0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const u32 s = mem.ld32(seq_addr + 16u * (u32)w + 4u * (u32)g);
+        const u32 ok = qual_ok8_top(funnel_r(qw[2 * g], qw[2 * g + 1], qsh), funnel_r(qw[2 * g + 1], qw[2 * g + 2], qsh), qg);
+        const Planes8 e = seq_planes8_raw(s);
+        if (g == 0) { mV = insert_top_byte<0>(mV, e.v & ok); m0 = insert_top_byte<0>(m0, e.b0); m1 = insert_top_byte<0>(m1, e.b1); }
+        else if (g == 1) { mV = insert_top_byte<1>(mV, e.v & ok); m0 = insert_top_byte<1>(m0, e.b0); m1 = insert_top_byte<1>(m1, e.b1); }
+        else if (g == 2) { mV = insert_top_byte<2>(mV, e.v & ok); m0 = insert_top_byte<2>(m0, e.b0); m1 = insert_top_byte<2>(m1, e.b1); }
+        else { mV = insert_top_byte<3>(mV, e.v & ok); m0 = insert_top_byte<3>(m0, e.b0); m1 = insert_top_byte<3>(m1, e.b1); }
+    }
+    mV &= bit_range(q_lo - 32 * w, (q_hi < L ? q_hi : L) - 32 * w);      // pileup.py:67-78 (also cuts bases >= L)
+    oV = mV; o0 = m0 & mV; o1 = m1 & mV;
+}
+
 // All query planes of a read of at most 56 bases at once (the compact slot, common.cuh): every word of SEQ and QUAL
 // is loaded once, groups of eight bases outside the window are skipped as a whole, the window itself is one mask at the
 // end. g[w] = { V, B0, B1 } of query bases 32w .. 32w+31.

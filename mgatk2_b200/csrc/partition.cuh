@@ -417,14 +417,14 @@ __device__ __forceinline__ void store_wide(const ScatterArgs &a, const M &mem, u
     } else if (h.simple) {
         for (int k = 0; k < W; k++) {
             u32 v = 0u, b0 = 0u, b1 = 0u;
-            if (k < nq) query_mask_group(mem, seq_addr, L, k, q_lo, q_hi, qg, v, b0, b1);
+            if (k < nq) query_mask_group_straight(mem, seq_addr, L, k, q_lo, q_hi, qg, v, b0, b1);
             out.put(make_uint4(v, b0, b1, 0u));
         }
     } else {
         const SharedMem smem;
         for (int w = 0; w < nq; w++) {
             u32 v, b0, b1;
-            query_mask_group(mem, seq_addr, L, w, q_lo, q_hi, qg, v, b0, b1);
+            query_mask_group_straight(mem, seq_addr, L, w, q_lo, q_hi, qg, v, b0, b1);
             smem.st128(scratch_addr + 16u * (u32)w, v, b0, b1, 0u);
         }
         const QueryPlanesMem<SharedMem> q{smem, scratch_addr, nq};

@@ -466,7 +466,11 @@ __device__ __forceinline__ void unit_statistics(const PileupArgs &a, int cell, i
 #ifndef MGATK_PILEUP_HINT
 #define MGATK_PILEUP_HINT 500u
 #endif
-constexpr int kStages = MGATK_PILEUP_STAGES;   // units in flight per CTA of the main kernel: a warp may run this far ahead of the slowest
+#ifndef MGATK_PILEUP_WIDE_STAGES
+#define MGATK_PILEUP_WIDE_STAGES 2            // wide slots: stages of 32 KB - two of them leave room for three CTAs per SM
+#endif
+// units in flight per CTA of the main kernel: a warp may run this far ahead of the slowest
+template <bool kCompact> struct PileupStages { static constexpr int value = kCompact ? MGATK_PILEUP_STAGES : MGATK_PILEUP_WIDE_STAGES; };
 
 // ---------------------------------------------------------------------------------------------
 // Main kernel: every unit fits one stage. Warp kWarpsPerCta is the producer: unit index from the global counter, the
@@ -478,6 +482,7 @@ constexpr int kStages = MGATK_PILEUP_STAGES;   // units in flight per CTA of the
 template <bool kCompact, int kPpad>
 __global__ void __launch_bounds__(kThreads + 32, kCompact ? MGATK_PILEUP_CTAS : 3)     // wide slots: the walk over plane groups needs the registers
 k_pileup_main(PileupArgs a, int stage_bytes) {
+    constexpr int kStages = PileupStages<kCompact>::value;
     extern __shared__ __align__(128) uint8_t dyn[];          // [kStages][stage_bytes]
     __shared__ __align__(8) u64 s_full[kStages], s_empty[kStages];
     __shared__ Unit s_unit[kStages];

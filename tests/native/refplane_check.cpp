@@ -86,6 +86,12 @@ int main() {
         if (cigar_ref_span(mem, blob, ncig) != (int)span) { printf("span mismatch\n"); bad++; break; }
         const int W = (int)((span + 31) / 32) + 1;
         std::vector<u32> got(3 * W, 0);
+        for (int w = 0; w < nq; w++) {                          // the straight-line form of a group gives the same planes
+            u32 a0, a1, a2, b0, b1, b2;
+            query_mask_group(mem, seq, L, w, lo, hi, qg, a0, a1, a2);
+            query_mask_group_straight(mem, seq, L, w, lo, hi, qg, b0, b1, b2);
+            if (a0 != b0 || a1 != b1 || a2 != b2) { printf("query_mask_group_straight mismatch L=%d w=%d d=%d minq=%d\n", L, w, d, minq); bad++; break; }
+        }
         if (small) {
             u32 g[2][3] = {{0, 0, 0}, {0, 0, 0}};
             for (int w = 0; w < nq; w++) query_mask_group(mem, seq, L, w, lo, hi, qg, g[w][0], g[w][1], g[w][2]);
