@@ -2,13 +2,17 @@
 """Benchmark of the per-cell chrM pileup hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA, C-ABI)
-    python bench.py --impl reference [...]                       CPU arm (oracle port, all host threads)
+    python bench.py --impl reference [...]                       the reference's own Python (baseline/_ref), C port beside it
+    torchrun ... bench.py --gpus N --scaling strong              ONE configs[2]-shaped input split by barcode over N GPUs
 
 A step is one pass of stages 1-6 over one batch of synthetic records. At N=1 the workload is
 BASELINE.json configs[1] (2 000 cells x 20 M records, 2x50 bp, default `run` filters); at N>1 every
 rank owns a barcode shard of that same size (weak scaling, no data-path collective). `value` is records/s
 with inputs resident in HBM (CUDA events, max over ranks); `e2e` is the same metric through
-`mgatk_pileup_host` with pinned HOST buffers (H2D + kernels + D2H inside the timed region).
+`mgatk_pileup_host_submit` / `_wait` with pinned HOST buffers (H2D + kernels + D2H inside the timed region, two batches in
+flight) next to a probe of the box's host -> device ceiling; `roofline` is the WHOLE step against the measured HBM
+bandwidth, with the dominant kernel reported against its own algorithmic bytes; `cpu_baseline` is the unmodified
+reference (kind "reference") on a bounded sample, with the C port on all host threads as `cpu_baseline.port`.
 """
 from __future__ import annotations
 

@@ -15,7 +15,7 @@ import json
 import re
 
 STAGE_OF = (("k_hist", "filter+planes+partition"), ("k_scan", "filter+planes+partition"), ("k_scatter", "filter+planes+partition"),
-            ("k_publish_m", "filter+planes+partition"), ("k_init", "filter+planes+partition"), ("k_dedup", "dedup"), ("k_plan", "plan"),
+            ("k_publish_m", "filter+planes+partition"), ("k_init", "filter+planes+partition"), ("k_dedup", "dedup"), ("k_find_long_runs", "dedup"), ("k_plan", "plan"),
             ("k_pileup", "pileup"), ("k_totals", "totals+median"), ("k_base_totals", "totals+median"), ("k_median", "totals+median"))
 
 
