@@ -102,19 +102,32 @@ def decode_datatype(b: bytes):
 
 # --------------------------------------------------------------------------------------------- writer
 class _Out:
-    def __init__(self):
-        self.buf = bytearray()
+    """Append-only output with a running offset; written straight to the file (chunks never pile up in memory)."""
+
+    def __init__(self, path):
+        self.f = open(path, "wb")
+        self.pos = 0
 
     def tell(self):
-        return len(self.buf)
+        return self.pos
 
     def align(self, a=8):
-        self.buf += b"\0" * (-len(self.buf) % a)
+        self.put(b"\0" * (-self.pos % a))
 
     def put(self, b: bytes) -> int:
-        at = len(self.buf)
-        self.buf += b
+        at = self.pos
+        if b:
+            self.f.write(b)
+            self.pos += len(b)
         return at
+
+    def patch(self, at: int, b: bytes):
+        self.f.seek(at)
+        self.f.write(b)
+        self.f.seek(self.pos)
+
+    def close(self):
+        self.f.close()
 
 
 def _msg(mtype: int, body: bytes, flags: int = 0) -> bytes:
@@ -188,7 +201,7 @@ class H5Writer:
 
     def __init__(self, path, threads: int = 8):
         self.path = path
-        self.out = _Out()
+        self.out = _Out(path)
         self.out.put(b"\0" * 64)                             # superblock (48 bytes), written last
         self.heap = _GlobalHeap(self.out.put(b"\0" * _GlobalHeap.SIZE))
         self.root = {"links": [], "attrs": []}
@@ -200,6 +213,8 @@ class H5Writer:
     def __exit__(self, et, ev, tb):
         if et is None:
             self.close()
+        else:
+            self.out.close()
         return False
 
     def attr(self, name: str, value, group=None):
@@ -315,10 +330,9 @@ class H5Writer:
         root_addr = self._write_group(self.root)
         eof = self.out.tell()
         sb = SIGNATURE + struct.pack("<BBBBQQQQ", 3, 8, 8, 0, 0, UNDEF, eof, root_addr)
-        self.out.buf[0:48] = sb + struct.pack("<I", lookup3(sb))
-        self.out.buf[self.heap.address:self.heap.address + _GlobalHeap.SIZE] = self.heap.encode()
-        with open(self.path, "wb") as f:
-            f.write(self.out.buf)
+        self.out.patch(0, sb + struct.pack("<I", lookup3(sb)))
+        self.out.patch(self.heap.address, self.heap.encode())
+        self.out.close()
 
 
 # --------------------------------------------------------------------------------------------- reader

@@ -274,3 +274,21 @@ def test_pipeline_writes_the_default_hdf5_layout(golden_dir, tmp_path):
     np.testing.assert_array_equal(m.objects["genome_coverage"].read(), np.array([len(x) / 16569 * 100 for x in dep], np.float32))
     assert m.objects["reference"].read().tobytes() == b"".join(l.split(b"\t")[1] for l in d["txt_refAllele"].tobytes().splitlines()[1:])
     assert (out / "qc" / "cell_stats.csv").read_bytes() == d["txt_cell_stats"].tobytes()
+
+
+def test_bam_file_streamed_through_the_seam(golden_dir, tmp_path):
+    """A BAM longer than `max_batch_records` is decoded in parts (native reader, parts cut on reference_start borders, next
+    part decoded on the prefetch thread) and counted through the accumulating device path: same result as the one-shot
+    read of the same file."""
+    from mgatk2_b200 import BAMReader
+    from mgatk2_b200.bamio import write_bam
+    d, batch, barcodes, params = load_golden(f"{golden_dir}/synth_run_default.npz")
+    path = str(tmp_path / "possorted_bam.bam")
+    write_bam(path, batch, barcodes, extra=[("chr1", 5), ("chrX", 9), (None, -1)])
+    one = BAMReader(path, make_config(params), set(barcodes), barcode_list=barcodes)
+    rbb_one, stats_one = one.collect_reads_by_barcode()
+    parts = BAMReader(path, make_config(params), set(barcodes), barcode_list=barcodes, max_batch_records=max(batch.n_records // 6, 1))
+    rbb_parts, stats_parts = parts.collect_reads_by_barcode()
+    assert not one.streamed and parts.streamed
+    assert stats_one == stats_parts
+    _same_cells(rbb_one, rbb_parts)
