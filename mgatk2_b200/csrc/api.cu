@@ -186,15 +186,25 @@ int warp_buffer_for(const mgatk_batch *b) {
     return (int)((w + 127) / 128 * 128);
 }
 
-template <bool kCompact, int kGroups>
-int launch_scatter(mgatk_handle *h, cudaStream_t s, const ScatterArgs &a) {
+template <bool kCompact, int kGroups, bool kQualAnd>
+int launch_scatter_q(mgatk_handle *h, cudaStream_t s, const ScatterArgs &a) {
     constexpr int kT = kCompact ? kPartThreads : kWideThreads;
     const size_t smem = scatter_smem_bytes<kT>(a.bins, a.wbuf, a.words, kCompact);
-    CU(cudaFuncSetAttribute(k_scatter_planes<kCompact, kT, kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_scatter_planes<kCompact, kT, kGroups><<<a.nchunks, kT, smem, s>>>(a);
+    CU(cudaFuncSetAttribute(k_scatter_planes<kCompact, kT, kGroups, kQualAnd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_scatter_planes<kCompact, kT, kGroups, kQualAnd><<<a.nchunks, kT, smem, s>>>(a);
     h->launches += 1;
     CU(cudaGetLastError());
     return MGATK_OK;
+}
+
+template <bool kCompact, int kGroups>
+int launch_scatter(mgatk_handle *h, cudaStream_t s, const ScatterArgs &a) {
+#if MGATK_LUT_PLANES && MGATK_QUAL_AND
+    // min_base_quality in [0, 127] - every real run: the instance whose quality test knows it (two instructions fewer per
+    // eight bases); anything else (a negative threshold, one nothing passes) takes the general instance
+    if (a.min_baseq >= 0 && a.min_baseq <= 127) return launch_scatter_q<kCompact, kGroups, true>(h, s, a);
+#endif
+    return launch_scatter_q<kCompact, kGroups, false>(h, s, a);
 }
 
 constexpr int kChrMPpad = (int)MGATK_POS_PAD(16569);    // the plane pitch of chrM is compiled in
@@ -351,11 +361,17 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
         else k_find_long_runs<false><<<blocks, 256, 0, s>>>(grouped, L.fmt.bytes, m_ptr, da.cell_first, da.n_first, flag);
         h->launches += 1;
     }
+    // (developer knob: unused dynamic shared memory caps the resident CTAs per SM - 45 KB: five, 56 KB: four)
+    const int dpad = env_int("MGATK_DEDUP_PAD", 0);
+    if (dpad > 0) {
+        CU(cudaFuncSetAttribute(k_dedup<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dpad));
+        CU(cudaFuncSetAttribute(k_dedup<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dpad));
+    }
     if (compact) {
-        k_dedup<true, false><<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(da);
+        k_dedup<true, false><<<(unsigned)L.dedup_blocks, kDedupThreads, dpad, s>>>(da);
         k_dedup<true, true><<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(da);
     } else {
-        k_dedup<false, false><<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(da);
+        k_dedup<false, false><<<(unsigned)L.dedup_blocks, kDedupThreads, dpad, s>>>(da);
         k_dedup<false, true><<<(unsigned)L.dedup_blocks, kDedupThreads, 0, s>>>(da);
     }
     h->launches += 2;

@@ -138,6 +138,147 @@ __device__ __forceinline__ u32 median_scan(const u32 *hist, u32 rem, u32 &bin) {
     return 0;
 }
 
+// The same by one warp (every lane calls it, every lane gets the result): eight bins per lane, a warp scan of the lane
+// sums, and the lane that holds the answer walks its eight bins. `total` = sum of all 256 bins.
+__device__ __forceinline__ u32 median_scan_warp(const u32 *hist, u32 rem, u32 &bin, u32 &total, int lane) {
+    const uint4 a = reinterpret_cast<const uint4 *>(hist)[2 * lane], b = reinterpret_cast<const uint4 *>(hist)[2 * lane + 1];
+    const u32 c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    u32 sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) sum += c[q];
+    u32 inc = sum;
+    for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
+    total = __shfl_sync(kFull, inc, 31);
+    const u32 holds = __ballot_sync(kFull, inc > rem);     // lanes whose bins reach beyond rank `rem`
+    if (!holds) { bin = 255; return 0; }
+    const int L = __ffs(holds) - 1;
+    u32 acc = inc - sum, fb = 0, fr = 0;
+    bool found = false;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        if (!found && rem < acc + c[q]) { fb = 8u * (u32)lane + (u32)q; fr = rem - acc; found = true; }
+        acc += c[q];
+    }
+    bin = __shfl_sync(kFull, fb, L);
+    return __shfl_sync(kFull, fr, L);
+}
+
+#ifndef MGATK_MEDIAN_V2
+#define MGATK_MEDIAN_V2 1
+#endif
+#if MGATK_MEDIAN_V2
+// Depths below 256 - nearly all of them - get an exact histogram in the first pass (`fine`), deeper ones are counted by
+// their high byte (`hist`): a median below 256 is read off `fine` at once, only a deeper one needs the second pass over
+// the plane (low bytes inside its high-byte bin). The selections are made by one warp (median_scan_warp).
+__global__ void __launch_bounds__(256)
+k_median(const uint16_t *__restrict__ planes, int P, int ppad, mgatk_cell_qc *__restrict__ qc,
+         const mgatk_overflow *__restrict__ ovf, const mgatk_stats *__restrict__ stats, int64_t ovf_cap) {
+    __shared__ __align__(16) u32 hist[256];                  // depths >= 256 by high byte; later: scratch of the second pass / the list
+    // depths 1..255, four copies picked by lane (neighbouring positions carry nearly the same depth: one copy would make
+    // most lanes of a warp meet on one counter), 8 words apart in their banks; summed into the first copy afterwards
+    constexpr int kFineStride = 264;
+    __shared__ __align__(16) u32 fine[4 * kFineStride];
+    __shared__ u32 sel[4];                                   // per median: coarse bin (or 0xffffffff / 0xfffffffe = none / done), remainder or value
+    __shared__ u32 s_list, s_val;
+    const int c = blockIdx.x, t = threadIdx.x, lane = t & 31;
+    const uint16_t *cov = planes + ((size_t)c * MGATK_N_PLANES + MGATK_PLANE_COVERAGE) * ppad;
+    hist[t] = 0;
+    for (int e = t; e < 4 * kFineStride; e += 256) fine[e] = 0;
+    if (t == 0) s_list = 0;
+    __syncthreads();
+    {   // eight positions per load (rows are 128-byte aligned, the padding beyond P is zero)
+        const uint4 *row = reinterpret_cast<const uint4 *>(cov);
+        u32 *mine = fine + (lane & 3) * kFineStride;
+        for (int q = t; q < ppad / 8; q += 256) {
+            const uint4 w = __ldg(row + q);
+            const u32 x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const u32 a = x[k] & 0xffffu, b = x[k] >> 16;
+                if (a) atomicAdd(a < 256u ? &mine[a] : &hist[a >> 8], 1u);
+                if (b) atomicAdd(b < 256u ? &mine[b] : &hist[b >> 8], 1u);
+            }
+        }
+    }
+    // saturated positions of this cell whose exact depth sits in the overflow list
+    const bool deep = qc[c].max_depth > 65535u && ovf != nullptr;
+    const int64_t n_list = deep ? min((int64_t)stats->n_overflow, ovf_cap) : 0;
+    const u32 want = ((u32)MGATK_PLANE_COVERAGE << 24);
+    if (deep) {
+        u32 mine = 0;
+        for (int64_t e = t; e < n_list; e += 256) mine += ovf[e].cell == c && (ovf[e].plane_pos & 0xff000000u) == want;
+        if (mine) atomicAdd(&s_list, mine);
+    }
+    __syncthreads();
+    fine[t] += fine[kFineStride + t] + fine[2 * kFineStride + t] + fine[3 * kFineStride + t];      // (thread t alone touches bin t)
+    __syncthreads();
+    if (t < 32) {                                            // warp 0: totals and both selections
+        u32 bin, n_low, n_high, dummy;
+        median_scan_warp(fine, 0u, bin, n_low, lane);
+        median_scan_warp(hist, 0u, bin, n_high, lane);
+        const u32 n = n_low + n_high;
+        for (int s = 0; s < 2; s++) {
+            const u32 k = s == 0 ? (n - 1) / 2 : n / 2;
+            u32 b = 0xffffffffu, r = 0;
+            if (n) {
+                if (k < n_low) { median_scan_warp(fine, k, r, dummy, lane); b = 0xfffffffeu; }       // the depth itself
+                else r = median_scan_warp(hist, k - n_low, b, dummy, lane);
+            }
+            if (lane == 0) { sel[2 * s] = b; sel[2 * s + 1] = r; }
+        }
+        if (lane == 0) s_val = n;
+    }
+    __syncthreads();
+    if (sel[0] == 0xffffffffu) { if (t == 0) { qc[c].median_lo = 0; qc[c].median_hi = 0; } return; }
+    const u32 n = s_val, n_below = n - s_list;               // values below the listed ones (a true 65535 included)
+    const u32 k[2] = {(n - 1) / 2, n / 2};
+    u32 res[2] = {0, 0};
+    bool have_low = false;                                   // hist holds the low-byte histogram of bin sel[0]
+    for (int s = 0; s < 2; s++) {
+        if (k[s] >= n_below) {                               // the (k - n_below)-th smallest listed depth
+            u32 rem = k[s] - n_below, prefix = 0, mask = 0;
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                __syncthreads();
+                hist[t] = 0;
+                __syncthreads();
+                for (int64_t e = t; e < n_list; e += 256)
+                    if (ovf[e].cell == c && (ovf[e].plane_pos & 0xff000000u) == want && (ovf[e].value & mask) == prefix)
+                        atomicAdd(&hist[(ovf[e].value >> shift) & 255u], 1u);
+                __syncthreads();
+                if (t == 0) { u32 bin; const u32 r = median_scan(hist, rem, bin); sel[0] = bin; sel[1] = r; }
+                __syncthreads();
+                prefix |= sel[0] << shift; mask |= 255u << shift; rem = sel[1];
+            }
+            res[s] = prefix;
+            continue;
+        }
+        const u32 bin = sel[2 * s], rem = sel[2 * s + 1];
+        if (bin == 0xfffffffeu) { res[s] = rem; continue; }   // below 256: read off the exact histogram
+        if (!(s == 1 && have_low && bin == sel[0])) {        // (same high byte as the lower median: its low-byte histogram is still valid)
+            __syncthreads();
+            hist[t] = 0;
+            __syncthreads();
+            const uint4 *row = reinterpret_cast<const uint4 *>(cov);
+            for (int q = t; q < ppad / 8; q += 256) {
+                const uint4 w = __ldg(row + q);
+                const u32 x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    const u32 a = x[kk] & 0xffffu, b = x[kk] >> 16;
+                    if (a && (a >> 8) == bin) atomicAdd(&hist[a & 255u], 1u);
+                    if (b && (b >> 8) == bin) atomicAdd(&hist[b & 255u], 1u);
+                }
+            }
+            __syncthreads();
+            have_low = s == 0;
+        }
+        if (t == 0) { u32 b; median_scan(hist, rem, b); s_val = (bin << 8) | b; }
+        __syncthreads();
+        res[s] = s_val;
+    }
+    if (t == 0) { qc[c].median_lo = res[0]; qc[c].median_hi = res[1]; }
+}
+#else
 __global__ void __launch_bounds__(256)
 k_median(const uint16_t *__restrict__ planes, int P, int ppad, mgatk_cell_qc *__restrict__ qc,
          const mgatk_overflow *__restrict__ ovf, const mgatk_stats *__restrict__ stats, int64_t ovf_cap) {
@@ -237,5 +378,6 @@ k_median(const uint16_t *__restrict__ planes, int P, int ppad, mgatk_cell_qc *__
     }
     if (t == 0) { qc[c].median_lo = res[0]; qc[c].median_hi = res[1]; }
 }
+#endif
 
 }  // namespace mgatk

@@ -275,6 +275,17 @@ __device__ __forceinline__ size_t rank_step(Pack *packed, u32 *off, int bins, in
     return (size_t)base + v.before(wid) + __popc(peers & ((1u << lane) - 1u));
 }
 
+#ifndef MGATK_LUT_PLANES
+#define MGATK_LUT_PLANES 1           // 0: the per-nibble logic of round 2's first builder (kept for A/B runs, tools/stage_sweep.py)
+#endif
+#if MGATK_LUT_PLANES
+#define MGATK_MASK_GROUP query_mask_group_lut<kQualAnd>
+#else
+#define MGATK_MASK_GROUP query_mask_group_straight
+#endif
+#ifndef MGATK_QUAL_AND
+#define MGATK_QUAL_AND 1             // a second instance of the scatter for min_base_quality in [0, 127] (api.cu: launch_scatter)
+#endif
 #ifndef MGATK_SCATTER_CTAS
 #define MGATK_SCATTER_CTAS 3
 #endif
@@ -359,7 +370,7 @@ __device__ __forceinline__ SlotHead slot_head(const ScatterArgs &a, const M &mem
 }
 
 // planes of a compact slot (at most 56 reference positions) in registers
-template <int kGroups, class M>
+template <int kGroups, bool kQualAnd, class M>
 __device__ __forceinline__ void compact_planes(const ScatterArgs &a, const M &mem, u32 cig_addr, const SlotHead &h, QualGe qg, u32 (&g)[2][3]) {
     const int q_lo = a.dist > 0 ? a.dist : 0;                             // pileup.py:67-72
     int q_hi = a.dist > 0 ? h.L - a.dist : h.L;
@@ -370,8 +381,13 @@ __device__ __forceinline__ void compact_planes(const ScatterArgs &a, const M &me
         return;
     }
     // straight-line builder (all seven groups, no per-group conditions; what lies outside the window is masked at the end):
-    // partition 0.797 -> 0.714 ms on C2 against the form that skips groups outside the window (query_planes56)
+    // partition 0.797 -> 0.714 ms on C2 against the form that skips groups outside the window (query_planes56).
+    // Planes by table lookup (two PRMTs per eight bases, bitplane.cuh): a third fewer integer instructions per read.
+#if MGATK_LUT_PLANES
+    query_planes56_lut<kGroups, kQualAnd>(mem, cig_addr + 4u * (u32)h.ncig, h.L, q_lo, q_hi, qg, g);
+#else
     query_planes56_straight<kGroups>(mem, cig_addr + 4u * (u32)h.ncig, h.L, q_lo, q_hi, qg, g);
+#endif
     if (!h.simple) {
         QueryPlanes64 q;
         q.v = ((u64)g[1][0] << 32) | g[0][0]; q.b0 = ((u64)g[1][1] << 32) | g[0][1]; q.b1 = ((u64)g[1][2] << 32) | g[0][2];
@@ -399,7 +415,7 @@ struct SectorWriter {
 };
 
 // a wide slot, written sector by sector
-template <class M>
+template <bool kQualAnd, class M>
 __device__ __forceinline__ void store_wide(const ScatterArgs &a, const M &mem, u32 cig_addr, const SlotHead &h, const RawRec &r, int cell,
                                            uint8_t *dst, QualGe qg, u32 scratch_addr) {
     const int q_lo = a.dist > 0 ? a.dist : 0;
@@ -417,14 +433,14 @@ __device__ __forceinline__ void store_wide(const ScatterArgs &a, const M &mem, u
     } else if (h.simple) {
         for (int k = 0; k < W; k++) {
             u32 v = 0u, b0 = 0u, b1 = 0u;
-            if (k < nq) query_mask_group_straight(mem, seq_addr, L, k, q_lo, q_hi, qg, v, b0, b1);
+            if (k < nq) MGATK_MASK_GROUP(mem, seq_addr, L, k, q_lo, q_hi, qg, v, b0, b1);
             out.put(make_uint4(v, b0, b1, 0u));
         }
     } else {
         const SharedMem smem;
         for (int w = 0; w < nq; w++) {
             u32 v, b0, b1;
-            query_mask_group_straight(mem, seq_addr, L, w, q_lo, q_hi, qg, v, b0, b1);
+            MGATK_MASK_GROUP(mem, seq_addr, L, w, q_lo, q_hi, qg, v, b0, b1);
             smem.st128(scratch_addr + 16u * (u32)w, v, b0, b1, 0u);
         }
         const QueryPlanesMem<SharedMem> q{smem, scratch_addr, nq};
@@ -442,7 +458,8 @@ __device__ __forceinline__ void store_wide(const ScatterArgs &a, const M &mem, u
 // handed back to the TMA unit for the next step, and only then the CTA ranks the step (two barriers) and stores.
 // kGroups (compact slots): groups of eight query bases the plane builder computes = ceil(longest window end / 8), where
 // no window of the batch ends beyond max_read_extent - min_distance_from_end (5, 6 or 7; wide slots: unused)
-template <bool kCompact, int kPartThreads, int kGroups>
+// kQualAnd: min_base_quality lies in [0, 127] (every real run), the quality test needs no mode select (bitplane.cuh)
+template <bool kCompact, int kPartThreads, int kGroups, bool kQualAnd>
 __global__ void __launch_bounds__(kPartThreads, MGATK_SCATTER_CTAS)
 k_scatter_planes(ScatterArgs a) {
     constexpr int kPartWarps = kPartThreads / 32;
@@ -497,11 +514,11 @@ k_scatter_planes(ScatterArgs a) {
                     const SharedMemPure smem;
                     const u32 sb = wbuf_addr + 16u * (cur.off - beg16) + tok;
                     h = slot_head(a, smem, sb, cur, extent_err);
-                    compact_planes<kGroups>(a, smem, sb, h, qg, g);
+                    compact_planes<kGroups, kQualAnd>(a, smem, sb, h, qg, g);
                 }
             } else if (d >= 0) {
                 h = slot_head(a, gb, 0u, cur, extent_err);
-                compact_planes<kGroups>(a, gb, 0u, h, qg, g);
+                compact_planes<kGroups, kQualAnd>(a, gb, 0u, h, qg, g);
             }
             __syncwarp();                                    // every lane has read the buffer: it goes back to the TMA unit
             have = stage_blobs(a.b, r1, lane, wbuf_addr, bar_addr, a.wbuf, beg16);
@@ -517,10 +534,10 @@ k_scatter_planes(ScatterArgs a) {
                     const SharedMem smem;
                     const u32 sb = wbuf_addr + 16u * (cur.off - beg16) + tok;
                     const SlotHead h = slot_head(a, smem, sb, cur, extent_err);
-                    store_wide(a, smem, sb, h, cur, cell, dst, qg, scratch_addr);
+                    store_wide<kQualAnd>(a, smem, sb, h, cur, cell, dst, qg, scratch_addr);
                 } else {
                     const SlotHead h = slot_head(a, gb, 0u, cur, extent_err);
-                    store_wide(a, gb, 0u, h, cur, cell, dst, qg, scratch_addr);
+                    store_wide<kQualAnd>(a, gb, 0u, h, cur, cell, dst, qg, scratch_addr);
                 }
             }
             __syncwarp();

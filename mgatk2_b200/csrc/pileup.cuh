@@ -95,6 +95,9 @@ k_plan_scan(const mgatk_cell_qc *__restrict__ qc, int n_cells, int min_reads,
     if (t == 0) { cell_start[n_cells] = (int32_t)(carry_s >> 32); unit_start[n_cells] = (int32_t)(u32)carry_s; *n_units = (int32_t)(u32)carry_s; }
 }
 
+#ifndef MGATK_PLAN_GALLOP
+#define MGATK_PLAN_GALLOP 1
+#endif
 __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk_cell_qc *__restrict__ qc,
                              SlotList sl, const int32_t *__restrict__ unit_start, int n_cells,
                              int min_reads, int unit_reads, int ppad, int halo, Unit *__restrict__ units,
@@ -119,12 +122,18 @@ __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk
     if (cnt == 0) { un.rbeg = un.rend = 0; }
     else {
         const int first = un.t0 - halo + 1;                // reads starting before cannot reach t0
+#if MGATK_PLAN_GALLOP
+        // both borders sit just below the reads the tile borders were taken from (plan 0.041 -> ? ms on C2)
+        un.rbeg = un.t0 == 0 ? cs : lower_bound_near(sl, cs, ce, cs + min(k * per, cnt - 1), first);   // the leftmost tile also takes the reads left of 0
+        un.rend = lower_bound_near(sl, cs, ce, cs + min((k + 1) * per, cnt - 1), un.t1);      // (>= rbeg: t1 >= t0 > first)
+#else
         int a = cs, b = un.t0 == 0 ? cs : ce;              // the leftmost tile also takes the reads left of 0
         while (a < b) { int mid = (a + b) >> 1; if (sl.pos(mid) < first) a = mid + 1; else b = mid; }
         un.rbeg = a;
         b = ce;
         while (a < b) { int mid = (a + b) >> 1; if (sl.pos(mid) < un.t1) a = mid + 1; else b = mid; }
         un.rend = a;
+#endif
     }
     // a tile with more reads than a stage of the main kernel holds (a hot spot, a deep pile) goes to the list of
     // k_pileup_big, which walks it in sub-tiles and batches

@@ -31,6 +31,8 @@ int main() {
         u32 want = 0;
         for (int i = 0; i < 8; i++) { const int8_t b = (int8_t)(((i < 4 ? q0 : q1) >> (8 * (i & 3))) & 255); if ((int)b >= minq) want |= 1u << (24 + i); }
         if (qual_ok8_top(q0, q1, g) != want) { printf("qual_ok8_top mismatch\n"); bad++; }
+        if ((qual_ok8_raw(q0, q1, g) & 0xff000000u) != want) { printf("qual_ok8_raw mismatch\n"); bad++; }
+        if (g.sel == 0u && (qual_ok8_raw<true>(q0, q1, g) & 0xff000000u) != want) { printf("qual_ok8_raw<and> mismatch minq=%d\n", minq); bad++; }
     }
     // seq: all nibble patterns by random words + structured words
     for (int it = 0; it < 4000000 && !bad; it++) {
@@ -45,9 +47,25 @@ int main() {
         const Planes8 e = seq_planes8_top(s);
         const u32 v = want[0] | want[1] | want[2] | want[3];
         if (e.v != v || (e.b0 & v) != (want[1] | want[3]) || (e.b1 & v) != (want[2] | want[3])) { printf("seq_planes8_top mismatch %08x\n", s); bad++; }
+        const Planes8 t = seq_planes8_lut(s);                 // the table-lookup form: b0, b1 exact, scrap below the top byte
+        if ((t.v & 0xff000000u) != v || (t.b0 & 0xff000000u) != (want[1] | want[3]) || (t.b1 & 0xff000000u) != (want[2] | want[3])) { printf("seq_planes8_lut mismatch %08x\n", s); bad++; }
         u32 back[4];
         planes_to_bases(e.v, e.b0 & e.v, e.b1 & e.v, back);
         for (int x = 0; x < 4; x++) if (back[x] != want[x]) { printf("planes_to_bases mismatch %08x\n", s); bad++; break; }
+    }
+    for (u32 h = 0; h < 65536 && !bad; h++) {                // every pair of SEQ bytes in both halves of the word
+        const u32 s = h * 0x00010001u;
+        const Planes8 e = seq_planes8_top(s), t = seq_planes8_lut(s);
+        if ((t.v & 0xff000000u) != e.v || (t.b0 & 0xff000000u) != (e.b0 & e.v) || (t.b1 & 0xff000000u) != (e.b1 & e.v)) { printf("seq_planes8_lut exhaustive %08x\n", s); bad++; }
+    }
+    // every quality byte against every threshold through the raw form (mask applied by the caller)
+    for (int minq = -200; minq <= 200 && !bad; minq++) {
+        QualGe g = make_qual_ge(minq);
+        if (g.none) continue;
+        for (int v = 0; v < 256; v++) for (int lane = 0; lane < 4; lane++) {
+            u32 q = rnd(); q &= ~(0xffu << (8 * lane)); q |= (u32)v << (8 * lane);
+            if (((qual_ge4_raw(q, g) >> (8 * lane + 7)) & 1) != (u32)((int)(int8_t)v >= minq)) { printf("qual_ge4_raw minq=%d v=%d\n", minq, v); bad++; }
+        }
     }
     // bit_range / funnel_r
     for (int lo = -40; lo <= 40; lo++) for (int hi = -40; hi <= 72; hi++) {
@@ -72,6 +90,24 @@ int main() {
         }
         for (int p = 0; p < 32; p++) for (int r = 0; r < 32; r++)
             if (((x[p] >> r) & 1) != ((org[r] >> p) & 1)) { printf("transpose\n"); bad++; p = 32; break; }
+    }
+    // planning: lower_bound_near against the plain definition, any guess, ties, ranges of every size
+    {
+        struct Starts { const int *p; int pos(int i) const { return p[i]; } };
+        static int arr[5000];
+        for (int it = 0; it < 300000 && !bad; it++) {
+            const int n = (it % 7 == 0) ? (int)(rnd() % 5000) : (int)(rnd() % 60);
+            const int spread = 1 + (int)(rnd() % ((it & 1) ? 40 : 20000));
+            int v = (int)(rnd() % 100) - 50;
+            for (int i = 0; i < n; i++) { v += (int)(rnd() % spread) * (int)(rnd() & 1); arr[i] = v; }
+            const int lo = n ? (int)(rnd() % (n + 1)) : 0, hi = lo + (n - lo ? (int)(rnd() % (n - lo + 1)) : 0);
+            const int key = (n ? arr[rnd() % n] : 0) + (int)(rnd() % 5) - 2;
+            const int guess = (int)(rnd() % (n + 20)) - 10;
+            int want = lo;
+            while (want < hi && arr[want] < key) want++;
+            const Starts sl{arr};
+            if (lower_bound_near(sl, lo, hi, guess, key) != want) { printf("lower_bound_near n=%d lo=%d hi=%d guess=%d key=%d\n", n, lo, hi, guess, key); bad++; }
+        }
     }
     if (bad) { printf("FAILED %d\n", bad); return 1; }
     printf("bitplane helpers ok\n");

@@ -91,6 +91,12 @@ int main() {
             query_mask_group(mem, seq, L, w, lo, hi, qg, a0, a1, a2);
             query_mask_group_straight(mem, seq, L, w, lo, hi, qg, b0, b1, b2);
             if (a0 != b0 || a1 != b1 || a2 != b2) { printf("query_mask_group_straight mismatch L=%d w=%d d=%d minq=%d\n", L, w, d, minq); bad++; break; }
+            query_mask_group_lut(mem, seq, L, w, lo, hi, qg, b0, b1, b2);      // and so does the table-lookup form
+            if (a0 != b0 || a1 != b1 || a2 != b2) { printf("query_mask_group_lut mismatch L=%d w=%d d=%d minq=%d\n", L, w, d, minq); bad++; break; }
+            if (qg.sel == 0u && !qg.none) {
+                query_mask_group_lut<true>(mem, seq, L, w, lo, hi, qg, b0, b1, b2);
+                if (a0 != b0 || a1 != b1 || a2 != b2) { printf("query_mask_group_lut<and> mismatch L=%d w=%d d=%d minq=%d\n", L, w, d, minq); bad++; break; }
+            }
         }
         if (small) {
             u32 g[2][3] = {{0, 0, 0}, {0, 0, 0}};
@@ -102,6 +108,14 @@ int main() {
             if (memcmp(g56, g, sizeof(g))) { printf("query_planes56_straight mismatch L=%d d=%d minq=%d\n", L, d, minq); bad++; break; }
             if (hi <= 40) { query_planes56_straight<5>(mem, seq, L, lo, hi, qg, g56); if (memcmp(g56, g, sizeof(g))) { printf("straight<5> mismatch\n"); bad++; break; } }
             if (hi <= 48) { query_planes56_straight<6>(mem, seq, L, lo, hi, qg, g56); if (memcmp(g56, g, sizeof(g))) { printf("straight<6> mismatch\n"); bad++; break; } }
+            query_planes56_lut<7>(mem, seq, L, lo, hi, qg, g56);       // table-lookup planes (PRMT), quality mask applied once
+            if (memcmp(g56, g, sizeof(g))) { printf("query_planes56_lut mismatch L=%d d=%d minq=%d\n", L, d, minq); bad++; break; }
+            if (hi <= 40) { query_planes56_lut<5>(mem, seq, L, lo, hi, qg, g56); if (memcmp(g56, g, sizeof(g))) { printf("lut<5> mismatch\n"); bad++; break; } }
+            if (hi <= 48) { query_planes56_lut<6>(mem, seq, L, lo, hi, qg, g56); if (memcmp(g56, g, sizeof(g))) { printf("lut<6> mismatch\n"); bad++; break; } }
+            if (qg.sel == 0u && !qg.none) {                          // min_baseq in [0, 127]: the form that knows it
+                query_planes56_lut<7, true>(mem, seq, L, lo, hi, qg, g56);
+                if (memcmp(g56, g, sizeof(g))) { printf("query_planes56_lut<7, and> mismatch L=%d d=%d minq=%d\n", L, d, minq); bad++; break; }
+            }
             QueryPlanes64 q;
             q.v = ((unsigned long long)g[1][0] << 32) | g[0][0]; q.b0 = ((unsigned long long)g[1][1] << 32) | g[0][1];
             q.b1 = ((unsigned long long)g[1][2] << 32) | g[0][2];
