@@ -501,9 +501,11 @@ k_scatter_planes(ScatterArgs a) {
         // readers.py:96-97 unmapped / secondary / supplementary; :104-111 tag absent or not whitelisted
         const int cell = (!cur.valid || (cur.flag & 0x904) || cur.bc < 0 || cur.bc >= a.n_cells) ? -1 : cur.bc;
         const int d = cell >= 0 ? (cell >> a.shift) & (bins - 1) : -1;
-        const u64 byte_off = 16ull * cur.off;
-        const u64 left = (u64)a.b.blob_bytes > byte_off ? (u64)a.b.blob_bytes - byte_off : 0ull;
-        const GlobalBlob gb{a.b.blob + byte_off, left > 0xffffffffull ? 0xffffffffu : (u32)left};    // when the step is not staged
+        auto global_blob = [&]() {                           // the record's blob in the caller's memory (when the step is not staged)
+            const u64 byte_off = 16ull * cur.off;
+            const u64 left = (u64)a.b.blob_bytes > byte_off ? (u64)a.b.blob_bytes - byte_off : 0ull;
+            return GlobalBlob{a.b.blob + byte_off, left > 0xffffffffull ? 0xffffffffu : (u32)left};
+        };
         if (kCompact) {
             SlotHead h;
             u32 g[2][3];
@@ -517,6 +519,7 @@ k_scatter_planes(ScatterArgs a) {
                     compact_planes<kGroups, kQualAnd>(a, smem, sb, h, qg, g);
                 }
             } else if (d >= 0) {
+                const GlobalBlob gb = global_blob();
                 h = slot_head(a, gb, 0u, cur, extent_err);
                 compact_planes<kGroups, kQualAnd>(a, gb, 0u, h, qg, g);
             }
@@ -536,6 +539,7 @@ k_scatter_planes(ScatterArgs a) {
                     const SlotHead h = slot_head(a, smem, sb, cur, extent_err);
                     store_wide<kQualAnd>(a, smem, sb, h, cur, cell, dst, qg, scratch_addr);
                 } else {
+                    const GlobalBlob gb = global_blob();
                     const SlotHead h = slot_head(a, gb, 0u, cur, extent_err);
                     store_wide<kQualAnd>(a, gb, 0u, h, cur, cell, dst, qg, scratch_addr);
                 }
