@@ -452,6 +452,8 @@ def run_b200(a):
         "counted": {"total_reads": res.stats["total_reads"], "filtered_reads": res.stats["filtered_reads"],
                     "dup_with_length": res.stats["dup_with_length"], "sum_depth": int(res.cell_qc["sum_depth"].sum())},
         "synth_seconds": t_gen, **({"strong": strong_check} if a.scaling == "strong" else {}),
+        **({"verified": "per-cell QC rows (reads, pairs, depth sum, covered, max, both medians), base totals and the "
+                        "three counters equal to the oracle at full size"} if a.verify else {}),
     }))
     if world > 1:
         dist.destroy_process_group()
