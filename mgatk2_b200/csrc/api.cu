@@ -22,6 +22,10 @@ constexpr int kMaxDigitBits = 11;                    // 2048 bins * 20 B = 40 KB
 constexpr int kMaxStages = 16;
 constexpr int kTotalsMaxPpad = 1 << 16;              // contigs up to this long get their base totals from the pileup kernel itself
 
+#ifndef MGATK_FUSED_SMALL
+#define MGATK_FUSED_SMALL 1          // 1: bin totals by atomics + one-pass bin scan, stage1_reads published by k_find_long_runs, totals widened by k_median
+#endif
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 int env_int(const char *name, int fallback) {
@@ -75,7 +79,7 @@ bool make_layout(int64_t n, int32_t n_cells, int extent, Layout &L) {
     const size_t cap = (size_t)(n > 0 ? n : 1);
     for (int gen = 0; gen < 2; gen++) { L.slots[gen] = o; o += align_up(cap * (size_t)L.fmt.bytes); }
     L.mat = o; o += align_up((size_t)L.nchunks * max_bins * 4);
-    L.part = o; o += align_up((size_t)L.ngroups * max_bins * 4);
+    L.part = o; o += align_up(((size_t)L.ngroups + 1) * max_bins * 4 + 4);      // group sums + one row of bin totals (+ their sum)
     L.cell_start = o; o += align_up(((size_t)n_cells + 1) * 4);
     L.cell_first = o; o += align_up(((size_t)n_cells + 2) * 4);        // two-digit partition of compact slots: first slot of every cell
     L.unit_start = o; o += align_up(((size_t)n_cells + 1) * 4);
@@ -150,9 +154,11 @@ __global__ void k_init(mgatk_stats *stats, int64_t n_records, int32_t *work_coun
     *work_counter = 0;
     *ticket = 0;
 }
+#if !MGATK_FUSED_SMALL
 __global__ void k_publish_m(mgatk_stats *stats, const int64_t *m, int accumulate) {
     stats->stage1_reads = (accumulate ? stats->stage1_reads : 0) + (uint64_t)*m;
 }
+#endif
 
 void mark(mgatk_handle *h, cudaStream_t s, const char *name) {
     if (h->n_stages < kMaxStages) {
@@ -167,11 +173,19 @@ template <class Src>
 int histogram_and_scan(mgatk_handle *h, cudaStream_t s, const Src &src, const Layout &L, int pass, char *ws, int64_t *m_out) {
     const int bins = 1 << L.bits[pass];
     u32 *mat = (u32 *)(ws + L.mat), *part = (u32 *)(ws + L.part);
-    k_hist<Src><<<L.nchunks, kHistThreads, (size_t)bins * 4, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat);
     dim3 sg((bins + 255) / 256, L.ngroups);
-    k_scan_group_sums<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part);
+#if MGATK_FUSED_SMALL
+    u32 *bintot = part + (size_t)L.ngroups * bins;       // [bins + 1]: bin totals, then their exclusive scan (the spare row of `part`)
+    k_hist<Src><<<L.nchunks, kHistThreads, (size_t)bins * 4, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, bintot);
+    k_scan_group_sums<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part, bintot);
+    k_scan_cells<<<1, 1024, 0, s>>>(bintot, bins, m_out);
+    k_scan_apply<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part, bintot);
+#else
+    k_hist<Src><<<L.nchunks, kHistThreads, (size_t)bins * 4, s>>>(src, L.chunk, L.nchunks, L.shift[pass], bins, mat, nullptr);
+    k_scan_group_sums<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part, nullptr);
     k_scan_bases<<<1, 1024, 0, s>>>(part, L.ngroups, bins, m_out);
-    k_scan_apply<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part);
+    k_scan_apply<<<sg, 256, 0, s>>>(mat, L.nchunks, bins, part, nullptr);
+#endif
     h->launches += 4;
     CU(cudaGetLastError());
     return MGATK_OK;
@@ -332,8 +346,10 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
         CU(cudaGetLastError());
         grouped = slots_b; piled = slots_a;
     }
+#if !MGATK_FUSED_SMALL
     k_publish_m<<<1, 1, 0, s>>>(o->stats, m_ptr, accumulate);
     h->launches += 1;
+#endif
     mark(h, s, "filter+planes+partition");
 
     // ---- stage 2: dedup, mapq gate, compaction of the reads to pile up ----
@@ -357,8 +373,9 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
         u32 *flag = (u32 *)(ws + L.scalars + 40);
         da.long_runs = flag;
         const unsigned blocks = (unsigned)((b->n_records / kLongRun + 255) / 256 + 1);
-        if (compact) k_find_long_runs<true><<<blocks, 256, 0, s>>>(grouped, L.fmt.bytes, m_ptr, da.cell_first, da.n_first, flag);
-        else k_find_long_runs<false><<<blocks, 256, 0, s>>>(grouped, L.fmt.bytes, m_ptr, da.cell_first, da.n_first, flag);
+        mgatk_stats *pub = MGATK_FUSED_SMALL ? o->stats : nullptr;     // stats.stage1_reads is published by this kernel's first thread
+        if (compact) k_find_long_runs<true><<<blocks, 256, 0, s>>>(grouped, L.fmt.bytes, m_ptr, da.cell_first, da.n_first, flag, pub, accumulate);
+        else k_find_long_runs<false><<<blocks, 256, 0, s>>>(grouped, L.fmt.bytes, m_ptr, da.cell_first, da.n_first, flag, pub, accumulate);
         h->launches += 1;
     }
     // (developer knob: unused dynamic shared memory caps the resident CTAs per SM - 45 KB: five, 56 KB: four)
@@ -419,9 +436,12 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
     if (accumulate) return MGATK_OK;                     // filters, coverage, statistics: mgatk_stream_finish_device
 
     // ---- reference-allele totals, median depth ----
+    const bool widen_in_median = MGATK_FUSED_SMALL && fused_totals;      // k_median's CTAs widen the totals on their way in
     if (fused_totals) {
-        k_totals_widen<<<(P + 255) / 256, 256, 0, s>>>(a.totals32, P, ppad, (u64 *)o->base_totals);
-        h->launches++;
+        if (!widen_in_median) {
+            k_totals_widen<<<(P + 255) / 256, 256, 0, s>>>(a.totals32, P, ppad, (u64 *)o->base_totals);
+            h->launches++;
+        }
     } else {
         dim3 tg((ppad / 2 + 127) / 128, min((C + kTotalsCellGroup - 1) / kTotalsCellGroup, 65535));
         k_base_totals<<<tg, 128, 0, s>>>(o->planes, C, P, ppad, (u64 *)o->base_totals);
@@ -431,7 +451,8 @@ int run_device(mgatk_handle *h, const mgatk_params *p, const mgatk_batch *b, con
             h->launches++;
         }
     }
-    k_median<<<C, 256, 0, s>>>(o->planes, P, ppad, o->cell_qc, o->overflow_capacity > 0 ? o->overflow : nullptr, o->stats, o->overflow_capacity);
+    k_median<<<C, 256, 0, s>>>(o->planes, P, ppad, o->cell_qc, o->overflow_capacity > 0 ? o->overflow : nullptr, o->stats, o->overflow_capacity,
+                               widen_in_median ? a.totals32 : nullptr, (u64 *)o->base_totals);
     h->launches++;
     CU(cudaGetLastError());
     mark(h, s, "totals+median");
@@ -598,7 +619,8 @@ int mgatk_stream_finish_device(mgatk_handle *h, const mgatk_params *p, const mga
         k_base_totals_overflow<<<8, 256, 0, s>>>(o->overflow, o->stats, o->overflow_capacity, P, (u64 *)o->base_totals);
         h->launches++;
     }
-    k_median<<<C, 256, 0, s>>>(o->planes, P, ppad, o->cell_qc, o->overflow_capacity > 0 ? o->overflow : nullptr, o->stats, o->overflow_capacity);
+    k_median<<<C, 256, 0, s>>>(o->planes, P, ppad, o->cell_qc, o->overflow_capacity > 0 ? o->overflow : nullptr, o->stats, o->overflow_capacity,
+                               nullptr, nullptr);
     h->launches++;
     CU(cudaGetLastError());
     return MGATK_OK;

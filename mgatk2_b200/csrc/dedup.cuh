@@ -43,7 +43,10 @@ struct DedupArgs {
 // before it: a run of 2 kLongRun slots or more cannot hide. Sets *flag (cleared by the caller).
 template <bool kCompact>
 __global__ void k_find_long_runs(const uint8_t *__restrict__ slots, int slot_bytes, const int64_t *__restrict__ m_ptr,
-                                 const u32 *__restrict__ cell_first, int n_first, u32 *__restrict__ flag) {
+                                 const u32 *__restrict__ cell_first, int n_first, u32 *__restrict__ flag,
+                                 mgatk_stats *__restrict__ publish, int accumulate) {
+    if (publish && blockIdx.x == 0 && threadIdx.x == 0)      // readers.py:111 survivors of stage 1 (streamed batches keep counting)
+        publish->stage1_reads = (accumulate ? publish->stage1_reads : 0) + (uint64_t)*m_ptr;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1) * kLongRun;
     if (i >= *m_ptr) return;
     const uint4 a = *reinterpret_cast<const uint4 *>(slots + (size_t)i * slot_bytes);

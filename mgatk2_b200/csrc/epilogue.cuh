@@ -172,7 +172,15 @@ __device__ __forceinline__ u32 median_scan_warp(const u32 *hist, u32 rem, u32 &b
 // the plane (low bytes inside its high-byte bin). The selections are made by one warp (median_scan_warp).
 __global__ void __launch_bounds__(256)
 k_median(const uint16_t *__restrict__ planes, int P, int ppad, mgatk_cell_qc *__restrict__ qc,
-         const mgatk_overflow *__restrict__ ovf, const mgatk_stats *__restrict__ stats, int64_t ovf_cap) {
+         const mgatk_overflow *__restrict__ ovf, const mgatk_stats *__restrict__ stats, int64_t ovf_cap,
+         const u32 *__restrict__ t32, u64 *__restrict__ totals) {
+    if (t32)                                                 // the base totals the pileup kernel reduced, widened to int64 [P][4] (k_totals_widen)
+        for (int p = blockIdx.x * 256 + threadIdx.x; p < P; p += gridDim.x * 256) {
+            ulonglong2 lo, hi;
+            lo.x = t32[p]; lo.y = t32[(size_t)ppad + p]; hi.x = t32[(size_t)2 * ppad + p]; hi.y = t32[(size_t)3 * ppad + p];
+            reinterpret_cast<ulonglong2 *>(totals)[2 * (size_t)p] = lo;
+            reinterpret_cast<ulonglong2 *>(totals)[2 * (size_t)p + 1] = hi;
+        }
     __shared__ __align__(16) u32 hist[256];                  // depths >= 256 by high byte; later: scratch of the second pass / the list
     // depths 1..255, four copies picked by lane (neighbouring positions carry nearly the same depth: one copy would make
     // most lanes of a warp meet on one counter), 8 words apart in their banks; summed into the first copy afterwards
@@ -281,7 +289,15 @@ k_median(const uint16_t *__restrict__ planes, int P, int ppad, mgatk_cell_qc *__
 #else
 __global__ void __launch_bounds__(256)
 k_median(const uint16_t *__restrict__ planes, int P, int ppad, mgatk_cell_qc *__restrict__ qc,
-         const mgatk_overflow *__restrict__ ovf, const mgatk_stats *__restrict__ stats, int64_t ovf_cap) {
+         const mgatk_overflow *__restrict__ ovf, const mgatk_stats *__restrict__ stats, int64_t ovf_cap,
+         const u32 *__restrict__ t32, u64 *__restrict__ totals) {
+    if (t32)                                                 // the base totals the pileup kernel reduced, widened to int64 [P][4] (k_totals_widen)
+        for (int p = blockIdx.x * 256 + threadIdx.x; p < P; p += gridDim.x * 256) {
+            ulonglong2 lo, hi;
+            lo.x = t32[p]; lo.y = t32[(size_t)ppad + p]; hi.x = t32[(size_t)2 * ppad + p]; hi.y = t32[(size_t)3 * ppad + p];
+            reinterpret_cast<ulonglong2 *>(totals)[2 * (size_t)p] = lo;
+            reinterpret_cast<ulonglong2 *>(totals)[2 * (size_t)p + 1] = hi;
+        }
     __shared__ u32 hist[256];
     __shared__ u32 sel[4];                                   // bin, remainder for lo / hi
     __shared__ u32 s_list, s_val;

@@ -65,11 +65,13 @@ constexpr int kHistAhead = 4;      // steps loaded before counting (k_hist)
 #define MGATK_HIST_THREADS 1024
 #endif
 constexpr int kHistThreads = MGATK_HIST_THREADS;
+// `bintot` (may be null): per-bin totals that k_scan_group_sums adds up afterwards - cleared here by the first CTA.
 template <class Src>
 __global__ void __launch_bounds__(kHistThreads)
-k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict__ mat) {
+k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict__ mat, u32 *__restrict__ bintot) {
     extern __shared__ u32 smem[];
     u32 *h = smem;
+    if (bintot && blockIdx.x == 0) for (int b = threadIdx.x; b <= bins; b += kHistThreads) bintot[b] = 0;
     for (int b = threadIdx.x; b < bins; b += kHistThreads) h[b] = 0;
     __syncthreads();
     const int64_t n = src.count();
@@ -118,7 +120,10 @@ k_hist(Src src, int64_t chunk, int nchunks, int shift, int bins, u32 *__restrict
 }
 
 // scan of mat[chunk][bin] in (bin, chunk) order: S1 group sums, S2 bases, S3 in-place exclusive prefixes
-__global__ void k_scan_group_sums(const u32 *__restrict__ mat, int nchunks, int bins, u32 *__restrict__ part) {
+// With `bintot` the bin totals are added up here (one atomic per group and bin), the scan over the bins is a single pass
+// over `bins` numbers (k_scan_cells) and k_scan_apply sums the groups before its own: the one-CTA pass over the whole
+// [groups][bins] matrix (k_scan_bases, 18 us on C2) drops out.
+__global__ void k_scan_group_sums(const u32 *__restrict__ mat, int nchunks, int bins, u32 *__restrict__ part, u32 *__restrict__ bintot) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
     if (b >= bins) return;
     const int w0 = g * kScanGroup;
@@ -129,6 +134,7 @@ __global__ void k_scan_group_sums(const u32 *__restrict__ mat, int nchunks, int 
 #pragma unroll
     for (int k = 0; k < kScanGroup; k++) s += v[k];
     part[(size_t)g * bins + b] = s;
+    if (bintot && s) atomicAdd(&bintot[b], s);
 }
 
 __global__ void __launch_bounds__(1024)
@@ -171,14 +177,21 @@ k_scan_bases(u32 *__restrict__ part, int ngroups, int bins, int64_t *__restrict_
     if (t == 0 && total_out) *total_out = carry_s;
 }
 
-__global__ void k_scan_apply(u32 *__restrict__ mat, int nchunks, int bins, const u32 *__restrict__ part) {
+// `binbase` (may be null): exclusive scan of the bin totals; then part[][] still holds the plain group sums and the base
+// of group g is binbase[b] + the sums of the groups before it.
+__global__ void k_scan_apply(u32 *__restrict__ mat, int nchunks, int bins, const u32 *__restrict__ part, const u32 *__restrict__ binbase) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
     if (b >= bins) return;
     const int w0 = g * kScanGroup;
     u32 v[kScanGroup];
 #pragma unroll
     for (int k = 0; k < kScanGroup; k++) v[k] = w0 + k < nchunks ? mat[(size_t)(w0 + k) * bins + b] : 0u;
-    u32 run = part[(size_t)g * bins + b];
+    u32 run;
+    if (binbase) {
+        run = binbase[b];
+#pragma unroll 4
+        for (int q = 0; q < g; q++) run += part[(size_t)q * bins + b];
+    } else run = part[(size_t)g * bins + b];
 #pragma unroll
     for (int k = 0; k < kScanGroup; k++) if (w0 + k < nchunks) { mat[(size_t)(w0 + k) * bins + b] = run; run += v[k]; }
 }
@@ -201,7 +214,7 @@ k_cell_counts(SrcUser src, int smem_cells, u32 *__restrict__ counts) {
 }
 
 __global__ void __launch_bounds__(1024)
-k_scan_cells(u32 *__restrict__ counts, int n) {              // in place, exclusive; counts[n] = total
+k_scan_cells(u32 *__restrict__ counts, int n, int64_t *__restrict__ total_out = nullptr) {   // in place, exclusive; counts[n] = total
     __shared__ u32 warp_sums[32];
     __shared__ u32 carry_s;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -227,7 +240,7 @@ k_scan_cells(u32 *__restrict__ counts, int n) {              // in place, exclus
         if (t == 1023) carry_s = carry + warp_sums[31] + inc;
         __syncthreads();
     }
-    if (t == 0) counts[n] = carry_s;
+    if (t == 0) { counts[n] = carry_s; if (total_out) *total_out = (int64_t)carry_s; }
 }
 
 constexpr int kPartWarps = kPartThreads / 32;
