@@ -43,6 +43,10 @@ def available() -> bool:
 
 def _activate():
     os.environ.setdefault("TQDM_DISABLE", "1")     # the reference wraps its loops in tqdm progress bars
+    # Workers of the reference's process pool are spawned: they re-run the parent's main module (bench.py) and then
+    # unpickle their first task, which imports `processing` before `core` - the reference's circular import fails in that
+    # order (its own CLI imports `core` first). bench.py sees this variable in a worker and activates the same way.
+    os.environ["MGATK_REF_ACTIVATE"] = "1"
     for p in (STUBS, REF_DIR):
         if p not in sys.path:
             sys.path.insert(0, p)       # spawned pool workers inherit sys.path (multiprocessing preparation data)

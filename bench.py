@@ -91,6 +91,12 @@ def default_params(n_cells, extent, which="run"):
 
 
 # --------------------------------------------------------------------------- CPU arms
+if __name__ == "__mp_main__" and os.environ.get("MGATK_REF_ACTIVATE"):
+    # a spawned worker of the reference's own process pool (reference arm only): import the reference in its working order
+    from baseline import ref_harness as _rh
+    _rh._activate()
+
+
 def cpu_sample(a, cells=None):
     """Bounded sample with the per-cell shape of the workload (same records per cell)."""
     from mgatk2_b200.synth import synth_batch
@@ -165,6 +171,29 @@ def time_reference_python(a, steps, warmup, budget_s):
             "reference_stats": {k: int(v) for k, v in stats.items() if isinstance(v, (int, np.integer))}}
 
 
+def time_reference_pool(a, records_per_cell=3000):
+    """Side figure of the reference arm: the reference's process pool at work. At the workload's depth the reference
+    forces its sequential loop (`processors.py:99-101`), so its `--threads` never shows; this sample stays below 2 500
+    reads per cell (one pass, all host cores, worker start-up included - the reference pays it on every run)."""
+    from baseline import ref_harness as rh
+    if not rh.available():
+        return None
+    from mgatk2_b200.synth import make_whitelist, synth_batch
+    cores = os.cpu_count() or 1
+    cells = int(min(256, 16 * cores))
+    recs = cells * records_per_cell
+    batch = synth_batch(cells, recs, a.profile, seed=BASE_SEED + CONFIG_INDEX + 199)
+    wl = make_whitelist(cells)
+    path = rh.prepare(batch, wl)
+    try:
+        dt, stats, _, mode = rh.run_once(path, wl, n_cores=cores, **filter_kwargs(a.params))
+    finally:
+        rh.release(path)
+    return {"value": recs / dt, "unit": UNIT, "cores": cores, "kind": "reference", "seconds_per_pass": dt,
+            "sample": f"{cells} cells x {recs} records ({records_per_cell} per cell: below the reference's 2500-reads-per-cell "
+                      f"switch), one pass, {mode}"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -172,6 +201,12 @@ def run_reference(a):
     port = port_figure(a)
     ref = time_reference_python(a, a.steps, a.warmup, budget_s=150.0)
     cpu = dict(ref, port=port) if ref else port
+    try:
+        pool = time_reference_pool(a)
+        if pool:
+            cpu["pool"] = pool
+    except Exception as e:                                  # a side figure never fails the arm
+        cpu["pool"] = {"unavailable": f"{type(e).__name__}: {e}"}
     v = cpu["value"]
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
