@@ -89,6 +89,9 @@ __device__ __noinline__ u32 warp_lookback(const uint8_t *slots, size_t sb, u32 p
     return mine;
 }
 
+// Resident CTAs per SM the kernel is compiled for: six of 256 threads at 40 registers. Measured on C2 at 4 / 5 / 6 / 8 per
+// SM: 0.467 / 0.383 / 0.293 / 0.315 ms (fewer: too little latency hiding; eight at 32 registers: the tiles in flight
+// outgrow what the L2 keeps for the copy pass) - profiles/r2_sweep_dedup_ctas_per_sm.log, r2_sweep_occupancy_c2.log.
 #ifndef MGATK_DEDUP_CTAS
 #define MGATK_DEDUP_CTAS (1536 / MGATK_DEDUP_THREADS)
 #endif
